@@ -1,0 +1,89 @@
+"""ctypes binding of ``libgenhancer_b200.so`` (the C ABI declared in ``include/genhancer_b200.h``).
+
+The product path has **no** CPU or PyTorch fallback: if the shared library is missing or a
+call fails, we raise.  The library is built in-tree by ``__graft_entry__.build()``
+(``make -C genhancer_b200/csrc``) so that it travels with the repo snapshot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgenhancer_b200.so")
+
+GH_BF16, GH_F32 = 0, 1
+ACT_NONE, ACT_GELU_TANH, ACT_QUICK_GELU, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3, 4
+
+
+class GhError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_int64), ("a_mn_major", C.c_int32),
+        ("b", C.c_void_p), ("ldb", C.c_int64), ("b_mn_major", C.c_int32),
+        ("d", C.c_void_p), ("ldd", C.c_int64), ("d_dtype", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("alpha", C.c_float),
+        ("bias", C.c_void_p), ("bias_dtype", C.c_int32),
+        ("act", C.c_int32), ("act_grad", C.c_int32),
+        ("aux_in", C.c_void_p), ("ld_aux_in", C.c_int64),
+        ("aux_out", C.c_void_p), ("ld_aux_out", C.c_int64),
+        ("gate", C.c_void_p), ("gate_ld", C.c_int64), ("rows_per_batch", C.c_int32),
+        ("residual", C.c_void_p), ("ld_res", C.c_int64), ("res_dtype", C.c_int32),
+    ]
+
+
+_vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+# Every symbol include/genhancer_b200.h declares, with its argument types.
+# tests/test_abi.py checks that the built library exports exactly these.
+SIGNATURES: dict[str, list] = {
+    "gh_last_error": [],
+    "gh_version": [],
+    "gh_init": [C.c_int],
+    "gh_gemm_bf16": [C.POINTER(GemmArgs), _vp],
+    "gh_fm_interp_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "gh_fm_mse_loss_fwdbwd": [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp],
+}
+
+_lib = None
+_lock = threading.Lock()
+_inited_devices: set[int] = set()
+
+
+def _declare(lib):
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_char_p if name == "gh_last_error" else C.c_int
+
+
+def lib():
+    """Load (once) and return the ctypes handle. Raises if the extension is not built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise GhError(
+                        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU / PyTorch fallback on the product path)")
+                h = C.CDLL(LIB_PATH)
+                _declare(h)
+                _lib = h
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise GhError(f"genhancer_b200 error {status}: {lib().gh_last_error().decode()}")
+
+
+def init(device_index: int) -> None:
+    if device_index not in _inited_devices:
+        check(lib().gh_init(int(device_index)))
+        _inited_devices.add(device_index)

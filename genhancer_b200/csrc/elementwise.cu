@@ -1,0 +1,102 @@
+// genhancer_b200 -- HBM-bound flow-matching kernels (128-bit loads, warp-shuffle reductions).
+#include "common.cuh"
+#include "internal.h"
+
+namespace gh {
+
+// x_t = bf16((1-t) x1 + t x0)        algorithmic bytes / element: 4 + 4 + 2 = 10
+__global__ void __launch_bounds__(256) fm_interp_kernel(const float4* __restrict__ x1, const float4* __restrict__ x0,
+                                                        const float* __restrict__ t, uint2* __restrict__ xt,
+                                                        int64_t n4, int64_t per_sample4) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float tb = __ldg(t + i / per_sample4);
+    const float4 a = __ldcs(x1 + i);
+    const float4 b = __ldcs(x0 + i);
+    const float om = 1.f - tb;
+    // same operation order as the reference expression (1 - t) * x_1 + t * x_0 (no fma contraction)
+    uint2 o;
+    o.x = pack_bf16x2(__fadd_rn(__fmul_rn(om, a.x), __fmul_rn(tb, b.x)),
+                      __fadd_rn(__fmul_rn(om, a.y), __fmul_rn(tb, b.y)));
+    o.y = pack_bf16x2(__fadd_rn(__fmul_rn(om, a.z), __fmul_rn(tb, b.z)),
+                      __fadd_rn(__fmul_rn(om, a.w), __fmul_rn(tb, b.w)));
+    xt[i] = o;
+  }
+}
+
+// loss += sum((pred - (x0 - x1))^2) / numel ; dpred = bf16(scale * 2 (pred - (x0-x1)) / numel)
+// algorithmic bytes / element: 2 + 4 + 4 + 2 = 12
+__global__ void __launch_bounds__(256) fm_mse_kernel(const uint2* __restrict__ pred, const float4* __restrict__ x0,
+                                                     const float4* __restrict__ x1, float* __restrict__ loss,
+                                                     uint2* __restrict__ dpred, float gscale, float inv_numel,
+                                                     int64_t n4) {
+  float acc = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint2 pr = __ldcs(pred + i);
+    const float4 a = __ldcs(x0 + i);
+    const float4 b = __ldcs(x1 + i);
+    const float2 p0 = unpack_bf16x2(pr.x), p1 = unpack_bf16x2(pr.y);
+    const float d0 = p0.x - (a.x - b.x), d1 = p0.y - (a.y - b.y);
+    const float d2 = p1.x - (a.z - b.z), d3 = p1.y - (a.w - b.w);
+    acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    if (dpred) {
+      const float g = 2.f * gscale * inv_numel;
+      uint2 o;
+      o.x = pack_bf16x2(g * d0, g * d1);
+      o.y = pack_bf16x2(g * d2, g * d3);
+      dpred[i] = o;
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss, v * inv_numel);
+  }
+}
+
+static inline int ew_grid(int64_t n_items, int block) {
+  const int64_t want = (n_items + block - 1) / block;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;  // 8 resident CTAs of 256 threads per SM
+  return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace gh
+
+extern "C" int gh_fm_interp_fwd(const float* x1, const float* x0, const float* t, void* xt_bf16, int64_t batch,
+                                int64_t per_sample, void* stream) {
+  using namespace gh;
+  GH_REQUIRE(x1 && x0 && t && xt_bf16, GH_ERR_NULL, "gh_fm_interp_fwd: NULL pointer");
+  GH_REQUIRE(batch >= 0 && per_sample >= 0, GH_ERR_BAD_SHAPE, "gh_fm_interp_fwd: negative size");
+  if (batch == 0 || per_sample == 0) return GH_OK;
+  GH_REQUIRE(per_sample % 4 == 0, GH_ERR_BAD_SHAPE, "gh_fm_interp_fwd: per_sample=%lld must be a multiple of 4",
+             (long long)per_sample);
+  GH_REQUIRE(aligned16(x1) && aligned16(x0) && aligned16(xt_bf16), GH_ERR_ALIGN, "gh_fm_interp_fwd: 16B alignment");
+  const int64_t n4 = batch * per_sample / 4;
+  fm_interp_kernel<<<ew_grid(n4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x1), reinterpret_cast<const float4*>(x0), t,
+      reinterpret_cast<uint2*>(xt_bf16), n4, per_sample / 4);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+extern "C" int gh_fm_mse_loss_fwdbwd(const void* pred_bf16, const float* x0, const float* x1, float* loss_accum,
+                                     void* dpred_bf16, float grad_scale, int64_t numel, void* stream) {
+  using namespace gh;
+  GH_REQUIRE(pred_bf16 && x0 && x1 && loss_accum, GH_ERR_NULL, "gh_fm_mse_loss_fwdbwd: NULL pointer");
+  GH_REQUIRE(numel > 0 && numel % 4 == 0, GH_ERR_BAD_SHAPE,
+             "gh_fm_mse_loss_fwdbwd: numel=%lld must be a positive multiple of 4", (long long)numel);
+  GH_REQUIRE(aligned16(x0) && aligned16(x1) && aligned16(pred_bf16) && (!dpred_bf16 || aligned16(dpred_bf16)),
+             GH_ERR_ALIGN, "gh_fm_mse_loss_fwdbwd: 16B alignment");
+  const int64_t n4 = numel / 4;
+  fm_mse_kernel<<<ew_grid(n4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint2*>(pred_bf16), reinterpret_cast<const float4*>(x0),
+      reinterpret_cast<const float4*>(x1), loss_accum, reinterpret_cast<uint2*>(dpred_bf16), grad_scale,
+      1.0f / static_cast<float>(numel), n4);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}

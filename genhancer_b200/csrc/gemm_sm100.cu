@@ -1,0 +1,138 @@
+// genhancer_b200 -- gh_gemm_bf16: host launcher of the tcgen05 GEMM (see umma_gemm.cuh).
+#include <cstdlib>
+
+#include "internal.h"
+#include "umma_gemm.cuh"
+
+namespace gh {
+
+template <int BN, bool A_MN, bool B_MN>
+static int set_attr() {
+  auto* k = umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM>;
+  GH_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+  return GH_OK;
+}
+
+int gemm_init() {
+#define GH_SET(BN)                                   \
+  if (int e = set_attr<BN, false, false>()) return e; \
+  if (int e = set_attr<BN, false, true>()) return e;  \
+  if (int e = set_attr<BN, true, false>()) return e;  \
+  if (int e = set_attr<BN, true, true>()) return e;
+  GH_SET(256)
+  GH_SET(128)
+  GH_SET(64)
+#undef GH_SET
+  return GH_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM>
+      <<<grid, 256, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+template <int BN>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                          cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, p, s);
+  if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, p, s);
+  if (a_mn && !b_mn) return launch<BN, true, false>(ta, tb, p, s);
+  return launch<BN, true, true>(ta, tb, p, s);
+}
+
+static int pick_bn(int M, int N) {
+  // minimise waves(BN) * BN (MMA time per tile is proportional to BN); ties -> larger tile
+  const int mb = (M + 127) / 128;
+  const int sms = num_sms();
+  int best = 256;
+  long best_cost = -1;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && bn / 2 >= N) continue;  // tile wider than 2x the problem
+    const long tiles = static_cast<long>(mb) * ((N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    const long cost = waves * bn;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace gh
+
+extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
+  using namespace gh;
+  GH_REQUIRE(a != nullptr, GH_ERR_NULL, "gh_gemm_bf16: args is NULL");
+  GH_REQUIRE(a->a && a->b && a->d, GH_ERR_NULL, "gh_gemm_bf16: a/b/d must be non-NULL");
+  GH_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, GH_ERR_BAD_SHAPE, "gh_gemm_bf16: M,N,K must be positive (%d,%d,%d)",
+             a->M, a->N, a->K);
+  GH_REQUIRE(a->N % 8 == 0, GH_ERR_BAD_SHAPE, "gh_gemm_bf16: N=%d must be a multiple of 8", a->N);
+  GH_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0 && a->ldd % 4 == 0, GH_ERR_ALIGN,
+             "gh_gemm_bf16: lda/ldb must be multiples of 8, ldd of 4 (%lld,%lld,%lld)", (long long)a->lda,
+             (long long)a->ldb, (long long)a->ldd);
+  GH_REQUIRE(aligned16(a->a) && aligned16(a->b) && aligned16(a->d), GH_ERR_ALIGN,
+             "gh_gemm_bf16: a/b/d must be 16-byte aligned");
+  GH_REQUIRE(a->lda >= (a->a_mn_major ? a->M : a->K) && a->ldb >= (a->b_mn_major ? a->N : a->K) && a->ldd >= a->N,
+             GH_ERR_BAD_SHAPE, "gh_gemm_bf16: leading dimension smaller than the row length");
+  GH_REQUIRE(a->act >= 0 && a->act <= 4, GH_ERR_UNSUPPORTED, "gh_gemm_bf16: unknown act %d", a->act);
+  GH_REQUIRE(!a->act_grad || a->aux_in, GH_ERR_NULL, "gh_gemm_bf16: act_grad needs aux_in");
+  GH_REQUIRE(!a->gate || a->rows_per_batch > 0, GH_ERR_BAD_SHAPE, "gh_gemm_bf16: gate needs rows_per_batch > 0");
+  GH_REQUIRE((a->d_dtype == GH_BF16 || a->d_dtype == GH_F32), GH_ERR_UNSUPPORTED, "gh_gemm_bf16: bad d_dtype");
+  GH_REQUIRE((!a->aux_in || a->ld_aux_in % 4 == 0) && (!a->aux_out || a->ld_aux_out % 4 == 0) &&
+                 (!a->gate || a->gate_ld % 4 == 0) && (!a->residual || a->ld_res % 4 == 0),
+             GH_ERR_ALIGN, "gh_gemm_bf16: epilogue operand leading dimensions must be multiples of 4");
+
+  const int bn = pick_bn(a->M, a->N);
+  GemmParams p{};
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.num_m_blocks = (a->M + 127) / 128;
+  p.num_n_blocks = (a->N + bn - 1) / bn;
+  p.num_k_blocks = (a->K + 63) / 64;
+  p.a_stage_tx_bytes = 128 * 64 * 2;
+  p.mn_lbo = 8192; p.mn_sbo = 1024; p.mn_kstep = 2048;
+  if (const char* dbg = getenv("GH_DEBUG_MN_DESC")) {  // bring-up aid: "lbo,sbo,kstep" in bytes
+    unsigned l, sb, ks;
+    if (sscanf(dbg, "%u,%u,%u", &l, &sb, &ks) == 3) { p.mn_lbo = l; p.mn_sbo = sb; p.mn_kstep = ks; }
+  }
+  p.ep.d = a->d; p.ep.ldd = a->ldd; p.ep.d_f32 = (a->d_dtype == GH_F32);
+  p.ep.alpha = a->alpha;
+  p.ep.bias = a->bias; p.ep.bias_f32 = (a->bias_dtype == GH_F32);
+  p.ep.act = a->act; p.ep.act_grad = a->act_grad;
+  p.ep.aux_in = static_cast<const __nv_bfloat16*>(a->aux_in); p.ep.ld_aux_in = a->ld_aux_in;
+  p.ep.aux_out = static_cast<__nv_bfloat16*>(a->aux_out); p.ep.ld_aux_out = a->ld_aux_out;
+  p.ep.gate = static_cast<const __nv_bfloat16*>(a->gate); p.ep.gate_ld = a->gate_ld;
+  p.ep.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : 1;
+  p.ep.residual = a->residual; p.ep.ld_res = a->ld_res; p.ep.res_f32 = (a->res_dtype == GH_F32);
+
+  CUtensorMap ta, tb;
+  {
+    // A: K-major -> dims (K, M) box (64, 128); MN-major -> dims (M, K) box (64, 64)
+    uint64_t dims[2], strides[1] = {static_cast<uint64_t>(a->lda) * 2};
+    uint32_t box[2];
+    if (!a->a_mn_major) { dims[0] = a->K; dims[1] = a->M; box[0] = 64; box[1] = 128; }
+    else                { dims[0] = a->M; dims[1] = a->K; box[0] = 64; box[1] = 64; }
+    if (int e = make_tmap_bf16(&ta, a->a, 2, dims, strides, box, nullptr)) return e;
+  }
+  {
+    uint64_t dims[2], strides[1] = {static_cast<uint64_t>(a->ldb) * 2};
+    uint32_t box[2];
+    if (!a->b_mn_major) { dims[0] = a->K; dims[1] = a->N; box[0] = 64; box[1] = static_cast<uint32_t>(bn); }
+    else                { dims[0] = a->N; dims[1] = a->K; box[0] = 64; box[1] = 64; }
+    if (int e = make_tmap_bf16(&tb, a->b, 2, dims, strides, box, nullptr)) return e;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
+  switch (bn) {
+    case 256: return dispatch_major<256>(amn, bmn, ta, tb, p, s);
+    case 128: return dispatch_major<128>(amn, bmn, ta, tb, p, s);
+    default: return dispatch_major<64>(amn, bmn, ta, tb, p, s);
+  }
+}

@@ -1,0 +1,342 @@
+// genhancer_b200 -- persistent, warp-specialised tcgen05 GEMM core for sm_100a.
+//
+//   warp 0      : TMA producer   (one lane issues cp.async.bulk.tensor into a smem ring)
+//   warp 1      : MMA issuer     (one lane issues tcgen05.mma, accumulators in TMEM)
+//   warp 2      : TMEM allocator / deallocator
+//   warps 4..7  : epilogue       (tcgen05.ld -> fp32 smem transpose -> fused math ->
+//                                 coalesced 8/16-byte global stores)
+//
+// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue,
+// two accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1),
+// and a static persistent tile schedule (grid = #SMs, M-grouped rasterisation for L2 reuse).
+//
+// The same kernel body serves
+//   MODE_GEMM : D[M,N] = A * B^T with A/B either K-major or MN-major (fwd, dgrad, wgrad)
+//   MODE_CONV : implicit-GEMM convolution over an NHWC activation; the A tile of each
+//               (tap, channel-chunk) K-step is a shifted 4-D TMA box whose out-of-bounds
+//               part is zero-filled by the hardware (padding costs nothing).
+#pragma once
+#include "common.cuh"
+
+namespace gh {
+
+enum { MODE_GEMM = 0, MODE_CONV = 1 };
+
+struct EpilogueParams {
+  void* d;
+  int64_t ldd;
+  int d_f32;
+  float alpha;
+  const void* bias;
+  int bias_f32;
+  int act;
+  int act_grad;
+  const __nv_bfloat16* aux_in;
+  int64_t ld_aux_in;
+  __nv_bfloat16* aux_out;
+  int64_t ld_aux_out;
+  const __nv_bfloat16* gate;
+  int64_t gate_ld;
+  int rows_per_batch;
+  const void* residual;
+  int64_t ld_res;
+  int res_f32;
+};
+
+struct ConvGeom {  // MODE_CONV only
+  int B, Ho, Wo;   // output extent
+  int TW, TH;      // output patch per M tile (TW*TH <= 128)
+  int tiles_w, tiles_h;
+  int KW;          // filter width (taps = KH*KW)
+  int cin_chunks;  // Cin / 64
+  int stride, pad; // input coord = out*stride + tap - pad
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  uint32_t a_stage_tx_bytes;  // bytes TMA deposits for the A tile of one stage
+  uint32_t mn_lbo, mn_sbo, mn_kstep;  // MN-major descriptor geometry (bytes); see common.cuh
+  EpilogueParams ep;
+  ConvGeom cv;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_LD = 36;  // floats per staged row (32 + 4 pad, keeps 16B alignment)
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + align slack
+};
+
+__device__ __forceinline__ void decode_tile(int tile, int num_m_blocks, int num_n_blocks, int& m_blk, int& n_blk) {
+  constexpr int G = 8;  // M-blocks per raster group
+  const int tiles_per_group = G * num_n_blocks;
+  const int group = tile / tiles_per_group;
+  const int first_m = group * G;
+  const int gsize = min(G, num_m_blocks - first_m);
+  const int in_group = tile - group * tiles_per_group;
+  m_blk = first_m + in_group % gsize;
+  n_blk = in_group / gsize;
+}
+
+// 4 consecutive outputs of one row: fused epilogue + store
+__device__ __forceinline__ void epilogue_store4(const EpilogueParams& ep, float4 acc, int64_t out_row, int gm,
+                                                int gn) {
+  float v[4] = {acc.x * ep.alpha, acc.y * ep.alpha, acc.z * ep.alpha, acc.w * ep.alpha};
+  if (ep.bias) {
+    if (ep.bias_f32) {
+      const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(ep.bias) + gn);
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    } else {
+      const uint2 b = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(ep.bias) + gn);
+      const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b1.x; v[3] += b1.y;
+    }
+  }
+  if (ep.aux_out) {
+    uint2 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(ep.aux_out + out_row * ep.ld_aux_out + gn) = o;
+  }
+  if (ep.act_grad) {
+    const uint2 x = *reinterpret_cast<const uint2*>(ep.aux_in + out_row * ep.ld_aux_in + gn);
+    const float2 x0 = unpack_bf16x2(x.x), x1 = unpack_bf16x2(x.y);
+    v[0] *= act_bwd(ep.act, x0.x); v[1] *= act_bwd(ep.act, x0.y);
+    v[2] *= act_bwd(ep.act, x1.x); v[3] *= act_bwd(ep.act, x1.y);
+  } else if (ep.act != ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = act_fwd(ep.act, v[i]);
+  }
+  if (ep.gate) {
+    const int b = gm / ep.rows_per_batch;
+    const uint2 g = *reinterpret_cast<const uint2*>(ep.gate + static_cast<int64_t>(b) * ep.gate_ld + gn);
+    const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
+    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g1.x; v[3] *= g1.y;
+  }
+  if (ep.residual) {
+    if (ep.res_f32) {
+      const float4 r = *reinterpret_cast<const float4*>(static_cast<const float*>(ep.residual) +
+                                                        out_row * ep.ld_res + gn);
+      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+    } else {
+      const uint2 r = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(ep.residual) +
+                                                      out_row * ep.ld_res + gn);
+      const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y);
+      v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+    }
+  }
+  if (ep.d_f32) {
+    *reinterpret_cast<float4*>(static_cast<float*>(ep.d) + out_row * ep.ldd + gn) =
+        make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    uint2 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(ep.d) + out_row * ep.ldd + gn) = o;
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, int MODE>
+__global__ void __launch_bounds__(256, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  static_assert(!(MODE == MODE_CONV && A_MN), "conv A operand is K-major (NHWC channels)");
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment of the (shared-window) address
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint8_t* stage_base = smem;
+  float* epi_buf = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int nkb = p.num_k_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar[0], 1);
+    mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 4);  // one arrive per epilogue warp
+    mbar_init(&tempty_bar[1], 4);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = p.a_stage_tx_bytes + Cfg::B_BYTES;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      decode_tile(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+      int cb = 0, ch0 = 0, cw0 = 0;
+      if (MODE == MODE_CONV) {
+        const int tiles_per_img = p.cv.tiles_w * p.cv.tiles_h;
+        cb = m_blk / tiles_per_img;
+        const int r = m_blk - cb * tiles_per_img;
+        ch0 = (r / p.cv.tiles_w) * p.cv.TH;
+        cw0 = (r % p.cv.tiles_w) * p.cv.TW;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (lane == 0) {
+          uint8_t* sA = stage_base + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          if (MODE == MODE_CONV) {
+            const int tap = kb / p.cv.cin_chunks;
+            const int cc = kb - tap * p.cv.cin_chunks;
+            const int kh = tap / p.cv.KW, kw = tap - kh * p.cv.KW;
+            tma_load_4d(sA, &tmap_a, &full_bar[stage], cc * 64, cw0 * p.cv.stride + kw - p.cv.pad,
+                        ch0 * p.cv.stride + kh - p.cv.pad, cb);
+          } else if (!A_MN) {
+            tma_load_2d(sA, &tmap_a, &full_bar[stage], kb * 64, m_blk * 128);
+          } else {
+            tma_load_2d(sA, &tmap_a, &full_bar[stage], m_blk * 128, kb * 64);
+            tma_load_2d(sA + 8192, &tmap_a, &full_bar[stage], m_blk * 128 + 64, kb * 64);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB, &tmap_b, &full_bar[stage], kb * 64, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sB + i * 8192, &tmap_b, &full_bar[stage], n_blk * BN + i * 64, kb * 64);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, A_MN, B_MN);
+    const uint64_t a_desc_base = A_MN ? umma_desc_base(p.mn_lbo, p.mn_sbo) : umma_desc_base(16u, 1024u);
+    const uint64_t b_desc_base = B_MN ? umma_desc_base(p.mn_lbo, p.mn_sbo) : umma_desc_base(16u, 1024u);
+    const uint32_t A_KSTEP = A_MN ? p.mn_kstep : 32u;
+    const uint32_t B_KSTEP = B_MN ? p.mn_kstep : 32u;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+          const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_ss(d_tmem, umma_desc_at(a_desc_base, sA + k * A_KSTEP), umma_desc_at(b_desc_base, sB + k * B_KSTEP),
+                    idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);              // smem slot free once these MMAs retire
+          if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quadrant
+    float* st = epi_buf + ew * (32 * Cfg::EPI_LD);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      decode_tile(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n_blk * BN + c * 32 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(st + lane * Cfg::EPI_LD);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int sub_row = lane >> 3;
+        const int col4 = (lane & 7) * 4;
+        const int gn = n_blk * BN + c * 32 + col4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + sub_row;       // row within this warp's 32
+          const int tr = ew * 32 + row;            // row within the 128-row tile
+          const float4 a = *reinterpret_cast<const float4*>(st + row * Cfg::EPI_LD + col4);
+          bool ok = gn < p.N;
+          int64_t out_row;
+          int gm;
+          if (MODE == MODE_CONV) {
+            const int tiles_per_img = p.cv.tiles_w * p.cv.tiles_h;
+            const int cb = m_blk / tiles_per_img;
+            const int rr = m_blk - cb * tiles_per_img;
+            const int oh = (rr / p.cv.tiles_w) * p.cv.TH + tr / p.cv.TW;
+            const int ow = (rr % p.cv.tiles_w) * p.cv.TW + tr % p.cv.TW;
+            ok = ok && (tr < p.cv.TW * p.cv.TH) && (oh < p.cv.Ho) && (ow < p.cv.Wo);
+            out_row = (static_cast<int64_t>(cb) * p.cv.Ho + oh) * p.cv.Wo + ow;
+            gm = static_cast<int>(out_row);
+          } else {
+            gm = m_blk * 128 + tr;
+            ok = ok && (gm < p.M);
+            out_row = gm;
+          }
+          if (ok) epilogue_store4(p.ep, a, out_row, gm, gn);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+}  // namespace gh

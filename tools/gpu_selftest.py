@@ -1,0 +1,198 @@
+"""Bring-up self-test for the sm_100a kernels (run on the GPU box through gpurun).
+
+Prints one line per case so a failure localises itself; writes the same to
+gpurun_out/selftest.log.  Not a pytest file: tests/ holds the graded parity tests.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+
+from genhancer_b200 import kernels as K
+
+os.makedirs("gpurun_out", exist_ok=True)
+LOG = open("gpurun_out/selftest.log", "a")
+
+
+def say(*a):
+    s = " ".join(str(x) for x in a)
+    print(s, flush=True)
+    LOG.write(s + "\n")
+    LOG.flush()
+
+
+def relerr(got, ref):
+    got, ref = got.float(), ref.float()
+    return ((got - ref).norm() / (ref.norm() + 1e-12)).item()
+
+
+def gemm_case(M, N, Kd, a_mn=False, b_mn=False, pad=0, seed=0, **epi):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = "cuda"
+    A = torch.randn(M, Kd, device=dev, generator=g).to(torch.bfloat16)
+    B = torch.randn(N, Kd, device=dev, generator=g).to(torch.bfloat16)
+    ref = A.float() @ B.float().t()
+    a_in = A.t().contiguous() if a_mn else A
+    b_in = B.t().contiguous() if b_mn else B
+    if pad:
+        def padded(t):
+            buf = torch.zeros(t.shape[0], t.shape[1] + pad, device=dev, dtype=t.dtype)
+            buf[:, : t.shape[1]] = t
+            return buf[:, : t.shape[1]]
+        a_in, b_in = padded(a_in), padded(b_in)
+    kw = {}
+    if epi.get("bias"):
+        bias = torch.randn(N, device=dev, generator=g).to(torch.bfloat16)
+        kw["bias"] = bias
+        ref = ref + bias.float()
+    if epi.get("aux_out"):
+        kw["aux_out"] = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        aux_ref = ref.clone()
+    act = epi.get("act", 0)
+    if epi.get("act_grad"):
+        aux_in = torch.randn(M, N, device=dev, generator=g).to(torch.bfloat16)
+        kw["aux_in"] = aux_in
+        kw["act_grad"] = True
+        x = aux_in.float().requires_grad_(True)
+        y = {1: lambda v: torch.nn.functional.gelu(v, approximate="tanh"), 2: lambda v: v * torch.sigmoid(1.702 * v),
+             3: torch.nn.functional.gelu, 4: torch.nn.functional.silu}[act](x)
+        (dact,) = torch.autograd.grad(y.sum(), x)
+        ref = ref * dact
+    elif act:
+        ref = {1: lambda v: torch.nn.functional.gelu(v, approximate="tanh"), 2: lambda v: v * torch.sigmoid(1.702 * v),
+               3: torch.nn.functional.gelu, 4: torch.nn.functional.silu}[act](ref)
+    if epi.get("gate"):
+        rpb = epi["gate"]
+        nb = (M + rpb - 1) // rpb
+        gate = torch.randn(nb, N, device=dev, generator=g).to(torch.bfloat16)
+        kw["gate"] = gate
+        kw["rows_per_batch"] = rpb
+        ref = ref * gate.float().repeat_interleave(rpb, dim=0)[:M]
+    if epi.get("residual"):
+        res = torch.randn(M, N, device=dev, generator=g).to(torch.bfloat16)
+        kw["residual"] = res
+        ref = ref + res.float()
+    out_dtype = torch.float32 if epi.get("f32") else torch.bfloat16
+    out = K.gemm(a_in, b_in, a_mn=a_mn, b_mn=b_mn, act=act, out_dtype=out_dtype, **kw)
+    torch.cuda.synchronize()
+    e = relerr(out, ref)
+    tag = f"gemm M={M} N={N} K={Kd} a_mn={int(a_mn)} b_mn={int(b_mn)} pad={pad} epi={epi}"
+    ok = e < 1e-2
+    if epi.get("aux_out"):
+        e2 = relerr(kw["aux_out"], aux_ref)
+        ok = ok and e2 < 1e-2
+        tag += f" aux_err={e2:.2e}"
+    say(("PASS" if ok else "FAIL"), tag, f"relerr={e:.3e}")
+    return ok
+
+
+def time_gemm(M, N, Kd, a_mn=False, b_mn=False, iters=20):
+    dev = "cuda"
+    A = torch.randn((Kd, M) if a_mn else (M, Kd), device=dev).to(torch.bfloat16)
+    B = torch.randn((Kd, N) if b_mn else (N, Kd), device=dev).to(torch.bfloat16)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        K.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        K.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 2.0 * M * N * Kd / ms / 1e9
+    # library yardstick (cuBLAS through torch) on the same shape, for context only
+    Ar = A.t() if a_mn else A
+    Br = B.t() if b_mn else B
+    for _ in range(3):
+        torch.matmul(Ar, Br.t())
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(Ar, Br.t())
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / iters
+    say(f"TIME gemm M={M} N={N} K={Kd} a_mn={int(a_mn)} b_mn={int(b_mn)}: {ms:.3f} ms {tf:.0f} TFLOP/s | cuBLAS {ms2:.3f} ms "
+        f"{2.0 * M * N * Kd / ms2 / 1e9:.0f} TFLOP/s")
+
+
+def fm_cases():
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(1)
+    B, L = 4, 441
+    x1 = torch.randn(B, L, 64, device=dev, generator=g)
+    x0 = torch.randn(B, L, 64, device=dev, generator=g)
+    t = torch.sigmoid(torch.randn(B, device=dev, generator=g))
+    xt = K.fm_interp(x1, x0, t)
+    ref = ((1 - t[:, None, None]) * x1 + t[:, None, None] * x0).to(torch.bfloat16)
+    say("PASS" if torch.equal(xt, ref) else "FAIL", "fm_interp bit-exact:", torch.equal(xt, ref),
+        "maxdiff", (xt.float() - ref.float()).abs().max().item())
+    pred = torch.randn(B, L, 64, device=dev, generator=g).to(torch.bfloat16)
+    loss, dpred = K.fm_mse_loss(pred, x0, x1)
+    pr = pred.float().requires_grad_(True)
+    lref = torch.nn.functional.mse_loss(pr, (x0 - x1))
+    lref.backward()
+    e1 = abs(loss.item() - lref.item()) / abs(lref.item())
+    e2 = relerr(dpred, pr.grad)
+    say("PASS" if (e1 < 1e-5 and e2 < 5e-3) else "FAIL", f"fm_mse loss relerr={e1:.2e} dpred relerr={e2:.2e}")
+
+
+def main():
+    say("== genhancer_b200 selftest", time.strftime("%H:%M:%S"), torch.cuda.get_device_name(0))
+    which = sys.argv[1:] or ["fm", "gemm", "mn", "epi", "time"]
+    if "fm" in which:
+        fm_cases()
+    if "gemm" in which:
+        gemm_case(128, 64, 64)
+        gemm_case(128, 256, 64)
+        gemm_case(128, 256, 256)
+        gemm_case(256, 512, 512)
+        gemm_case(200, 328, 588, pad=4)
+        gemm_case(32, 3072, 768)
+        gemm_case(1000, 64, 3072)
+        gemm_case(3000, 3072, 1024)
+    if "mn" in which:
+        ok_b = gemm_case(128, 256, 256, b_mn=True)
+        ok_a = gemm_case(128, 256, 256, a_mn=True)
+        gemm_case(128, 64, 128, a_mn=True, b_mn=True)
+        gemm_case(304, 520, 328, a_mn=True, b_mn=True)
+        gemm_case(1000, 3072, 777 + 7, b_mn=True)
+        if not (ok_a and ok_b):
+            for cand in ["1024,8192,2048", "8192,1024,4096", "128,1024,2048", "1024,128,2048"]:
+                os.environ["GH_DEBUG_MN_DESC"] = cand
+                say("-- retry MN descriptors with", cand)
+                gemm_case(128, 256, 256, b_mn=True)
+                gemm_case(128, 256, 256, a_mn=True)
+            del os.environ["GH_DEBUG_MN_DESC"]
+    if "epi" in which:
+        gemm_case(300, 512, 256, bias=True)
+        gemm_case(300, 512, 256, bias=True, act=1)
+        gemm_case(300, 512, 256, bias=True, act=2)
+        gemm_case(300, 512, 256, bias=True, act=3)
+        gemm_case(300, 512, 256, bias=True, act=4)
+        gemm_case(300, 512, 256, bias=True, act=1, aux_out=True)
+        gemm_case(300, 512, 256, act=1, act_grad=True)
+        gemm_case(300, 512, 256, bias=True, gate=100, residual=True)
+        gemm_case(300, 512, 256, bias=True, f32=True)
+    if "time" in which:
+        time_gemm(4096, 4096, 4096)
+        time_gemm(8192, 8192, 8192)
+        time_gemm(14112, 9216, 3072)
+        time_gemm(14112, 3072, 12288)
+        time_gemm(14112, 12288, 3072)
+        time_gemm(14112, 3072, 9216, b_mn=True)
+        time_gemm(9216, 3072, 14112, a_mn=True, b_mn=True)
+        time_gemm(18464, 3072, 1024)
+        time_gemm(32, 18432, 3072)
+    say("== done")
+
+
+if __name__ == "__main__":
+    main()
