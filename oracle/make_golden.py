@@ -1,0 +1,365 @@
+"""Pin the oracle against the REAL reference and mint the golden fixtures (build container only).
+
+    python oracle/make_golden.py [--full]
+
+Imports /root/reference/Continuous (read-only) with the two shims from SURVEY.md section 8c
+(a stub for the unused `import clip`; HF `from_pretrained` replaced by random-init of the same
+architecture), loads deterministic synthetic weights (oracle.synth_state_dict) into the
+reference's own modules, runs the reference forward/backward, asserts that
+oracle/genhancer_oracle.py reproduces it, and writes small fixtures to tests/golden/*.pt.
+Weights are NOT stored: a fixture holds (config, key->shape, seed) and the tests regenerate
+the identical tensors.  /root/reference does not exist on the GPU box, so nothing at test or
+bench time imports it.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import types
+
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+REF = "/root/reference/Continuous"
+sys.path.insert(0, REF)
+sys.modules.setdefault("clip", types.ModuleType("clip"))  # CLIP_bank.py:1 imports it, never uses it
+
+from einops import rearrange  # noqa: E402
+from transformers import CLIPConfig, CLIPModel, SiglipConfig, SiglipModel  # noqa: E402
+
+import clip_models.CLIP_bank as bank  # noqa: E402  (reference)
+from clip_models.sampling import prepare_clip  # noqa: E402  (reference)
+from src.flux.model import Flux, FluxParams  # noqa: E402  (reference)
+from src.flux.modules.autoencoder import AutoEncoder, AutoEncoderParams  # noqa: E402  (reference)
+
+from oracle import genhancer_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+OPENAI_MEAN = (0.48145466, 0.4578275, 0.40821073)
+OPENAI_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def close(a, b, tol, what):
+    err = (a.double() - b.double()).abs().max().item()
+    ref = b.double().abs().max().item()
+    ok = err <= tol * max(ref, 1e-6)
+    print(f"  {'ok ' if ok else 'BAD'} {what}: max|d|={err:.3e} (ref max {ref:.3e})")
+    assert ok, what
+    return err
+
+
+def ref_clip_model(tc: O.TowerCfg):
+    if tc.kind == "clip":
+        vis = dict(hidden_size=tc.hidden, intermediate_size=tc.mlp, num_hidden_layers=tc.layers,
+                   num_attention_heads=tc.heads, image_size=tc.image_size, patch_size=tc.patch,
+                   hidden_act="quick_gelu", projection_dim=tc.proj_dim, layer_norm_eps=tc.eps)
+        txt = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2,
+                   projection_dim=tc.proj_dim, vocab_size=100, max_position_embeddings=8)
+        return CLIPModel(CLIPConfig(text_config=txt, vision_config=vis, projection_dim=tc.proj_dim))
+    vis = dict(hidden_size=tc.hidden, intermediate_size=tc.mlp, num_hidden_layers=tc.layers,
+               num_attention_heads=tc.heads, image_size=tc.image_size, patch_size=tc.patch,
+               hidden_act="gelu_pytorch_tanh", layer_norm_eps=tc.eps)
+    txt = dict(hidden_size=tc.hidden, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2,
+               vocab_size=100, max_position_embeddings=8)
+    return SiglipModel(SiglipConfig(text_config=txt, vision_config=vis))
+
+
+def load_subset(module, sd):
+    missing, unexpected = module.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    return missing
+
+
+def build_reference_wrapper(tc: O.TowerCfg, clip_dim: int, t5_dim: int, seed: int):
+    """The reference's own OpenAICLIP / SigLIP wrapper around a random-init HF model, then our synthetic weights."""
+    model = ref_clip_model(tc)
+
+    class Cfg:
+        clip_image_size = 224 if tc.kind == "clip" else 384  # only selects which from_pretrained path is taken
+        pass
+    Cfg.clip_dim, Cfg.t5_dim = clip_dim, t5_dim
+    shim = type("Shim", (), {"from_pretrained": staticmethod(lambda *a, **k: model)})
+    if tc.kind == "clip":
+        bank.CLIPModel = shim
+        wrap = bank.OpenAICLIP(Cfg())
+    else:
+        bank.SiglipModel = shim
+        wrap = bank.SigLIP(Cfg())
+    feat = tc.feat_dim
+    # reference hard-codes LayerNorm(768)/(1152); rebuild the projectors for reduced test sizes
+    if wrap.project_clip[0].normalized_shape[0] != feat:
+        import torch.nn as nn
+        wrap.project_clip = nn.Sequential(nn.LayerNorm(feat), nn.Linear(feat, clip_dim), nn.GELU(), nn.Linear(clip_dim, clip_dim))
+        wrap.project_t5 = nn.Sequential(nn.LayerNorm(feat), nn.Linear(feat, t5_dim), nn.GELU(), nn.Linear(t5_dim, t5_dim))
+    ks_t = O.tower_key_shapes(tc)
+    sd_t = O.synth_state_dict(ks_t, seed)
+    load_subset(wrap.model, sd_t)
+    ks_w = {**O.projector_key_shapes("project_clip", feat, clip_dim), **O.projector_key_shapes("project_t5", feat, t5_dim)}
+    sd_w = O.synth_state_dict(ks_w, seed + 1)
+    load_subset(wrap, sd_w)
+    wrap.float()
+    return wrap, sd_t, sd_w, ks_t, ks_w
+
+
+def golden_tower(name: str, tc: O.TowerCfg, clip_dim=48, t5_dim=96, B=2, seed=11):
+    print(f"[tower:{name}]")
+    wrap, sd_t, sd_w, ks_t, ks_w = build_reference_wrapper(tc, clip_dim, t5_dim, seed)
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(B, 3, tc.image_size, tc.image_size, generator=g)
+    mean = torch.tensor(OPENAI_MEAN if tc.kind == "clip" else (0.5,) * 3).view(1, 3, 1, 1)
+    std = torch.tensor(OPENAI_STD if tc.kind == "clip" else (0.5,) * 3).view(1, 3, 1, 1)
+    x = (img - mean) / std
+    for p_ in wrap.parameters():
+        p_.requires_grad_(False)
+    for n_, p_ in wrap.named_parameters():
+        if "project_clip" in n_ or "project_t5" in n_:
+            p_.requires_grad_(True)
+    out = wrap.model.vision_model(x, output_hidden_states=True)
+    cls, pc, pt5 = wrap(x)
+    (pc.square().mean() + pt5.square().mean()).backward()
+    # oracle on the same weights
+    sdw = {k: v.clone().requires_grad_(True) for k, v in sd_w.items()}
+    lhs, pooled = O.tower_forward(sd_t, x, tc)
+    ocls, opc, opt5 = O.clip_wrapper_forward(sd_t, sdw, x, tc)
+    (opc.square().mean() + opt5.square().mean()).backward()
+    close(lhs, out.last_hidden_state, 2e-5, "last_hidden_state")
+    close(pooled, out.pooler_output, 2e-5, "pooler_output")
+    close(ocls, cls, 2e-5, "class_token")
+    close(opc, pc, 2e-5, "projection_clip")
+    close(opt5, pt5, 2e-5, "projection_t5")
+    close(sdw["project_t5.1.weight"].grad, wrap.project_t5[1].weight.grad, 1e-4, "grad project_t5.1.weight")
+    fx = dict(kind="tower", cfg=tc.__dict__, clip_dim=clip_dim, t5_dim=t5_dim, seed=seed, key_shapes_tower=ks_t,
+              key_shapes_wrap=ks_w, img=img, last_hidden_state=out.last_hidden_state.detach(),
+              pooler_output=out.pooler_output.detach(), class_token=cls.detach(), projection_clip=pc.detach(),
+              projection_t5=pt5.detach(), grad_project_t5_1_weight=wrap.project_t5[1].weight.grad.clone(),
+              grad_project_clip_3_bias=wrap.project_clip[3].bias.grad.clone())
+    torch.save(fx, os.path.join(GOLD, f"tower_{name}.pt"))
+
+
+def golden_ae(seed=21):
+    print("[ae encoder]")
+    ac = O.AECfg(ch=64)
+    ae = AutoEncoder(AutoEncoderParams(resolution=256, in_channels=3, ch=ac.ch, out_ch=3, ch_mult=list(ac.ch_mult),
+                                       num_res_blocks=2, z_channels=16, scale_factor=ac.scale_factor,
+                                       shift_factor=ac.shift_factor))
+    ks = O.ae_encoder_key_shapes(ac)
+    sd = O.synth_state_dict(ks, seed)
+    missing, unexpected = ae.encoder.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(2, 3, 48, 48, generator=g)
+    x = (img - 0.5) / 0.5
+    with torch.no_grad():
+        mom = ae.encoder(x)
+        torch.manual_seed(seed)
+        z = ae.encode(x)  # consumes randn_like(mean)
+        torch.manual_seed(seed)
+        noise = torch.randn_like(mom[:, :16])
+        omom = O.ae_encoder_forward(sd, x, ac)
+        oz = O.ae_encode(sd, x, ac, noise)
+    close(omom, mom, 2e-5, "moments")
+    close(oz, z, 2e-5, "z (given the same noise)")
+    torch.save(dict(kind="ae", cfg=ac.__dict__, seed=seed, key_shapes=ks, img=img, noise=noise, moments=mom, z=z),
+               os.path.join(GOLD, "ae_small.pt"))
+
+
+def ref_flux(fc: O.FluxCfg):
+    return Flux(FluxParams(in_channels=fc.in_channels, vec_in_dim=fc.vec_in_dim, context_in_dim=fc.context_in_dim,
+                           hidden_size=fc.hidden_size, mlp_ratio=fc.mlp_ratio, num_heads=fc.num_heads, depth=fc.depth,
+                           depth_single_blocks=fc.depth_single_blocks, axes_dim=list(fc.axes_dim), theta=fc.theta,
+                           qkv_bias=fc.qkv_bias, guidance_embed=fc.guidance_embed))
+
+
+def golden_flux(name: str, n_txt: int, seed=31, video_ids=False):
+    print(f"[flux:{name}]")
+    fc = O.FluxCfg(vec_in_dim=32, context_in_dim=48, hidden_size=256, num_heads=2, depth=1, depth_single_blocks=2)
+    dit = ref_flux(fc)
+    ks = O.flux_key_shapes(fc)
+    assert {k: tuple(v.shape) for k, v in dit.state_dict().items()} == {k: tuple(v) for k, v in ks.items()}
+    sd = O.synth_state_dict(ks, seed)
+    dit.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed)
+    B, h2, w2 = 2, 3, 5
+    L = h2 * w2
+    img = torch.randn(B, L, 64, generator=g)
+    txt = torch.randn(B, n_txt, 48, generator=g)
+    y = torch.randn(B, 32, generator=g)
+    t = torch.sigmoid(torch.randn(B, generator=g))
+    guidance = torch.full((B,), 4.0)
+    img_ids = O.make_img_ids(B, h2, w2, 1.0 if video_ids else 0.0)
+    if video_ids:  # two conditioning frames at t=0 and t=2 (R/train_OpenAICLIP_video_stage1.py:405-420)
+        gh = int(round((n_txt // 2) ** 0.5))
+        txt_ids = torch.cat([O.create_spatio_temporal_ids(B, 0, gh, gh), O.create_spatio_temporal_ids(B, 2, gh, gh)], 1)
+    else:
+        txt_ids = torch.zeros(B, n_txt, 3)
+    target = torch.randn(B, L, 64, generator=g)
+    img_r, txt_r, y_r = (v.clone().requires_grad_(True) for v in (img, txt, y))
+    pred = dit(img=img_r, img_ids=img_ids, txt=txt_r, txt_ids=txt_ids, timesteps=t, y=y_r, guidance=guidance)
+    loss = F.mse_loss(pred.float(), target)
+    loss.backward()
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    img_o, txt_o, y_o = (v.clone().requires_grad_(True) for v in (img, txt, y))
+    opred = O.flux_forward(sdo, fc, img_o, img_ids, txt_o, txt_ids, t, y_o, guidance)
+    oloss = F.mse_loss(opred.float(), target)
+    oloss.backward()
+    close(opred, pred, 2e-5, "pred")
+    close(oloss, loss, 1e-6, "loss")
+    close(img_o.grad, img_r.grad, 1e-4, "d img")
+    close(txt_o.grad, txt_r.grad, 1e-4, "d txt")
+    close(y_o.grad, y_r.grad, 1e-4, "d y")
+    grads = {}
+    for k in ("img_in.weight", "double_blocks.0.img_attn.qkv.weight", "double_blocks.0.txt_mod.lin.bias",
+              "double_blocks.0.img_attn.norm.query_norm.scale", "single_blocks.1.linear2.weight",
+              "single_blocks.0.norm.key_norm.scale", "final_layer.adaLN_modulation.1.weight", "time_in.in_layer.weight"):
+        gr = dict(dit.named_parameters())[k].grad
+        close(sdo[k].grad, gr, 2e-4, f"d {k}")
+        grads[k] = gr.clone()
+    # bf16 run of the reference (what the training scripts actually execute: weight_dtype casts)
+    dit_bf = ref_flux(fc)
+    dit_bf.load_state_dict(sd, strict=True)
+    dit_bf = dit_bf.to(torch.bfloat16)
+    bf = torch.bfloat16
+    with torch.no_grad():
+        pred_bf = dit_bf(img=img.to(bf), img_ids=img_ids.to(bf), txt=txt.to(bf), txt_ids=txt_ids.to(bf),
+                         timesteps=t.to(bf), y=y.to(bf), guidance=guidance.to(bf))
+    torch.save(dict(kind="flux", cfg=fc.__dict__, seed=seed, key_shapes=ks, img=img, txt=txt, y=y, t=t, guidance=guidance,
+                    img_ids=img_ids, txt_ids=txt_ids, target=target, pred=pred.detach(), loss=loss.detach(),
+                    d_img=img_r.grad, d_txt=txt_r.grad, d_y=y_r.grad, grads=grads, pred_bf16=pred_bf),
+               os.path.join(GOLD, f"flux_{name}.pt"))
+
+
+def golden_step_small(seed=41):
+    """A whole image-mode stage-1 micro-step with every component at reduced size, through the reference's
+    own prepare_clip / Flux / AutoEncoder / OpenAICLIP code, vs oracle.stage1_image_step."""
+    print("[stage-1 image step, reduced sizes]")
+    tc = O.TowerCfg("clip", 128, 2, 2, 512, 112, 14, 64, 1e-5, "quick_gelu")
+    fc = O.FluxCfg(vec_in_dim=32, context_in_dim=48, hidden_size=256, num_heads=2, depth=1, depth_single_blocks=1)
+    ac = O.AECfg(ch=64)
+    wrap, sd_t, sd_w, ks_t, ks_w = build_reference_wrapper(tc, 32, 48, seed)
+    dit = ref_flux(fc)
+    ks_d = O.flux_key_shapes(fc)
+    sd_d = O.synth_state_dict(ks_d, seed + 2)
+    dit.load_state_dict(sd_d, strict=True)
+    ae = AutoEncoder(AutoEncoderParams(resolution=256, in_channels=3, ch=ac.ch, out_ch=3, ch_mult=list(ac.ch_mult),
+                                       num_res_blocks=2, z_channels=16, scale_factor=ac.scale_factor,
+                                       shift_factor=ac.shift_factor))
+    ks_a = O.ae_encoder_key_shapes(ac)
+    sd_a = O.synth_state_dict(ks_a, seed + 3)
+    ae.encoder.load_state_dict(sd_a, strict=True)
+    for n_, p_ in wrap.named_parameters():
+        p_.requires_grad_("project_clip" in n_ or "project_t5" in n_)
+    ae.requires_grad_(False)
+    g = torch.Generator().manual_seed(seed)
+    B = 2
+    img = torch.rand(B, 3, 112, 112, generator=g)
+    mean = torch.tensor(OPENAI_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(OPENAI_STD).view(1, 3, 1, 1)
+    # --- the reference step body (train_SigLIP_stage1.py:242-263), RNG draws in its order ---
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        x_1 = ae.encode(((img - 0.5) / 0.5).float())                     # draw #1
+    inp = prepare_clip(clip=wrap, original_img=(img - mean) / std, img=x_1)
+    x_1p = rearrange(x_1, "b c (h ph) (w pw) -> b (h w) (c ph pw)", ph=2, pw=2)
+    t = torch.sigmoid(torch.randn((B,)) * 1.0)                            # draw #2
+    x_0 = torch.randn_like(x_1p)                                          # draw #3
+    x_t = (1 - t[:, None, None]) * x_1p + t[:, None, None] * x_0
+    pred = dit(img=x_t, img_ids=inp["img_ids"], txt=inp["txt"], txt_ids=inp["txt_ids"], y=inp["vec"], timesteps=t,
+               guidance=torch.full((B,), 4.0))
+    loss = F.mse_loss(pred.float(), (x_0 - x_1p).float(), reduction="mean")
+    loss.backward()
+    # --- oracle with the same three draws ---
+    torch.manual_seed(seed)
+    noise = torch.randn(B, 16, 14, 14)
+    t_o = torch.sigmoid(torch.randn((B,)) * 1.0)
+    x0_o = torch.randn_like(x_1p)
+    assert torch.equal(t_o, t) and torch.equal(x0_o, x_0)
+    sdw = {k: v.clone().requires_grad_(True) for k, v in sd_w.items()}
+    sdd = {k: v.clone().requires_grad_(True) for k, v in sd_d.items()}
+    out = O.stage1_image_step(sd_t, sdw, sdd, sd_a, img, tc, fc, ac, OPENAI_MEAN, OPENAI_STD, noise, t, x_0)
+    out.loss.backward()
+    close(out.x_1, x_1p, 2e-5, "x_1 (patchified latent)")
+    close(out.x_t, x_t, 2e-5, "x_t")
+    close(out.pred, pred, 5e-5, "pred")
+    close(out.loss, loss, 1e-5, "loss")
+    close(sdw["project_t5.3.weight"].grad, wrap.project_t5[3].weight.grad, 5e-4, "d project_t5.3.weight")
+    close(sdd["txt_in.weight"].grad, dit.txt_in.weight.grad, 5e-4, "d txt_in.weight")
+    torch.save(dict(kind="step", tower_cfg=tc.__dict__, flux_cfg=fc.__dict__, ae_cfg=ac.__dict__, seed=seed,
+                    key_shapes=dict(tower=ks_t, wrap=ks_w, dit=ks_d, ae=ks_a), clip_dim=32, t5_dim=48, img=img,
+                    ae_noise=noise, t=t, x_0=x_0, x_1=x_1p.detach(), x_t=x_t.detach(), pred=pred.detach(),
+                    loss=loss.detach(), vec=inp["vec"].detach(), txt=inp["txt"].detach(),
+                    grad_project_t5_3_weight=wrap.project_t5[3].weight.grad.clone(),
+                    grad_txt_in_weight=dit.txt_in.weight.grad.clone(),
+                    grad_final_linear_weight=dit.final_layer.linear.weight.grad.clone()),
+               os.path.join(GOLD, "step_small.pt"))
+
+
+def golden_cfg1_full(seed=0):
+    """BASELINE config 1 at FULL size (ViT-L/14-224 + full DiT + full AE, B=2, fp32, CPU) through the reference."""
+    print("[cfg-1 full-size step through the reference -- ~1 min]")
+    tc, fc, ac = O.openai_vit_l14(224), O.FluxCfg(), O.AECfg()
+    wrap, sd_t, sd_w, ks_t, ks_w = build_reference_wrapper(tc, 768, 4096, seed)
+    dit = ref_flux(fc)
+    sd_d = O.synth_state_dict(O.flux_key_shapes(fc), seed + 2)
+    dit.load_state_dict(sd_d, strict=True)
+    ae = AutoEncoder(AutoEncoderParams(resolution=256, in_channels=3, ch=128, out_ch=3, ch_mult=[1, 2, 4, 4],
+                                       num_res_blocks=2, z_channels=16, scale_factor=0.3611, shift_factor=0.1159))
+    sd_a = O.synth_state_dict(O.ae_encoder_key_shapes(ac), seed + 3)
+    ae.encoder.load_state_dict(sd_a, strict=True)
+    for n_, p_ in wrap.named_parameters():
+        p_.requires_grad_("project_clip" in n_ or "project_t5" in n_)
+    ae.requires_grad_(False)
+    g = torch.Generator().manual_seed(seed)
+    B = 2
+    img = torch.rand(B, 3, 224, 224, generator=g)
+    mean = torch.tensor(OPENAI_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(OPENAI_STD).view(1, 3, 1, 1)
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        x_1 = ae.encode(((img - 0.5) / 0.5).float())
+    inp = prepare_clip(clip=wrap, original_img=(img - mean) / std, img=x_1)
+    cls = wrap(( img - mean) / std)[0].detach()
+    x_1p = rearrange(x_1, "b c (h ph) (w pw) -> b (h w) (c ph pw)", ph=2, pw=2)
+    t = torch.sigmoid(torch.randn((B,)) * 1.0)
+    x_0 = torch.randn_like(x_1p)
+    x_t = (1 - t[:, None, None]) * x_1p + t[:, None, None] * x_0
+    pred = dit(img=x_t, img_ids=inp["img_ids"], txt=inp["txt"], txt_ids=inp["txt_ids"], y=inp["vec"], timesteps=t,
+               guidance=torch.full((B,), 4.0))
+    loss = F.mse_loss(pred.float(), (x_0 - x_1p).float(), reduction="mean")
+    loss.backward()
+    torch.manual_seed(seed)
+    noise = torch.randn(B, 16, 28, 28)
+    print("  reference loss", loss.item())
+    with torch.no_grad():
+        out = O.stage1_image_step(sd_t, sd_w, sd_d, sd_a, img, tc, fc, ac, OPENAI_MEAN, OPENAI_STD, noise, t, x_0)
+    close(out.loss, loss, 1e-4, "loss (oracle vs reference, full size)")
+    close(out.class_token, cls, 1e-4, "class_token")
+    torch.save(dict(kind="cfg1", seed=seed, img=img, ae_noise=noise, t=t, x_0=x_0, loss=loss.detach(),
+                    class_token=cls, vec=inp["vec"].detach(), x_1=x_1p.detach(), pred=pred.detach(),
+                    grad_norm_project_t5_1_weight=wrap.project_t5[1].weight.grad.norm(),
+                    grad_final_linear_weight=dit.final_layer.linear.weight.grad.clone(),
+                    grad_img_in_weight=dit.img_in.weight.grad.clone()),
+               os.path.join(GOLD, "cfg1_full.pt"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also run BASELINE config 1 at full size (~1-2 min, ~12 GB)")
+    args = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    golden_tower("clip_small", O.TowerCfg("clip", 128, 2, 2, 512, 56, 14, 64, 1e-5, "quick_gelu"))
+    golden_tower("siglip_small", O.TowerCfg("siglip", 144, 2, 2, 304, 56, 14, 144, 1e-6, "gelu_tanh"))
+    golden_ae()
+    golden_flux("img", n_txt=1)
+    golden_flux("video", n_txt=8, video_ids=True)
+    golden_step_small()
+    if args.full:
+        golden_cfg1_full()
+    print("golden fixtures written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
