@@ -37,7 +37,23 @@ class GemmArgs(C.Structure):
     ]
 
 
-_vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+class RowsView(C.Structure):
+    _fields_ = [("rows_per_batch", C.c_int32), ("batch_stride", C.c_int64), ("row_stride", C.c_int64)]
+
+
+class AttnTensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("batch_stride", C.c_int64), ("head_stride", C.c_int64),
+                ("row_stride", C.c_int64)]
+
+
+class AttnOut(C.Structure):
+    _fields_ = [("seg0", C.c_void_p), ("seg0_batch_stride", C.c_int64), ("seg0_row_stride", C.c_int64),
+                ("seg1", C.c_void_p), ("seg1_batch_stride", C.c_int64), ("seg1_row_stride", C.c_int64),
+                ("n_split", C.c_int32)]
+
+
+_vp, _i64, _i32, _f32, _f64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_double
+_rv, _at, _ao = C.POINTER(RowsView), C.POINTER(AttnTensor), C.POINTER(AttnOut)
 
 # Every symbol include/genhancer_b200.h declares, with its argument types.
 # tests/test_abi.py checks that the built library exports exactly these.
@@ -48,6 +64,20 @@ SIGNATURES: dict[str, list] = {
     "gh_gemm_bf16": [C.POINTER(GemmArgs), _vp],
     "gh_fm_interp_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "gh_fm_mse_loss_fwdbwd": [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp],
+    "gh_layernorm_fwd": [_vp, _rv, _vp, _rv, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp],
+    "gh_layernorm_bwd_dx": [_vp, _rv, _vp, _rv, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _rv, _vp, _rv, _vp],
+    "gh_layernorm_bwd_params": [_vp, _rv, _vp, _rv, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp],
+    "gh_gate_bwd": [_vp, _rv, _vp, _rv, _i32, _i32, _vp, _i64, _vp, _rv, _vp, _i64, _vp],
+    "gh_colsum": [_vp, _rv, _i32, _i32, _vp, _i64, _vp],
+    "gh_rope_table": [_vp, _vp, _i64, _i32, _i32, _i32, _f64, _vp],
+    "gh_qk_norm_rope_fwd": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    "gh_qk_norm_rope_bwd": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp,
+                            _i64, _vp, _vp, _vp],
+    "gh_timestep_embedding": [_vp, _vp, _i32, _i32, _vp],
+    "gh_act_fwd": [_vp, _vp, _i64, _i32, _vp],
+    "gh_act_bwd": [_vp, _vp, _vp, _i64, _i32, _vp],
+    "gh_accum_cast": [_vp, _vp, _i32, _i64, _f32, _i32, _vp],
+    "gh_flash_attn_fwd": [_at, _at, _at, _i32, _i32, _i32, _i32, _i32, _f32, _ao, _vp, _vp],
 }
 
 _lib = None

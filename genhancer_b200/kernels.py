@@ -122,3 +122,216 @@ def fm_mse_loss(pred: torch.Tensor, x0: torch.Tensor, x1: torch.Tensor, grad_sca
                                            dpred.data_ptr() if want_grad else None, grad_scale, p.numel(), _stream()))
     _count()
     return loss, dpred
+
+
+# ----------------------------------------------------------------------------------------------
+# row-view helpers (see gh_rows_view in include/genhancer_b200.h)
+# ----------------------------------------------------------------------------------------------
+from ._lib import AttnOut, AttnTensor, RowsView  # noqa: E402
+
+
+def _rows_view(t: torch.Tensor) -> tuple[RowsView, int, int, int]:
+    """-> (view, rows, C, batches) for a [B, L, C] or [R, C] tensor with unit channel stride."""
+    if t.stride(-1) != 1:
+        raise _lib.GhError(f"channel dim must be contiguous, got strides {t.stride()}")
+    if t.dim() == 3:
+        B, L, Cc = t.shape
+        return RowsView(L, t.stride(0), t.stride(1)), B * L, Cc, B
+    if t.dim() == 2:
+        R, Cc = t.shape
+        return RowsView(max(R, 1), 0, t.stride(0)), R, Cc, 1
+    raise _lib.GhError(f"expected 2-D or 3-D tensor, got {tuple(t.shape)}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def layernorm_fwd(x, weight=None, bias=None, shift=None, scale=None, eps=1e-6, out=None, save_stats=True):
+    """bf16 LayerNorm over the last dim; affine (fp32 w,b) | AdaLN (bf16 shift/scale [B,C] rows of a wider tensor)."""
+    _ensure(x)
+    xv, rows, Cc, _ = _rows_view(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    yv, rows_y, _, _ = _rows_view(out)
+    assert rows_y == rows and x.dtype == BF16 and out.dtype == BF16
+    mean = torch.empty(rows, dtype=F32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=F32, device=x.device) if save_stats else None
+    mod_ld = 0
+    if scale is not None:
+        assert shift is not None and scale.dtype == BF16 and shift.dtype == BF16 and scale.stride(-1) == 1
+        assert scale.stride(0) == shift.stride(0)
+        mod_ld = scale.stride(0)
+    if weight is not None:
+        assert weight.dtype == F32 and bias is not None and bias.dtype == F32
+    check(_lib.lib().gh_layernorm_fwd(x.data_ptr(), C.byref(xv), out.data_ptr(), C.byref(yv), rows, Cc, _p(weight),
+                                      _p(bias), _p(shift), _p(scale), mod_ld, eps, _p(mean), _p(rstd), _stream()))
+    _count()
+    return out, mean, rstd
+
+
+def layernorm_bwd_dx(dy, x, mean, rstd, weight=None, scale=None, dres=None, out=None):
+    _ensure(dy)
+    dyv, rows, Cc, _ = _rows_view(dy)
+    xv, _, _, _ = _rows_view(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    dxv, _, _, _ = _rows_view(out)
+    drv = _rows_view(dres)[0] if dres is not None else None
+    mod_ld = scale.stride(0) if scale is not None else 0
+    check(_lib.lib().gh_layernorm_bwd_dx(dy.data_ptr(), C.byref(dyv), x.data_ptr(), C.byref(xv), rows, Cc,
+                                         mean.data_ptr(), rstd.data_ptr(), _p(weight), _p(scale), mod_ld, _p(dres),
+                                         C.byref(drv) if drv is not None else None, out.data_ptr(), C.byref(dxv),
+                                         _stream()))
+    _count()
+    return out
+
+
+def layernorm_bwd_params(dy, x, mean, rstd, dshift_acc, dscale_acc):
+    """dshift_acc/dscale_acc: fp32 [B, C] views (row pitch = stride(0)) accumulated with atomics."""
+    _ensure(dy)
+    dyv, _, Cc, nb = _rows_view(dy)
+    xv = _rows_view(x)[0]
+    assert dshift_acc.dtype == F32 and dscale_acc.dtype == F32
+    acc_ld = dshift_acc.stride(0) if dshift_acc.dim() == 2 else 0
+    if dscale_acc.dim() == 2:
+        assert dscale_acc.stride(0) == acc_ld
+    check(_lib.lib().gh_layernorm_bwd_params(dy.data_ptr(), C.byref(dyv), x.data_ptr(), C.byref(xv), nb, Cc,
+                                             mean.data_ptr(), rstd.data_ptr(), dshift_acc.data_ptr(),
+                                             dscale_acc.data_ptr(), acc_ld, _stream()))
+    _count()
+
+
+def gate_bwd(dout, u, gate, dgate_acc, out=None):
+    """out = res + gate[b]*u  ->  du = gate[b]*dout (returned), dgate_acc[b,:] += sum_l dout*u."""
+    _ensure(dout)
+    dov, _, Cc, nb = _rows_view(dout)
+    uv = _rows_view(u)[0]
+    if out is None:
+        out = torch.empty(dout.shape, dtype=BF16, device=dout.device)
+    duv = _rows_view(out)[0]
+    check(_lib.lib().gh_gate_bwd(dout.data_ptr(), C.byref(dov), u.data_ptr(), C.byref(uv), nb, Cc, gate.data_ptr(),
+                                 gate.stride(0), out.data_ptr(), C.byref(duv), dgate_acc.data_ptr(),
+                                 dgate_acc.stride(0) if dgate_acc.dim() == 2 else 0, _stream()))
+    _count()
+    return out
+
+
+def colsum(dy, acc):
+    """acc (fp32 [C] or [B, C]) += column sums of dy ([R, C] or [B, L, C])."""
+    _ensure(dy)
+    dyv, _, Cc, nb = _rows_view(dy)
+    if acc.dim() == 1:
+        if dy.dim() == 3:  # reduce over batch too: flatten needs contiguity
+            dyc = dy.reshape(-1, Cc)
+            dyv, _, Cc, nb = _rows_view(dyc)
+            dy = dyc
+        acc_ld = 0
+    else:
+        acc_ld = acc.stride(0)
+    check(_lib.lib().gh_colsum(dy.data_ptr(), C.byref(dyv), nb, Cc, acc.data_ptr(), acc_ld, _stream()))
+    _count()
+
+
+def rope_table(ids: torch.Tensor, axes_dim=(16, 56, 56), theta: float = 10_000.0) -> torch.Tensor:
+    """ids [..., L, 3] (any float dtype, integer-valued) -> fp32 [..., L, sum(axes)/2, 2] (cos, sin)."""
+    _ensure(ids)
+    idf = ids.to(F32).contiguous()
+    n_tok = idf.numel() // 3
+    half = sum(axes_dim) // 2
+    out = torch.empty(*idf.shape[:-1], half, 2, dtype=F32, device=ids.device)
+    check(_lib.lib().gh_rope_table(idf.data_ptr(), out.data_ptr(), n_tok, axes_dim[0], axes_dim[1], axes_dim[2],
+                                   float(theta), _stream()))
+    _count()
+    return out
+
+
+def qk_norm_rope_fwd(qkv, H, q_scale, k_scale, cs, q, k, v, l_off):
+    """qkv [B, L, 3*H*D] (row pitch free) -> writes q,k,v [B, H, Ltot, D] at token offset l_off. cs [B|1, Ltot, D/2, 2]."""
+    _ensure(qkv)
+    B, L, _ = qkv.shape
+    D = q.shape[-1]
+    Ltot = q.shape[2]
+    assert qkv.stride(2) == 1 and qkv.stride(0) == L * qkv.stride(1)
+    assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    csb = cs.stride(0) // 2 if cs.shape[0] > 1 else 0  # in float2 units
+    check(_lib.lib().gh_qk_norm_rope_fwd(qkv.data_ptr(), qkv.stride(1), B, L, H, D, Ltot, l_off, q_scale.data_ptr(),
+                                         k_scale.data_ptr(), cs.data_ptr(), csb, q.data_ptr(), k.data_ptr(),
+                                         v.data_ptr(), _stream()))
+    _count()
+
+
+def qk_norm_rope_bwd(dq, dk, dv, qkv, H, q_scale, k_scale, cs, l_off, dqkv, dscale_q_acc, dscale_k_acc):
+    _ensure(qkv)
+    B, L, _ = qkv.shape
+    D = dq.shape[-1]
+    Ltot = dq.shape[2]
+    assert dq.is_contiguous() and dk.is_contiguous() and dv.is_contiguous()
+    csb = cs.stride(0) // 2 if cs.shape[0] > 1 else 0
+    check(_lib.lib().gh_qk_norm_rope_bwd(dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), qkv.data_ptr(), qkv.stride(1),
+                                         B, L, H, D, Ltot, l_off, q_scale.data_ptr(), k_scale.data_ptr(),
+                                         cs.data_ptr(), csb, dqkv.data_ptr(), dqkv.stride(1),
+                                         dscale_q_acc.data_ptr(), dscale_k_acc.data_ptr(), _stream()))
+    _count()
+
+
+def timestep_embedding(t: torch.Tensor, round_bf16: bool = True) -> torch.Tensor:
+    _ensure(t)
+    tc = t.to(F32).contiguous()
+    out = torch.empty(tc.shape[0], 256, dtype=BF16, device=t.device)
+    check(_lib.lib().gh_timestep_embedding(tc.data_ptr(), out.data_ptr(), tc.shape[0], int(round_bf16), _stream()))
+    _count()
+    return out
+
+
+def act_fwd(x: torch.Tensor, act: int) -> torch.Tensor:
+    _ensure(x)
+    xc = x.contiguous()
+    out = torch.empty_like(xc)
+    check(_lib.lib().gh_act_fwd(xc.data_ptr(), out.data_ptr(), xc.numel(), act, _stream()))
+    _count()
+    return out
+
+
+def act_bwd(dy: torch.Tensor, x: torch.Tensor, act: int) -> torch.Tensor:
+    _ensure(x)
+    dyc, xc = dy.contiguous(), x.contiguous()
+    out = torch.empty_like(xc)
+    check(_lib.lib().gh_act_bwd(dyc.data_ptr(), xc.data_ptr(), out.data_ptr(), xc.numel(), act, _stream()))
+    _count()
+    return out
+
+
+def accum_cast(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0, accumulate: bool = False) -> None:
+    _ensure(src)
+    assert src.dtype == F32 and src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    check(_lib.lib().gh_accum_cast(src.data_ptr(), dst.data_ptr(), _dt(dst), src.numel(), scale, int(accumulate),
+                                   _stream()))
+    _count()
+
+
+def _attn_tensor(t: torch.Tensor) -> AttnTensor:
+    """t viewed as [B, H, L, D] with unit stride on D."""
+    assert t.dim() == 4 and t.stride(3) == 1 and t.dtype == BF16
+    return AttnTensor(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+
+
+def flash_attn_fwd(q, k, v, scale, out1, out0=None, n_split=0, want_lse=True):
+    """q,k,v: [B,H,L,D] views (any strides, D contiguous). out1/out0: token-major [B, L(seg), H*D] (row pitch free).
+    Rows l < n_split go to out0.  Returns lse2 [B,H,Lq] fp32 (log2 domain) or None."""
+    _ensure(q)
+    B, H, Lq, D = q.shape
+    Lk = k.shape[2]
+    at = [_attn_tensor(x) for x in (q, k, v)]
+    o = AttnOut()
+    if out0 is not None and n_split > 0:
+        assert out0.stride(2) == 1
+        o.seg0, o.seg0_batch_stride, o.seg0_row_stride = out0.data_ptr(), out0.stride(0), out0.stride(1)
+    assert out1.stride(2) == 1
+    o.seg1, o.seg1_batch_stride, o.seg1_row_stride = out1.data_ptr(), out1.stride(0), out1.stride(1)
+    o.n_split = n_split
+    lse = torch.empty(B, H, Lq, dtype=F32, device=q.device) if want_lse else None
+    check(_lib.lib().gh_flash_attn_fwd(C.byref(at[0]), C.byref(at[1]), C.byref(at[2]), B, H, Lq, Lk, D, float(scale),
+                                       C.byref(o), _p(lse), _stream()))
+    _count()
+    return lse

@@ -111,6 +111,100 @@ int gh_fm_interp_fwd(const float* x1, const float* x0, const float* t, void* xt_
 int gh_fm_mse_loss_fwdbwd(const void* pred_bf16, const float* x0, const float* x1, float* loss_accum,
                           void* dpred_bf16, float grad_scale, int64_t numel, void* stream);
 
+
+/* --------------------------------------------------------------------------
+ * Row views.  Token-major activations [B, L, C] are addressed as rows of C channels:
+ * row (b, l) lives at base + b * batch_stride + l * row_stride (ELEMENTS).  This lets the
+ * norm kernels read a slice of a concatenated txt|img sequence (Flux.forward drops the
+ * txt tokens before the last layer, src/flux/model.py:225) without a copy.
+ * rows_per_batch <= 0 means one flat batch.
+ * -------------------------------------------------------------------------- */
+typedef struct {
+  int32_t rows_per_batch;
+  int64_t batch_stride;
+  int64_t row_stride;
+} gh_rows_view;
+
+/* LayerNorm forward, bf16 in/out, fp32 statistics (saved for backward when non-NULL):
+ *   affine  (weight,bias fp32 [C])            y = n * w + b      -- HF CLIP/SigLIP layer_norm1/2, pre/post
+ *                                                                   layernorm (modeling_clip.py:358-361,659-662),
+ *                                                                   projector LN (CLIP_bank.py:18,24), adapter LN
+ *   AdaLN   (shift,scale bf16 [B, mod_ld])    y = (1 + scale[b]) * n + shift[b]
+ *                                                                -- layers.py:309-310,316-317,332,336,489,570
+ *   plain   (all NULL)                        y = n
+ * C % 8 == 0, C <= 4096. */
+int gh_layernorm_fwd(const void* x, const gh_rows_view* xv, void* y, const gh_rows_view* yv, int32_t rows,
+                     int32_t C, const float* weight, const float* bias, const void* shift, const void* scale,
+                     int64_t mod_ld, float eps, float* mean_out, float* rstd_out, void* stream);
+/* dx = rstd * (dn - mean(dn) - n * mean(dn * n)) [+ dres],  dn = dy * (w | 1 + scale[b] | 1). */
+int gh_layernorm_bwd_dx(const void* dy, const gh_rows_view* dyv, const void* x, const gh_rows_view* xv,
+                        int32_t rows, int32_t C, const float* mean, const float* rstd, const float* weight,
+                        const void* scale, int64_t mod_ld, const void* dres, const gh_rows_view* drv, void* dx,
+                        const gh_rows_view* dxv, void* stream);
+/* dshift_acc[b,c] += sum_l dy ; dscale_acc[b,c] += sum_l dy * n   (fp32 accumulators, atomics).
+ * With batches = 1 and rows_per_batch = all rows these are the affine LayerNorm's (dbias, dweight). */
+int gh_layernorm_bwd_params(const void* dy, const gh_rows_view* dyv, const void* x, const gh_rows_view* xv,
+                            int32_t batches, int32_t C, const float* mean, const float* rstd, float* dshift_acc,
+                            float* dscale_acc, int64_t acc_ld, void* stream);
+/* Backward of the gated residual  out = res + gate[b] * u  (layers.py:331-336,500):
+ *   du = gate[b] * dout ;  dgate_acc[b,c] += sum_l dout * u. */
+int gh_gate_bwd(const void* dout, const gh_rows_view* dov, const void* u, const gh_rows_view* uv, int32_t batches,
+                int32_t C, const void* gate, int64_t gate_ld, void* du, const gh_rows_view* duv, float* dgate_acc,
+                int64_t acc_ld, void* stream);
+/* acc[b,c] += sum_l dy[b,l,c]  (bias gradients). */
+int gh_colsum(const void* dy, const gh_rows_view* dyv, int32_t batches, int32_t C, float* acc, int64_t acc_ld,
+              void* stream);
+
+/* RoPE cos/sin table from integer-valued ids (EmbedND + rope, layers.py:18-25, math.py:15-22):
+ * ids fp32 [n_tokens, 3] -> cos_sin float2 [n_tokens, (a0+a1+a2)/2]; angles in float64. */
+int gh_rope_table(const float* ids, void* cos_sin, int64_t n_tokens, int32_t axis0, int32_t axis1, int32_t axis2,
+                  double theta, void* stream);
+/* QKNorm (RMSNorm over head dim, layers.py:63-84) + apply_rope (math.py:25-30) + head-major scatter:
+ * qkv bf16 [B, L, 3, H, D] (row pitch ld_qkv) -> q, k, v bf16 [B, H, Ltot, D] at token offset l_off
+ * (the txt|img concat of layers.py:323-326 is done by writing both streams into the same buffers). D = 128. */
+int gh_qk_norm_rope_fwd(const void* qkv, int64_t ld_qkv, int32_t B, int32_t L, int32_t H, int32_t D, int32_t Ltot,
+                        int32_t l_off, const void* q_scale, const void* k_scale, const void* cos_sin,
+                        int64_t cs_batch_stride, void* q, void* k, void* v, void* stream);
+int gh_qk_norm_rope_bwd(const void* dq, const void* dk, const void* dv, const void* qkv, int64_t ld_qkv, int32_t B,
+                        int32_t L, int32_t H, int32_t D, int32_t Ltot, int32_t l_off, const void* q_scale,
+                        const void* k_scale, const void* cos_sin, int64_t cs_batch_stride, void* dqkv,
+                        int64_t ld_dqkv, float* dscale_q_acc, float* dscale_k_acc, void* stream);
+
+/* timestep_embedding (layers.py:28-49): t fp32 [B] -> bf16 [B, 256] = [cos | sin](1000 t f_k).
+ * round_bf16 = 1 reproduces the scripts' bf16 cast of t before the multiply (train_SigLIP_stage1.py:260). */
+int gh_timestep_embedding(const float* t, void* out_bf16, int32_t B, int32_t round_bf16, void* stream);
+/* elementwise activation / its backward on bf16 (nn.SiLU of Modulation / LastLayer, layers.py:170,566). */
+int gh_act_fwd(const void* x, void* y, int64_t numel, int32_t act, void* stream);
+int gh_act_bwd(const void* dy, const void* x, void* dx, int64_t numel, int32_t act, void* stream);
+/* dst (bf16|fp32) = scale * src_fp32 (+ dst): flush of the fp32 small-gradient scratch into .grad. */
+int gh_accum_cast(const float* src, void* dst, int32_t dst_dtype, int64_t numel, float scale, int32_t accumulate,
+                  void* stream);
+
+/* --------------------------------------------------------------------------
+ * Flash attention (tcgen05 S/O accumulators in TMEM, TMA-staged tiles, online softmax).
+ * Replaces F.scaled_dot_product_attention at HF modeling_clip.py:319-331 (ViT, D=64, scale 1/8) and
+ * src/flux/math.py:9 (DiT joint attention over cat(txt,img), D=128), no mask, no dropout.
+ *
+ * q/k/v element [b,h,l,0:D] is contiguous bf16 at ptr + b*batch_stride + h*head_stride + l*row_stride
+ * (ELEMENTS; multiples of 8) -- head-major buffers and the fused-QKV GEMM output are both zero-copy.
+ * O is token-major [b, l, h*D + d] and may be split into two row segments (rows < n_split -> seg0).
+ * lse2 [B,H,Lq] fp32 = log2-domain logsumexp of the scaled scores (saved for backward; may be NULL).
+ * -------------------------------------------------------------------------- */
+typedef struct {
+  const void* ptr;
+  int64_t batch_stride, head_stride, row_stride;
+} gh_attn_tensor;
+typedef struct {
+  void* seg0;
+  int64_t seg0_batch_stride, seg0_row_stride;
+  void* seg1;
+  int64_t seg1_batch_stride, seg1_row_stride;
+  int32_t n_split;
+} gh_attn_out;
+int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh_attn_tensor* v, int32_t B, int32_t H,
+                      int32_t Lq, int32_t Lk, int32_t D, float scale, const gh_attn_out* o, float* lse2,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
