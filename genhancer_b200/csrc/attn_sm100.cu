@@ -263,6 +263,455 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
+// ============================================================================
+// Backward
+//   prep : delta[b,h,l] = sum_d dO*O ; dO gathered token-major(2 segments) -> head-major [B,H,L,D]
+//   dKV  : CTA = (128 keys, h, b), loops over 64-query blocks.  Works on the TRANSPOSED score tile so that the
+//          thread-owned TMEM lane is a key row and P^T / dS^T land in smem K-major without any transpose:
+//            S^T = K Q^T, dP^T = V dO^T, P^T = exp2(S^T c - lse_col), dS^T = P^T (dP^T - delta_col) scale
+//            dV += P^T dO,  dK += dS^T Q          (Q / dO tiles are reused as MN-major B operands)
+//   dQ   : CTA = (128 queries, h, b), loops over 64-key blocks:  S = Q K^T, dP = dO V^T, dQ += dS K
+// 7 GEMMs instead of the minimal 5 (S and dP are recomputed in the dQ pass), no atomics, deterministic.
+// ============================================================================
+struct AttnBwdParams {
+  int B, H, Lq, Lk;
+  float scale, scale_log2;
+  const float* lse2;   // [B,H,Lq]
+  const float* delta;  // [B,H,Lq]
+  bf16 *dq, *dk, *dv;  // element [b,h,l,:] at ptr + b*bs + h*hs + l*rs
+  int64_t dq_bs, dq_hs, dq_rs, dk_bs, dk_hs, dk_rs, dv_bs, dv_hs, dv_rs;
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(SegOut o, SegOut dout, int B, int H, int L,
+                                                            float* __restrict__ delta, bf16* __restrict__ do_hm) {
+  constexpr int E = D / 32;  // elements per lane (4 or 2)
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (wid >= static_cast<int64_t>(B) * L * H) return;
+  const int h = static_cast<int>(wid % H);
+  const int64_t tok = wid / H;
+  const int l = static_cast<int>(tok % L), b = static_cast<int>(tok / L);
+  const bf16* po = o.row(b, l) + h * D + lane * E;
+  const bf16* pd = dout.row(b, l) + h * D + lane * E;
+  bf16* dst = do_hm + ((static_cast<int64_t>(b) * H + h) * L + l) * D + lane * E;
+  float acc = 0.f;
+  if (E == 4) {
+    const uint2 a = *reinterpret_cast<const uint2*>(po), g = *reinterpret_cast<const uint2*>(pd);
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
+    acc = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y;
+    *reinterpret_cast<uint2*>(dst) = g;
+  } else {
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(po), g = *reinterpret_cast<const uint32_t*>(pd);
+    const float2 a0 = unpack_bf16x2(a), g0 = unpack_bf16x2(g);
+    acc = a0.x * g0.x + a0.y * g0.y;
+    *reinterpret_cast<uint32_t*>(dst) = g;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) delta[(static_cast<int64_t>(b) * H + h) * L + l] = acc;
+}
+
+template <int D>
+struct AttnBwdKVCfg {
+  static constexpr int KV_BYTES = 128 * D * 2;  // K_j or V_j (resident)
+  static constexpr int QD_BYTES = 64 * D * 2;   // Q_i or dO_i
+  static constexpr int NQ = 3;                  // Q/dO ring depth
+  static constexpr int T_BYTES = 128 * 64 * 2;  // P^T or dS^T
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = KV_BYTES;
+  static constexpr int OFF_Q = 2 * KV_BYTES;
+  static constexpr int OFF_DO = OFF_Q + NQ * QD_BYTES;
+  static constexpr int OFF_PT = OFF_DO + NQ * QD_BYTES;
+  static constexpr int OFF_DST = OFF_PT + T_BYTES;
+  static constexpr int OFF_STAT = OFF_DST + T_BYTES;     // float [2][2][64]: lse, delta per S buffer
+  static constexpr int OFF_BAR = OFF_STAT + 2 * 2 * 64 * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int TM_DV = 256, TM_DK = 256 + D;
+};
+
+template <int D>
+__global__ void __launch_bounds__(160, 1)
+flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                     const AttnBwdParams p) {
+  using Cfg = AttnBwdKVCfg<D>;
+  constexpr int DC = D / 64;
+  constexpr int NQ = Cfg::NQ;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sDO = smem + Cfg::OFF_DO;
+  uint8_t* sPT = smem + Cfg::OFF_PT;
+  uint8_t* sDST = smem + Cfg::OFF_DST;
+  float* sStat = reinterpret_cast<float*>(smem + Cfg::OFF_STAT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* bar_kv = bars + 0;
+  uint64_t* bar_qd = bars + 1;   // [3]
+  uint64_t* bar_sd = bars + 4;   // [2]
+  uint64_t* bar_pd = bars + 6;
+  uint64_t* bar_acc = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int nq = (p.Lq + 63) / 64;
+
+  if (warp == 4 && lane == 0) {
+    mbar_init(bar_kv, 1);
+    for (int i = 0; i < NQ; ++i) mbar_init(&bar_qd[i], 1);
+    mbar_init(&bar_sd[0], 1); mbar_init(&bar_sd[1], 1);
+    mbar_init(bar_pd, 4);
+    mbar_init(bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
+      constexpr uint32_t idesc_a = umma_idesc_bf16(128, D, false, true);
+      const uint64_t kdesc = umma_desc_base(16u, 1024u);
+      const uint64_t mdesc = umma_desc_base(8192u, 1024u);
+      auto load_qd = [&](int i) {
+        const int s = i % NQ;
+        mbar_arrive_expect_tx(&bar_qd[s], 2 * Cfg::QD_BYTES);
+#pragma unroll
+        for (int c = 0; c < DC; ++c) {
+          tma_load_4d(sQ + s * Cfg::QD_BYTES + c * 8192, &tm_q, &bar_qd[s], c * 64, i * 64, h, b);
+          tma_load_4d(sDO + s * Cfg::QD_BYTES + c * 8192, &tm_do, &bar_qd[s], c * 64, i * 64, h, b);
+        }
+      };
+      auto issue_sd = [&](int i) {
+        const int s = i % NQ;
+        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+        const uint32_t aQ = smem_u32(sQ + s * Cfg::QD_BYTES), aD = smem_u32(sDO + s * Cfg::QD_BYTES);
+        const uint32_t tS = tmem + (i & 1) * 128, tP = tS + 64;
+#pragma unroll
+        for (int c = 0; c < DC; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, umma_desc_at(kdesc, aK + c * 16384 + k * 32), umma_desc_at(kdesc, aQ + c * 8192 + k * 32),
+                    idesc_s, (c | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int c = 0; c < DC; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tP, umma_desc_at(kdesc, aV + c * 16384 + k * 32), umma_desc_at(kdesc, aD + c * 8192 + k * 32),
+                    idesc_s, (c | k) != 0 ? 1u : 0u);
+        umma_commit(&bar_sd[i & 1]);
+      };
+      mbar_arrive_expect_tx(bar_kv, 2 * Cfg::KV_BYTES);
+#pragma unroll
+      for (int c = 0; c < DC; ++c) {
+        tma_load_4d(sK + c * 16384, &tm_k, bar_kv, c * 64, k0, h, b);
+        tma_load_4d(sV + c * 16384, &tm_v, bar_kv, c * 64, k0, h, b);
+      }
+      load_qd(0);
+      if (nq > 1) load_qd(1);
+      mbar_wait(bar_kv, 0);
+      mbar_wait(&bar_qd[0], 0);
+      tc_fence_after();
+      issue_sd(0);
+      for (int i = 0; i < nq; ++i) {
+        if (i + 1 < nq) {
+          mbar_wait(&bar_qd[(i + 1) % NQ], ((i + 1) / NQ) & 1);
+          tc_fence_after();
+          issue_sd(i + 1);
+        }
+        mbar_wait(bar_pd, i & 1);  // P^T_i, dS^T_i in smem; implies acc MMAs of i-1 have retired
+        tc_fence_after();
+        if (i + 2 < nq) load_qd(i + 2);  // ring slot (i+2)%3 == (i-1)%3 is free
+        {
+          const int s = i % NQ;
+          const uint32_t aPT = smem_u32(sPT), aDST = smem_u32(sDST);
+          const uint32_t aQ = smem_u32(sQ + s * Cfg::QD_BYTES), aD = smem_u32(sDO + s * Cfg::QD_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tmem + Cfg::TM_DV, umma_desc_at(kdesc, aPT + k * 32), umma_desc_at(mdesc, aD + k * 2048), idesc_a,
+                    (i | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tmem + Cfg::TM_DK, umma_desc_at(kdesc, aDST + k * 32), umma_desc_at(mdesc, aQ + k * 2048), idesc_a,
+                    (i | k) != 0 ? 1u : 0u);
+          umma_commit(bar_acc);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int row = threadIdx.x;  // key row within the block == TMEM lane
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const int64_t stat_base = (static_cast<int64_t>(b) * p.H + h) * p.Lq;
+    for (int i = 0; i < nq; ++i) {
+      // stage lse / delta of this query block (threads 0-63 -> lse, 64-127 -> delta)
+      float* st = sStat + (i & 1) * 128;
+      {
+        const int c = row & 63;
+        const int ql = i * 64 + c;
+        const float v = ql < p.Lq ? (row < 64 ? p.lse2[stat_base + ql] : p.delta[stat_base + ql]) : 0.f;
+        st[row] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&bar_sd[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      const int q_left = p.Lq - i * 64;
+      uint32_t pt[32], dst[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32(t_lane + (i & 1) * 128 + half * 32, s);
+        tmem_ld_32x32(t_lane + (i & 1) * 128 + 64 + half * 32, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const int cc = half * 32 + c;
+          float p0 = exp2f(__uint_as_float(s[c]) * p.scale_log2 - st[cc]);
+          float p1 = exp2f(__uint_as_float(s[c + 1]) * p.scale_log2 - st[cc + 1]);
+          if (cc >= q_left) p0 = 0.f;
+          if (cc + 1 >= q_left) p1 = 0.f;
+          const float d0 = p0 * (__uint_as_float(dp[c]) - st[64 + cc]) * p.scale;
+          const float d1 = p1 * (__uint_as_float(dp[c + 1]) - st[64 + cc + 1]) * p.scale;
+          pt[cc >> 1] = pack_bf16x2(p0, p1);
+          dst[cc >> 1] = pack_bf16x2(d0, d1);
+        }
+      }
+      if (i > 0) mbar_wait(bar_acc, (i - 1) & 1);  // previous dV/dK MMAs no longer read sPT/sDST
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        st_sw128(sPT, row, c, make_uint4(pt[4 * c], pt[4 * c + 1], pt[4 * c + 2], pt[4 * c + 3]));
+        st_sw128(sDST, row, c, make_uint4(dst[4 * c], dst[4 * c + 1], dst[4 * c + 2], dst[4 * c + 3]));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pd);
+    }
+    mbar_wait(bar_acc, (nq - 1) & 1);
+    tc_fence_after();
+    const int kl = k0 + row;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      bf16* dstp = which ? p.dk + b * p.dk_bs + h * p.dk_hs + static_cast<int64_t>(kl) * p.dk_rs
+                         : p.dv + b * p.dv_bs + h * p.dv_hs + static_cast<int64_t>(kl) * p.dv_rs;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32(t_lane + (which ? Cfg::TM_DK : Cfg::TM_DV) + c * 32, o);
+        tmem_ld_wait();
+        if (kl < p.Lk) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]), __uint_as_float(o[8 * q4 + 1]));
+            w.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]), __uint_as_float(o[8 * q4 + 3]));
+            w.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]), __uint_as_float(o[8 * q4 + 5]));
+            w.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]), __uint_as_float(o[8 * q4 + 7]));
+            *reinterpret_cast<uint4*>(dstp + c * 32 + q4 * 8) = w;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+template <int D>
+struct AttnBwdQCfg {
+  static constexpr int Q_BYTES = 128 * D * 2;  // Q_i or dO_i (resident)
+  static constexpr int KV_BYTES = 64 * D * 2;  // K_j or V_j
+  static constexpr int NK = 3;
+  static constexpr int T_BYTES = 128 * 64 * 2;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_DO = Q_BYTES;
+  static constexpr int OFF_K = 2 * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + NK * KV_BYTES;
+  static constexpr int OFF_DS = OFF_V + NK * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_DS + T_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int TM_DQ = 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(160, 1)
+flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                    const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                    const AttnBwdParams p) {
+  using Cfg = AttnBwdQCfg<D>;
+  constexpr int DC = D / 64;
+  constexpr int NK = Cfg::NK;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sDO = smem + Cfg::OFF_DO;
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sDS = smem + Cfg::OFF_DS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_kv = bars + 1;   // [3]
+  uint64_t* bar_sd = bars + 4;   // [2]
+  uint64_t* bar_pd = bars + 6;
+  uint64_t* bar_acc = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int nkv = (p.Lk + 63) / 64;
+
+  if (warp == 4 && lane == 0) {
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < NK; ++i) mbar_init(&bar_kv[i], 1);
+    mbar_init(&bar_sd[0], 1); mbar_init(&bar_sd[1], 1);
+    mbar_init(bar_pd, 4);
+    mbar_init(bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
+      constexpr uint32_t idesc_a = umma_idesc_bf16(128, D, false, true);
+      const uint64_t kdesc = umma_desc_base(16u, 1024u);
+      const uint64_t mdesc = umma_desc_base(8192u, 1024u);
+      auto load_kv = [&](int j) {
+        const int s = j % NK;
+        mbar_arrive_expect_tx(&bar_kv[s], 2 * Cfg::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < DC; ++c) {
+          tma_load_4d(sK + s * Cfg::KV_BYTES + c * 8192, &tm_k, &bar_kv[s], c * 64, j * 64, h, b);
+          tma_load_4d(sV + s * Cfg::KV_BYTES + c * 8192, &tm_v, &bar_kv[s], c * 64, j * 64, h, b);
+        }
+      };
+      auto issue_sd = [&](int j) {
+        const int s = j % NK;
+        const uint32_t aQ = smem_u32(sQ), aD = smem_u32(sDO);
+        const uint32_t aK = smem_u32(sK + s * Cfg::KV_BYTES), aV = smem_u32(sV + s * Cfg::KV_BYTES);
+        const uint32_t tS = tmem + (j & 1) * 128, tP = tS + 64;
+#pragma unroll
+        for (int c = 0; c < DC; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, umma_desc_at(kdesc, aQ + c * 16384 + k * 32), umma_desc_at(kdesc, aK + c * 8192 + k * 32),
+                    idesc_s, (c | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int c = 0; c < DC; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tP, umma_desc_at(kdesc, aD + c * 16384 + k * 32), umma_desc_at(kdesc, aV + c * 8192 + k * 32),
+                    idesc_s, (c | k) != 0 ? 1u : 0u);
+        umma_commit(&bar_sd[j & 1]);
+      };
+      mbar_arrive_expect_tx(bar_q, 2 * Cfg::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < DC; ++c) {
+        tma_load_4d(sQ + c * 16384, &tm_q, bar_q, c * 64, q0, h, b);
+        tma_load_4d(sDO + c * 16384, &tm_do, bar_q, c * 64, q0, h, b);
+      }
+      load_kv(0);
+      if (nkv > 1) load_kv(1);
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv[0], 0);
+      tc_fence_after();
+      issue_sd(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) {
+          mbar_wait(&bar_kv[(j + 1) % NK], ((j + 1) / NK) & 1);
+          tc_fence_after();
+          issue_sd(j + 1);
+        }
+        mbar_wait(bar_pd, j & 1);
+        tc_fence_after();
+        if (j + 2 < nkv) load_kv(j + 2);
+        {
+          const uint32_t aDS = smem_u32(sDS), aK = smem_u32(sK + (j % NK) * Cfg::KV_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tmem + Cfg::TM_DQ, umma_desc_at(kdesc, aDS + k * 32), umma_desc_at(mdesc, aK + k * 2048), idesc_a,
+                    (j | k) != 0 ? 1u : 0u);
+          umma_commit(bar_acc);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int row = threadIdx.x;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const int ql = q0 + row;
+    const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + ql;
+    const float lse = ql < p.Lq ? p.lse2[stat] : 0.f;
+    const float dl = ql < p.Lq ? p.delta[stat] : 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&bar_sd[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const int kv_left = p.Lk - j * 64;
+      uint32_t ds[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32(t_lane + (j & 1) * 128 + half * 32, s);
+        tmem_ld_32x32(t_lane + (j & 1) * 128 + 64 + half * 32, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const int cc = half * 32 + c;
+          float p0 = exp2f(__uint_as_float(s[c]) * p.scale_log2 - lse);
+          float p1 = exp2f(__uint_as_float(s[c + 1]) * p.scale_log2 - lse);
+          if (cc >= kv_left) p0 = 0.f;
+          if (cc + 1 >= kv_left) p1 = 0.f;
+          ds[cc >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dl) * p.scale,
+                                    p1 * (__uint_as_float(dp[c + 1]) - dl) * p.scale);
+        }
+      }
+      if (j > 0) mbar_wait(bar_acc, (j - 1) & 1);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        st_sw128(sDS, row, c, make_uint4(ds[4 * c], ds[4 * c + 1], ds[4 * c + 2], ds[4 * c + 3]));
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pd);
+    }
+    mbar_wait(bar_acc, (nkv - 1) & 1);
+    tc_fence_after();
+    bf16* dstp = p.dq + b * p.dq_bs + h * p.dq_hs + static_cast<int64_t>(ql) * p.dq_rs;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_lane + Cfg::TM_DQ + c * 32, o);
+      tmem_ld_wait();
+      if (ql < p.Lq) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]), __uint_as_float(o[8 * q4 + 1]));
+          w.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]), __uint_as_float(o[8 * q4 + 3]));
+          w.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]), __uint_as_float(o[8 * q4 + 5]));
+          w.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]), __uint_as_float(o[8 * q4 + 7]));
+          *reinterpret_cast<uint4*>(dstp + c * 32 + q4 * 8) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // 4-D map over [b, h, l, d] with arbitrary (16-byte multiple) strides; box = 64 x box_rows x 1 x 1
 static int make_qkv_map(CUtensorMap* m, const gh_attn_tensor* t, int B, int H, int L, int D, int box_rows) {
   const uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(L), static_cast<uint64_t>(H),
@@ -283,6 +732,14 @@ int attn_init() {
                                      AttnFwdCfg<64>::SMEM_BYTES));
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnFwdCfg<128>::SMEM_BYTES));
+  GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AttnBwdKVCfg<64>::SMEM_BYTES));
+  GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AttnBwdKVCfg<128>::SMEM_BYTES));
+  GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AttnBwdQCfg<64>::SMEM_BYTES));
+  GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AttnBwdQCfg<128>::SMEM_BYTES));
   return GH_OK;
 }
 
@@ -322,5 +779,80 @@ extern "C" int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* 
   else
     flash_fwd_kernel<128><<<grid, 160, AttnFwdCfg<128>::SMEM_BYTES, s>>>(mq, mk_, mv, p);
   GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+static void seg_from(const gh_attn_out* o, SegOut* s) {
+  s->p0 = static_cast<bf16*>(o->seg0); s->bs0 = o->seg0_batch_stride; s->rs0 = o->seg0_row_stride;
+  s->p1 = static_cast<bf16*>(o->seg1); s->bs1 = o->seg1_batch_stride; s->rs1 = o->seg1_row_stride;
+  s->n_split = o->n_split;
+}
+
+extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh_attn_tensor* v,
+                                 const gh_attn_out* o, const gh_attn_out* d_o, const float* lse2, int32_t B,
+                                 int32_t H, int32_t Lq, int32_t Lk, int32_t D, float scale, const gh_attn_tensor* dq,
+                                 const gh_attn_tensor* dk, const gh_attn_tensor* dv, void* ws_do_headmajor,
+                                 float* ws_delta, void* stream) {
+  GH_REQUIRE(attn_tensor_ok(q) && attn_tensor_ok(k) && attn_tensor_ok(v) && attn_tensor_ok(dq) && attn_tensor_ok(dk) &&
+                 attn_tensor_ok(dv),
+             GH_ERR_ALIGN, "gh_flash_attn_bwd: q/k/v/dq/dk/dv must be non-NULL, 16B aligned, strides multiples of 8");
+  GH_REQUIRE(o && d_o && o->seg1 && d_o->seg1 && lse2 && ws_do_headmajor && ws_delta, GH_ERR_NULL,
+             "gh_flash_attn_bwd: NULL pointer");
+  GH_REQUIRE(D == 64 || D == 128, GH_ERR_UNSUPPORTED, "gh_flash_attn_bwd: head dim %d unsupported (64, 128)", D);
+  GH_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, GH_ERR_BAD_SHAPE, "gh_flash_attn_bwd: bad shape");
+  if (B == 0 || Lq == 0) return GH_OK;
+  GH_REQUIRE(aligned16(ws_do_headmajor), GH_ERR_ALIGN, "gh_flash_attn_bwd: workspace must be 16B aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SegOut so, sdo;
+  seg_from(o, &so);
+  seg_from(d_o, &sdo);
+  const int64_t n = static_cast<int64_t>(B) * Lq * H;
+  if (D == 64)
+    attn_bwd_prep_kernel<64><<<static_cast<int>((n + 7) / 8), 256, 0, s>>>(so, sdo, B, H, Lq, ws_delta,
+                                                                          static_cast<bf16*>(ws_do_headmajor));
+  else
+    attn_bwd_prep_kernel<128><<<static_cast<int>((n + 7) / 8), 256, 0, s>>>(so, sdo, B, H, Lq, ws_delta,
+                                                                           static_cast<bf16*>(ws_do_headmajor));
+  GH_CHECK_CUDA(cudaGetLastError());
+
+  gh_attn_tensor dot;
+  dot.ptr = ws_do_headmajor;
+  dot.row_stride = D;
+  dot.head_stride = static_cast<int64_t>(Lq) * D;
+  dot.batch_stride = static_cast<int64_t>(H) * Lq * D;
+  AttnBwdParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse2 = lse2; p.delta = ws_delta;
+  p.dq = static_cast<bf16*>(const_cast<void*>(dq->ptr)); p.dq_bs = dq->batch_stride; p.dq_hs = dq->head_stride; p.dq_rs = dq->row_stride;
+  p.dk = static_cast<bf16*>(const_cast<void*>(dk->ptr)); p.dk_bs = dk->batch_stride; p.dk_hs = dk->head_stride; p.dk_rs = dk->row_stride;
+  p.dv = static_cast<bf16*>(const_cast<void*>(dv->ptr)); p.dv_bs = dv->batch_stride; p.dv_hs = dv->head_stride; p.dv_rs = dv->row_stride;
+  {
+    CUtensorMap mk_, mv, mq, mdo;
+    if (int e = make_qkv_map(&mk_, k, B, H, Lk, D, 128)) return e;
+    if (int e = make_qkv_map(&mv, v, B, H, Lk, D, 128)) return e;
+    if (int e = make_qkv_map(&mq, q, B, H, Lq, D, 64)) return e;
+    if (int e = make_qkv_map(&mdo, &dot, B, H, Lq, D, 64)) return e;
+    dim3 grid((Lk + 127) / 128, H, B);
+    if (D == 64)
+      flash_bwd_dkv_kernel<64><<<grid, 160, AttnBwdKVCfg<64>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, p);
+    else
+      flash_bwd_dkv_kernel<128><<<grid, 160, AttnBwdKVCfg<128>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, p);
+    GH_CHECK_CUDA(cudaGetLastError());
+  }
+  {
+    CUtensorMap mk_, mv, mq, mdo;
+    if (int e = make_qkv_map(&mk_, k, B, H, Lk, D, 64)) return e;
+    if (int e = make_qkv_map(&mv, v, B, H, Lk, D, 64)) return e;
+    if (int e = make_qkv_map(&mq, q, B, H, Lq, D, 128)) return e;
+    if (int e = make_qkv_map(&mdo, &dot, B, H, Lq, D, 128)) return e;
+    dim3 grid((Lq + 127) / 128, H, B);
+    if (D == 64)
+      flash_bwd_dq_kernel<64><<<grid, 160, AttnBwdQCfg<64>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, p);
+    else
+      flash_bwd_dq_kernel<128><<<grid, 160, AttnBwdQCfg<128>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, p);
+    GH_CHECK_CUDA(cudaGetLastError());
+  }
   return GH_OK;
 }

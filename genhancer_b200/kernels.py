@@ -335,3 +335,31 @@ def flash_attn_fwd(q, k, v, scale, out1, out0=None, n_split=0, want_lse=True):
                                        C.byref(o), _p(lse), _stream()))
     _count()
     return lse
+
+
+def _attn_out(out1, out0, n_split) -> AttnOut:
+    o = AttnOut()
+    if out0 is not None and n_split > 0:
+        assert out0.stride(2) == 1
+        o.seg0, o.seg0_batch_stride, o.seg0_row_stride = out0.data_ptr(), out0.stride(0), out0.stride(1)
+    assert out1.stride(2) == 1
+    o.seg1, o.seg1_batch_stride, o.seg1_row_stride = out1.data_ptr(), out1.stride(0), out1.stride(1)
+    o.n_split = n_split
+    return o
+
+
+def flash_attn_bwd(q, k, v, lse, scale, o1, do1, dq, dk, dv, o0=None, do0=None, n_split=0):
+    """Backward of flash_attn_fwd.  o*/do* token-major (same split as forward); dq/dk/dv [B,H,L,D] views (any
+    strides, D contiguous) are written."""
+    _ensure(q)
+    B, H, Lq, D = q.shape
+    Lk = k.shape[2]
+    at = [_attn_tensor(x) for x in (q, k, v, dq, dk, dv)]
+    o = _attn_out(o1, o0, n_split)
+    do = _attn_out(do1, do0, n_split)
+    ws_do = torch.empty(B, H, Lq, D, dtype=BF16, device=q.device)
+    ws_delta = torch.empty(B, H, Lq, dtype=F32, device=q.device)
+    check(_lib.lib().gh_flash_attn_bwd(C.byref(at[0]), C.byref(at[1]), C.byref(at[2]), C.byref(o), C.byref(do),
+                                       lse.data_ptr(), B, H, Lq, Lk, D, float(scale), C.byref(at[3]), C.byref(at[4]),
+                                       C.byref(at[5]), ws_do.data_ptr(), ws_delta.data_ptr(), _stream()))
+    _count(3)

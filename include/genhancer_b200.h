@@ -204,6 +204,15 @@ typedef struct {
 int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh_attn_tensor* v, int32_t B, int32_t H,
                       int32_t Lq, int32_t Lk, int32_t D, float scale, const gh_attn_out* o, float* lse2,
                       void* stream);
+/* Backward of the above (autograd of math.py:9 / modeling_clip.py:319-331): three launches --
+ * prep (delta = rowsum(dO*O), dO gathered head-major), dK/dV pass, dQ pass (S and dP recomputed; no atomics).
+ * o / d_o are token-major with the same two-segment split as the forward output; dq/dk/dv are written at
+ * [b,h,l,:] = ptr + b*batch_stride + h*head_stride + l*row_stride.
+ * Workspaces: ws_do_headmajor bf16 [B,H,Lq,D], ws_delta fp32 [B,H,Lq]. */
+int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh_attn_tensor* v, const gh_attn_out* o,
+                      const gh_attn_out* d_o, const float* lse2, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
+                      int32_t D, float scale, const gh_attn_tensor* dq, const gh_attn_tensor* dk,
+                      const gh_attn_tensor* dv, void* ws_do_headmajor, float* ws_delta, void* stream);
 
 #ifdef __cplusplus
 }

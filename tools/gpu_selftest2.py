@@ -182,6 +182,53 @@ def attn_case(B, H, L, D, n_split=0, fused_qkv=False, seed=5):
         f"relerr={e:.3e} lse relerr={e2:.3e} nan={torch.isnan(got.float()).any().item()}")
 
 
+def attn_bwd_case(B, H, L, D, n_split=0, fused_qkv=False, seed=7):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    if fused_qkv:
+        qkv = torch.randn(B, L, 3, H, D, device=dev, generator=g).to(BF)
+        q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        dqkv = torch.full_like(qkv, float("nan"))
+        dq, dk, dv = (dqkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    else:
+        q, k, v = (torch.randn(B, H, L, D, device=dev, generator=g).to(BF) for _ in range(3))
+        dq, dk, dv = (torch.full((B, H, L, D), float("nan"), device=dev, dtype=BF) for _ in range(3))
+    scale = D ** -0.5
+    out1 = torch.empty(B, L - n_split, H * D, device=dev, dtype=BF)
+    out0 = torch.empty(B, max(n_split, 1), H * D, device=dev, dtype=BF) if n_split else None
+    lse = K.flash_attn_fwd(q, k, v, scale, out1, out0, n_split)
+    do_full = torch.randn(B, L, H * D, device=dev, generator=g).to(BF)
+    do0 = do_full[:, :n_split].contiguous() if n_split else None
+    do1 = do_full[:, n_split:].contiguous()
+    K.flash_attn_bwd(q, k, v, lse, scale, out1, do1, dq, dk, dv, out0, do0, n_split)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, L, H * D)
+    ref.backward(do_full.float())
+    e = [rel(dq, qf.grad), rel(dk, kf.grad), rel(dv, vf.grad)]
+    say("PASS" if max(e) < 1.2e-2 else "FAIL", f"flash_bwd B={B} H={H} L={L} D={D} split={n_split} fused={fused_qkv}",
+        f"dq={e[0]:.3e} dk={e[1]:.3e} dv={e[2]:.3e}")
+
+
+def time_attn_bwd(B, H, L, D, iters=10):
+    q, k, v = (torch.randn(B, H, L, D, device=dev).to(BF) for _ in range(3))
+    dq, dk, dv = (torch.empty_like(q) for _ in range(3))
+    out = torch.empty(B, L, H * D, device=dev, dtype=BF)
+    do = torch.randn(B, L, H * D, device=dev).to(BF)
+    lse = K.flash_attn_fwd(q, k, v, D ** -0.5, out)
+    for _ in range(3):
+        K.flash_attn_bwd(q, k, v, lse, D ** -0.5, out, do, dq, dk, dv)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        K.flash_attn_bwd(q, k, v, lse, D ** -0.5, out, do, dq, dk, dv)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fl = 10.0 * B * H * L * L * D
+    say(f"TIME flash_bwd B={B} H={H} L={L} D={D}: {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s (algorithmic 5 GEMMs)")
+
+
 def time_attn(B, H, L, D, iters=10):
     q, k, v = (torch.randn(B, H, L, D, device=dev).to(BF) for _ in range(3))
     out = torch.empty(B, L, H * D, device=dev, dtype=BF)
@@ -229,6 +276,16 @@ def main():
         attn_case(1, 1, 64, 64)
         attn_case(2, 4, 577, 64, fused_qkv=True)
         attn_case(2, 4, 257, 64, fused_qkv=True)
+    if "attnbwd" in which:
+        attn_bwd_case(1, 1, 64, 128)
+        attn_bwd_case(1, 1, 128, 128)
+        attn_bwd_case(1, 2, 200, 128)
+        attn_bwd_case(2, 3, 442, 128, n_split=1)
+        attn_bwd_case(2, 2, 1017, 128, n_split=576)
+        attn_bwd_case(1, 1, 64, 64)
+        attn_bwd_case(2, 4, 577, 64, fused_qkv=True)
+        time_attn_bwd(32, 24, 442, 128)
+        time_attn_bwd(32, 16, 577, 64)
     if "time" in which:
         time_attn(32, 24, 442, 128)
         time_attn(32, 16, 577, 64)
