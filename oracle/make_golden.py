@@ -222,12 +222,26 @@ def golden_flux(name: str, n_txt: int, seed=31, video_ids=False):
     dit_bf.load_state_dict(sd, strict=True)
     dit_bf = dit_bf.to(torch.bfloat16)
     bf = torch.bfloat16
-    with torch.no_grad():
-        pred_bf = dit_bf(img=img.to(bf), img_ids=img_ids.to(bf), txt=txt.to(bf), txt_ids=txt_ids.to(bf),
-                         timesteps=t.to(bf), y=y.to(bf), guidance=guidance.to(bf))
+    txt_b, y_b = txt.to(bf).requires_grad_(True), y.to(bf).requires_grad_(True)
+    pred_bf = dit_bf(img=img.to(bf), img_ids=img_ids.to(bf), txt=txt_b, txt_ids=txt_ids.to(bf),
+                     timesteps=t.to(bf), y=y_b, guidance=guidance.to(bf))
+    F.mse_loss(pred_bf.float(), target).backward()
+
+    def cos(a, b):
+        a, b = a.double().flatten(), b.double().flatten()
+        return float(a @ b / (a.norm() * b.norm()))
+
+    # how well the reference's OWN bf16 run (what the training scripts execute) tracks its fp32 gradients:
+    # the calibration floor for the bf16 CUDA path (tests require: not worse than this by more than 0.01)
+    pb = dict(dit_bf.named_parameters())
+    bf16_cos = {k: cos(pb[k].grad, g) for k, g in grads.items()}
+    bf16_cos["d_txt"] = cos(txt_b.grad, txt_r.grad)
+    bf16_cos["d_y"] = cos(y_b.grad, y_r.grad)
+    print("  reference bf16-vs-fp32 gradient cosines:", {k: round(v, 4) for k, v in bf16_cos.items()})
     torch.save(dict(kind="flux", cfg=fc.__dict__, seed=seed, key_shapes=ks, img=img, txt=txt, y=y, t=t, guidance=guidance,
                     img_ids=img_ids, txt_ids=txt_ids, target=target, pred=pred.detach(), loss=loss.detach(),
-                    d_img=img_r.grad, d_txt=txt_r.grad, d_y=y_r.grad, grads=grads, pred_bf16=pred_bf),
+                    d_img=img_r.grad, d_txt=txt_r.grad, d_y=y_r.grad, grads=grads, pred_bf16=pred_bf.detach(),
+                    ref_bf16_grad_cos=bf16_cos),
                os.path.join(GOLD, f"flux_{name}.pt"))
 
 

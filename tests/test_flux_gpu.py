@@ -1,0 +1,79 @@
+"""GPU parity of the fused DiT engine (Flux.forward / backward) against the golden vectors minted from the
+reference's own Flux (tests/golden/flux_*.pt, generator: oracle/make_golden.py)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import cosine, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(fx):
+    from genhancer_b200.flux.model import Flux, FluxParams
+    from oracle import genhancer_oracle as O
+
+    cfg = dict(fx["cfg"])
+    cfg["axes_dim"] = list(cfg["axes_dim"])
+    dit = Flux(FluxParams(**cfg))
+    sd = O.synth_state_dict(fx["key_shapes"], fx["seed"])
+    dit.load_state_dict(sd, strict=True)
+    return dit.to("cuda").to(torch.bfloat16), sd
+
+
+@pytest.mark.parametrize("name", ["flux_img.pt", "flux_video.pt"])
+def test_flux_forward_backward_matches_reference(name):
+    fx = load_golden(name)
+    dit, _ = _build(fx)
+    dev, bf = "cuda", torch.bfloat16
+    img = fx["img"].to(dev).to(bf)
+    txt = fx["txt"].to(dev).to(bf).requires_grad_(True)
+    y = fx["y"].to(dev).to(bf).requires_grad_(True)
+    pred = dit(img=img, img_ids=fx["img_ids"].to(dev).to(bf), txt=txt, txt_ids=fx["txt_ids"].to(dev).to(bf),
+               timesteps=fx["t"].to(dev).to(bf), y=y, guidance=fx["guidance"].to(dev).to(bf))
+    assert pred.shape == fx["pred"].shape and pred.dtype == bf
+    # forward: against the reference's fp32 run and its own bf16 run (bf16 noise floor ~1e-2)
+    assert rel_err(pred, fx["pred"]) < 3e-2
+    assert rel_err(pred, fx["pred_bf16"]) < 3e-2
+    loss = F.mse_loss(pred.float(), fx["target"].to(dev))
+    assert abs(loss.item() - fx["loss"].item()) / fx["loss"].item() < 1e-2  # north_star: loss within 1e-2 relative
+    loss.backward()
+    # gradients vs the reference's fp32 gradients.  Floor = what the reference's OWN bf16 run achieves on the same
+    # tensors (stored by oracle/make_golden.py): we must be >= 0.99 or within 0.01 of that floor.
+    floor = fx["ref_bf16_grad_cos"]
+    assert cosine(txt.grad, fx["d_txt"]) > min(0.99, floor["d_txt"] - 0.01)
+    assert cosine(y.grad, fx["d_y"]) > min(0.99, floor["d_y"] - 0.01)
+    params = dict(dit.named_parameters())
+    for k, g in fx["grads"].items():
+        assert params[k].grad is not None, k
+        assert cosine(params[k].grad, g) > min(0.99, floor[k] - 0.01), (k, cosine(params[k].grad, g), floor[k])
+
+
+def test_flux_error_behaviour():
+    fx = load_golden("flux_img.pt")
+    dit, _ = _build(fx)
+    dev, bf = "cuda", torch.bfloat16
+    with pytest.raises(ValueError, match="3 dimensions"):
+        dit(img=fx["img"][0].to(dev), img_ids=fx["img_ids"].to(dev), txt=fx["txt"].to(dev), txt_ids=fx["txt_ids"].to(dev),
+            timesteps=fx["t"].to(dev), y=fx["y"].to(dev), guidance=fx["guidance"].to(dev))
+    with pytest.raises(ValueError, match="guidance"):
+        dit(img=fx["img"].to(dev).to(bf), img_ids=fx["img_ids"].to(dev), txt=fx["txt"].to(dev).to(bf),
+            txt_ids=fx["txt_ids"].to(dev), timesteps=fx["t"].to(dev), y=fx["y"].to(dev).to(bf), guidance=None)
+
+
+def test_flux_grad_accumulation_doubles():
+    fx = load_golden("flux_img.pt")
+    dit, _ = _build(fx)
+    dev, bf = "cuda", torch.bfloat16
+
+    def run():
+        pred = dit(img=fx["img"].to(dev).to(bf), img_ids=fx["img_ids"].to(dev), txt=fx["txt"].to(dev).to(bf),
+                   txt_ids=fx["txt_ids"].to(dev), timesteps=fx["t"].to(dev).to(bf), y=fx["y"].to(dev).to(bf),
+                   guidance=fx["guidance"].to(dev).to(bf))
+        F.mse_loss(pred.float(), fx["target"].to(dev)).backward()
+
+    run()
+    g1 = {k: p.grad.float().clone() for k, p in dit.named_parameters()}
+    run()
+    for k, p in dit.named_parameters():
+        assert rel_err(p.grad.float(), 2 * g1[k]) < 2e-2, k
