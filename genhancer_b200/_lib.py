@@ -52,6 +52,15 @@ class AttnOut(C.Structure):
                 ("n_split", C.c_int32)]
 
 
+class ConvArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("w", C.c_void_p), ("y", C.c_void_p), ("y_dtype", C.c_int32),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+                ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+                ("Ho", C.c_int32), ("Wo", C.c_int32),
+                ("bias", C.c_void_p), ("bias_dtype", C.c_int32), ("act", C.c_int32),
+                ("residual", C.c_void_p), ("res_dtype", C.c_int32)]
+
+
 _vp, _i64, _i32, _f32, _f64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_double
 _rv, _at, _ao = C.POINTER(RowsView), C.POINTER(AttnTensor), C.POINTER(AttnOut)
 
@@ -80,6 +89,15 @@ SIGNATURES: dict[str, list] = {
     "gh_flash_attn_fwd": [_at, _at, _at, _i32, _i32, _i32, _i32, _i32, _f32, _ao, _vp, _vp],
     "gh_flash_attn_bwd": [_at, _at, _at, _ao, _ao, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _at, _at, _at, _vp, _vp,
                           _vp],
+    "gh_conv2d_nhwc": [C.POINTER(ConvArgs), _vp],
+    "gh_patch_im2col": [_vp, _vp, _i32, _i32, _i32, _i64, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp],
+    "gh_im2col3x3_c3": [_vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp],
+    "gh_embed_assemble": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "gh_groupnorm_swish_nhwc": [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _f32, _i32, _vp, _vp],
+    "gh_softmax_rows": [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp],
+    "gh_ae_sample_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp],
+    "gh_sumsq_accum": [_vp, _i32, _i64, _vp, _vp],
+    "gh_adamw_step": [_vp, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _f32, _f32, _vp],
 }
 
 _lib = None

@@ -1,0 +1,258 @@
+"""CLIP / SigLIP vision towers on the sm_100a kernels, with HF-compatible module trees and state_dict keys.
+
+The reference does not contain the tower: it calls HF ``transformers`` (pinned 4.43.3) --
+``CLIPModel`` / ``SiglipModel`` ``.vision_model`` (modeling_clip.py:138-218,261-385,647-696;
+modeling_siglip.py:116-187,252-362,586-654).  These classes reproduce that arithmetic:
+
+  patch conv (im2col gather + tcgen05 GEMM) -> [cls] + pos -> [pre_layrnorm] -> N x {LN1 -> fused QKV GEMM ->
+  flash attention straight off the QKV buffer -> out_proj GEMM (+residual) -> LN2 -> fc1 GEMM (+act) ->
+  fc2 GEMM (+residual)} -> post_layernorm / MAP head.
+
+Stage 1 runs the tower frozen (no activations kept).  Compute is bf16 with fp32 accumulation; parameters stay
+fp32 in the module (as the reference's ``class_model.to(torch.float32)``, build_CLIP.py:9) and bf16 operand
+copies are cached until the parameters change.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from .. import kernels as K
+from ..kernels import ACT_GELU_TANH, ACT_QUICK_GELU, BF16, F32
+
+
+@dataclass
+class TowerConfig:
+    kind: str = "clip"          # "clip" (OpenAI / MetaCLIP) | "siglip"
+    hidden_size: int = 1024
+    num_hidden_layers: int = 24
+    num_attention_heads: int = 16
+    intermediate_size: int = 4096
+    image_size: int = 224
+    patch_size: int = 14
+    projection_dim: int = 768
+    layer_norm_eps: float = 1e-5
+    hidden_act: str = "quick_gelu"
+
+    @property
+    def grid(self) -> int:
+        return self.image_size // self.patch_size
+
+    @property
+    def num_tokens(self) -> int:
+        return self.grid ** 2 + (1 if self.kind == "clip" else 0)
+
+
+def openai_vit_l14(image_size: int) -> TowerConfig:
+    return TowerConfig("clip", 1024, 24, 16, 4096, image_size, 14, 768, 1e-5, "quick_gelu")
+
+
+def metaclip_h14(image_size: int = 224) -> TowerConfig:
+    return TowerConfig("clip", 1280, 32, 16, 5120, image_size, 14, 1024, 1e-5, "quick_gelu")
+
+
+def siglip_so400m(image_size: int) -> TowerConfig:
+    return TowerConfig("siglip", 1152, 27, 16, 4304, image_size, 14, 1152, 1e-6, "gelu_pytorch_tanh")
+
+
+class _Attn(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.q_proj, self.k_proj, self.v_proj, self.out_proj = (nn.Linear(d, d) for _ in range(4))
+
+
+class _MLP(nn.Module):
+    def __init__(self, d, m):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(d, m), nn.Linear(m, d)
+
+
+class _Layer(nn.Module):
+    def __init__(self, c: TowerConfig):
+        super().__init__()
+        self.layer_norm1 = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+        self.self_attn = _Attn(c.hidden_size)
+        self.layer_norm2 = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+        self.mlp = _MLP(c.hidden_size, c.intermediate_size)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, c: TowerConfig):
+        super().__init__()
+        self.layers = nn.ModuleList([_Layer(c) for _ in range(c.num_hidden_layers)])
+
+
+class _Embeddings(nn.Module):
+    def __init__(self, c: TowerConfig):
+        super().__init__()
+        if c.kind == "clip":
+            self.class_embedding = nn.Parameter(torch.randn(c.hidden_size))
+        self.patch_embedding = nn.Conv2d(3, c.hidden_size, c.patch_size, c.patch_size, bias=(c.kind == "siglip"))
+        self.position_embedding = nn.Embedding(c.num_tokens, c.hidden_size)
+
+
+class _MapHead(nn.Module):  # SiglipMultiheadAttentionPoolingHead parameter tree
+    def __init__(self, c: TowerConfig):
+        super().__init__()
+        self.probe = nn.Parameter(torch.randn(1, 1, c.hidden_size))
+        self.attention = nn.MultiheadAttention(c.hidden_size, c.num_attention_heads, batch_first=True)
+        self.layernorm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+        self.mlp = _MLP(c.hidden_size, c.intermediate_size)
+
+
+class VisionTransformer(nn.Module):
+    """`.vision_model` of the HF model: call -> object with .last_hidden_state [B,T,D] and .pooler_output [B,D]."""
+
+    def __init__(self, c: TowerConfig):
+        super().__init__()
+        self.config = c
+        self.embeddings = _Embeddings(c)
+        if c.kind == "clip":
+            self.pre_layrnorm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)  # (sic) HF spelling
+        self.encoder = _Encoder(c)
+        self.post_layernorm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+        if c.kind == "siglip":
+            self.head = _MapHead(c)
+        self._cache = None
+        self._cache_key = None
+        self._init_weights()
+
+    def _init_weights(self):  # HF _init_weights flavour (modeling_clip.py:403-459): small normal, unit LayerNorm
+        c = self.config
+        std = c.hidden_size ** -0.5
+        with torch.no_grad():
+            for n, p in self.named_parameters():
+                if "norm" in n:
+                    p.fill_(1.0) if n.endswith("weight") else p.zero_()
+                elif n.endswith("bias"):
+                    p.zero_()
+                elif "class_embedding" in n or "probe" in n:
+                    p.normal_(0, std)
+                elif "position_embedding" in n or "patch_embedding" in n:
+                    p.normal_(0, 0.02)
+                else:
+                    p.normal_(0, std * (2 * c.num_hidden_layers) ** -0.5 if ("out_proj" in n or "fc2" in n) else std)
+
+    # ---- bf16 operand cache -------------------------------------------------------------------
+    def _prepared(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._cache is not None and self._cache_key == key:
+            return self._cache
+        c = self.config
+        D, p = c.hidden_size, c.patch_size
+        kdim = 3 * p * p
+        ld = (kdim + 7) // 8 * 8
+        W = {}
+        pw = torch.zeros(D, ld, dtype=BF16, device=self.embeddings.patch_embedding.weight.device)
+        pw[:, :kdim] = self.embeddings.patch_embedding.weight.detach().reshape(D, kdim).to(BF16)
+        W["patch_w"], W["patch_ld"] = pw[:, :kdim], ld
+        W["patch_b"] = (self.embeddings.patch_embedding.bias.detach().float().contiguous()
+                        if self.embeddings.patch_embedding.bias is not None else None)
+        W["cls"] = self.embeddings.class_embedding.detach().float().contiguous() if c.kind == "clip" else None
+        W["pos"] = self.embeddings.position_embedding.weight.detach().float().contiguous()
+        f = lambda t: t.detach().float().contiguous()
+        b16 = lambda t: t.detach().to(BF16).contiguous()
+        if c.kind == "clip":
+            W["pre_ln"] = (f(self.pre_layrnorm.weight), f(self.pre_layrnorm.bias))
+        W["layers"] = []
+        for l in self.encoder.layers:
+            a = l.self_attn
+            W["layers"].append(dict(
+                ln1=(f(l.layer_norm1.weight), f(l.layer_norm1.bias)), ln2=(f(l.layer_norm2.weight), f(l.layer_norm2.bias)),
+                wqkv=b16(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)),
+                bqkv=f(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0)),
+                wo=b16(a.out_proj.weight), bo=f(a.out_proj.bias),
+                w1=b16(l.mlp.fc1.weight), b1=f(l.mlp.fc1.bias), w2=b16(l.mlp.fc2.weight), b2=f(l.mlp.fc2.bias)))
+        W["post_ln"] = (f(self.post_layernorm.weight), f(self.post_layernorm.bias))
+        self._cache, self._cache_key = W, key
+        return W
+
+    def forward(self, pixel_values, output_hidden_states: bool = False, _norm=None, **_):
+        """pixel_values: normalised images [B,3,S,S] (any float dtype).  `_norm=(mean3, std3)` lets the fused
+        training step hand over raw [0,1] images and fold transforms.Normalize into the im2col gather."""
+        c = self.config
+        if c.hidden_size // c.num_attention_heads != 64:
+            raise NotImplementedError(
+                f"head_dim {c.hidden_size // c.num_attention_heads}: the sm_100a ViT attention kernel is built for 64 "
+                "(OpenAI / MetaCLIP ViT-L/14); SigLIP-so400m (72) and ViT-H (80) are the next rows of SURVEY.md 8(a)")
+        W = self._prepared()
+        B = pixel_values.shape[0]
+        D, H, T = c.hidden_size, c.num_attention_heads, c.num_tokens
+        d = D // H
+        act = ACT_QUICK_GELU if c.hidden_act == "quick_gelu" else ACT_GELU_TANH
+        img = pixel_values.float().contiguous()
+        mean, std = _norm if _norm is not None else (None, None)
+        A = K.patch_im2col(img, c.patch_size, W["patch_ld"], mean, std)
+        patch = K.gemm(A, W["patch_w"], bias=W["patch_b"])
+        x = K.embed_assemble(patch, W["cls"], W["pos"], B, T, D)
+        if c.kind == "clip":
+            x, _, _ = K.layernorm_fwd(x, weight=W["pre_ln"][0], bias=W["pre_ln"][1], eps=c.layer_norm_eps, save_stats=False)
+        for L in W["layers"]:
+            h, _, _ = K.layernorm_fwd(x, weight=L["ln1"][0], bias=L["ln1"][1], eps=c.layer_norm_eps, save_stats=False)
+            qkv = K.gemm(h.view(-1, D), L["wqkv"], bias=L["bqkv"]).view(B, T, 3, H, d)
+            q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+            attn = torch.empty(B, T, D, dtype=BF16, device=x.device)
+            K.flash_attn_fwd(q, k, v, d ** -0.5, attn, want_lse=False)
+            x = K.gemm(attn.view(-1, D), L["wo"], bias=L["bo"], residual=x.view(-1, D)).view(B, T, D)
+            h, _, _ = K.layernorm_fwd(x, weight=L["ln2"][0], bias=L["ln2"][1], eps=c.layer_norm_eps, save_stats=False)
+            a = K.gemm(h.view(-1, D), L["w1"], bias=L["b1"], act=act)
+            x = K.gemm(a, L["w2"], bias=L["b2"], residual=x.view(-1, D)).view(B, T, D)
+        if c.kind == "clip":
+            pooled, _, _ = K.layernorm_fwd(x[:, 0:1], weight=W["post_ln"][0], bias=W["post_ln"][1], eps=c.layer_norm_eps,
+                                           save_stats=False)
+            return SimpleNamespace(last_hidden_state=x, pooler_output=pooled[:, 0], hidden_states=None)
+        raise NotImplementedError("SigLIP MAP pooling head: next row of SURVEY.md 8(a)")
+
+
+class VisionLanguageModel(nn.Module):
+    """Stands where HF ``CLIPModel`` / ``SiglipModel`` stands in the reference wrappers (``wrapper.model``):
+    `.vision_model`, `.visual_projection`, `.text_projection` (the 336 scripts re-wrap both projection weights as
+    contiguous Parameters, train_OpenAICLIP_video_stage1.py:197-200).  The text tower is not on the path."""
+
+    def __init__(self, c: TowerConfig):
+        super().__init__()
+        self.config = c
+        self.vision_model = VisionTransformer(c)
+        if c.kind == "clip":
+            self.visual_projection = nn.Linear(c.hidden_size, c.projection_dim, bias=False)
+            self.text_projection = nn.Linear(8, c.projection_dim, bias=False)  # placeholder: text tower unused
+            with torch.no_grad():
+                self.visual_projection.weight.normal_(0, c.hidden_size ** -0.5)
+
+    def get_image_features(self, pixel_values):
+        out = self.vision_model(pixel_values)
+        return project(self, out.pooler_output)
+
+    @classmethod
+    def from_pretrained(cls, path: str, c: TowerConfig):
+        """Load the vision-side tensors of an HF checkpoint directory (pytorch_model.bin / model.safetensors)."""
+        import os
+        m = cls(c)
+        sd = None
+        for fn in ("model.safetensors", "pytorch_model.bin"):
+            fp = os.path.join(path, fn)
+            if os.path.exists(fp):
+                if fn.endswith(".safetensors"):
+                    from safetensors.torch import load_file
+                    sd = load_file(fp)
+                else:
+                    sd = torch.load(fp, map_location="cpu", weights_only=True)
+                break
+        if sd is None:
+            raise FileNotFoundError(f"no model.safetensors / pytorch_model.bin under {path}")
+        own = m.state_dict()
+        picked = {k: v for k, v in sd.items() if k in own and tuple(v.shape) == tuple(own[k].shape)}
+        missing = [k for k in own if k not in picked and not k.startswith("text_projection")]
+        if missing:
+            raise RuntimeError(f"checkpoint {path} lacks vision tensors: {missing[:5]} ...")
+        m.load_state_dict(picked, strict=False)
+        return m
+
+
+def project(model: VisionLanguageModel, pooled: torch.Tensor) -> torch.Tensor:
+    """visual_projection (no bias) on the tcgen05 GEMM; frozen in stage 1."""
+    w = model.visual_projection.weight
+    return K.gemm(pooled.to(BF16).contiguous(), w.detach().to(BF16).contiguous())

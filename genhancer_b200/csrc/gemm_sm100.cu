@@ -74,7 +74,7 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
   GH_REQUIRE(a->a && a->b && a->d, GH_ERR_NULL, "gh_gemm_bf16: a/b/d must be non-NULL");
   GH_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, GH_ERR_BAD_SHAPE, "gh_gemm_bf16: M,N,K must be positive (%d,%d,%d)",
              a->M, a->N, a->K);
-  GH_REQUIRE(a->N % 8 == 0, GH_ERR_BAD_SHAPE, "gh_gemm_bf16: N=%d must be a multiple of 8", a->N);
+  GH_REQUIRE(a->N % 4 == 0, GH_ERR_BAD_SHAPE, "gh_gemm_bf16: N=%d must be a multiple of 4", a->N);
   GH_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0 && a->ldd % 4 == 0, GH_ERR_ALIGN,
              "gh_gemm_bf16: lda/ldb must be multiples of 8, ldd of 4 (%lld,%lld,%lld)", (long long)a->lda,
              (long long)a->ldb, (long long)a->ldd);

@@ -1,0 +1,300 @@
+// genhancer_b200 -- HBM-bound kernels around the vision tower and the FLUX autoencoder encoder:
+// im2col gathers feeding the tcgen05 GEMM, GroupNorm(32)+swish on NHWC, row softmax for the AE's
+// single-head mid attention, CLIP token assembly, DiagonalGaussian sampling + 2x2 patchify.
+#include "common.cuh"
+#include "internal.h"
+
+namespace gh {
+
+using bf16 = __nv_bfloat16;
+
+// ---------------------------------------------------------------------------
+// patch-embed im2col (stride == kernel, so it is a pure gather): image fp32 NCHW [B,3,S,S] ->
+// bf16 [B*G*G, ld] with k = c*p*p + i*p + j (the flattening of Conv2d weight [D,3,p,p]); optional
+// per-channel normalisation (x - mean) / std fused in.  One CTA per (b, patch-row).
+// HF CLIPVisionEmbeddings.patch_embedding, modeling_clip.py:147-153,208-209.
+// ---------------------------------------------------------------------------
+__global__ void patch_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int S, int p, int G,
+                                    int64_t ld, float m0, float m1, float m2, float is0, float is1, float is2) {
+  const int b = blockIdx.y, py = blockIdx.x;
+  const float mean[3] = {m0, m1, m2}, istd[3] = {is0, is1, is2};
+  const int row_elems = G * p;  // pixels of one image row that belong to patches
+  for (int ci = 0; ci < 3 * p; ++ci) {
+    const int c = ci / p, i = ci % p;
+    const float* src = img + ((static_cast<int64_t>(b) * 3 + c) * S + py * p + i) * S;
+    for (int x = threadIdx.x; x < row_elems; x += blockDim.x) {
+      const int px = x / p, j = x - px * p;
+      const float v = (src[x] - mean[c]) * istd[c];
+      out[(static_cast<int64_t>(b) * G * G + py * G + px) * ld + c * p * p + i * p + j] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// 3x3 / pad 1 im2col for the AE's conv_in (Cin = 3): image fp32 NCHW -> bf16 [B*H*W, 32], k = (kh*3+kw)*3 + c,
+// columns 27..31 zero; normalisation fused.  autoencoder.py:126.
+__global__ void im2col3x3_c3_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int H, int W,
+                                    float mean, float istd) {
+  const int64_t n = static_cast<int64_t>(B) * H * W;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = static_cast<int>(i % W);
+  const int y = static_cast<int>((i / W) % H);
+  const int b = static_cast<int>(i / (static_cast<int64_t>(W) * H));
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int yy = y + kh - 1, xx = x + kw - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          v[(kh * 3 + kw) * 3 + c] = (img[((static_cast<int64_t>(b) * 3 + c) * H + yy) * W + xx] - mean) * istd;
+      }
+    }
+  uint4* dst = reinterpret_cast<uint4*>(out + i * 32);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+    dst[q] = u;
+  }
+}
+
+// CLIP / SigLIP token assembly: out[b, t] = (t < has_cls ? cls : patch[b, t - has_cls]) + pos[t]
+// (modeling_clip.py:210-217).  8 channels per thread.
+__global__ void embed_assemble_kernel(const bf16* __restrict__ patch, const float* __restrict__ cls,
+                                      const float* __restrict__ pos, bf16* __restrict__ out, int B, int T, int D,
+                                      int has_cls) {
+  const int64_t n8 = static_cast<int64_t>(B) * T * D / 8;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int d = static_cast<int>((i * 8) % D);
+  const int t = static_cast<int>((i * 8 / D) % T);
+  const int b = static_cast<int>(i * 8 / (static_cast<int64_t>(D) * T));
+  float v[8];
+  if (t < has_cls) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = cls[d + j];
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(patch + (static_cast<int64_t>(b) * (T - has_cls) + t - has_cls) * D + d);
+    const float2 a = unpack_bf16x2(u.x), c2 = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), g = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = c2.x; v[3] = c2.y; v[4] = e.x; v[5] = e.y; v[6] = g.x; v[7] = g.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] += pos[static_cast<int64_t>(t) * D + d + j];
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
+// ---------------------------------------------------------------------------
+// GroupNorm(32 groups, eps) on NHWC bf16: pass 1 = per-(sample, group) sum / sum-of-squares (fp32 in-block,
+// fp64 across blocks), pass 2 = normalise + affine (+ swish).  autoencoder.py:21-22,62-78,156,177-178.
+// algorithmic bytes / element: 2 (stats read) + 2 (apply read) + 2 (write)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats,
+                                                       int64_t HW, int C, int pix_per_cta) {
+  __shared__ float red[32][2];
+  const int b = blockIdx.y;
+  if (threadIdx.x < 64) red[threadIdx.x >> 1][threadIdx.x & 1] = 0.f;
+  __syncthreads();
+  const int c8 = C / 8;
+  const int cpg = C / 32;
+  const int tpp = c8;                       // threads per pixel
+  const int ppi = blockDim.x / tpp;         // pixels per iteration (C <= 2048)
+  const int my_c = (threadIdx.x % tpp) * 8;
+  const int my_p = threadIdx.x / tpp;
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_cta;
+  const int64_t p1 = min(p0 + pix_per_cta, HW);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};  // one slot per channel pair (cpg >= 2)
+  if (my_p < ppi) {
+    for (int64_t pix = p0 + my_p; pix < p1; pix += ppi) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(b) * HW + pix) * C + my_c);
+      const float2 a = unpack_bf16x2(u.x), c2 = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), g = unpack_bf16x2(u.w);
+      s[0] += a.x + a.y;   ss[0] += a.x * a.x + a.y * a.y;
+      s[1] += c2.x + c2.y; ss[1] += c2.x * c2.x + c2.y * c2.y;
+      s[2] += e.x + e.y;   ss[2] += e.x * e.x + e.y * e.y;
+      s[3] += g.x + g.y;   ss[3] += g.x * g.x + g.y * g.y;
+    }
+    if (cpg >= 8) {  // all 8 channels of this thread sit in one group
+      atomicAdd(&red[my_c / cpg][0], s[0] + s[1] + s[2] + s[3]);
+      atomicAdd(&red[my_c / cpg][1], ss[0] + ss[1] + ss[2] + ss[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&red[(my_c + 2 * j) / cpg][0], s[j]);
+        atomicAdd(&red[(my_c + 2 * j) / cpg][1], ss[j]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64)
+    atomicAdd(stats + (static_cast<int64_t>(b) * 32 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1),
+              static_cast<double>(red[threadIdx.x >> 1][threadIdx.x & 1]));
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ stats,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       bf16* __restrict__ y, int64_t HW, int C, float eps, int swish,
+                                                       int64_t n8) {
+  const int cpg = C / 32;
+  const double cnt = static_cast<double>(HW) * cpg;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int c = static_cast<int>((i * 8) % C);
+    const int b = static_cast<int>(i * 8 / (HW * C));
+    const uint4 u = reinterpret_cast<const uint4*>(x)[i];
+    const float2 a = unpack_bf16x2(u.x), c2 = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), g = unpack_bf16x2(u.w);
+    float v[8] = {a.x, a.y, c2.x, c2.y, e.x, e.y, g.x, g.y};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int grp = (c + q * 2) / cpg;
+      const double sm = stats[(static_cast<int64_t>(b) * 32 + grp) * 2], sq = stats[(static_cast<int64_t>(b) * 32 + grp) * 2 + 1];
+      const double mean = sm / cnt;
+      const float rstd = rsqrtf(fmaxf(static_cast<float>(sq / cnt - mean * mean), 0.f) + eps);
+      const float mu = static_cast<float>(mean);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int cc = c + q * 2 + j;
+        float t = (v[q * 2 + j] - mu) * rstd * w[cc] + bias[cc];
+        if (swish) t = t * sigmoidf_(t);
+        v[q * 2 + j] = t;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(y)[i] = o;
+  }
+}
+
+// row softmax: p[r, :n] = softmax(scale * s[r, :n]) (fp32 in, bf16 out), one warp per row; pad columns [n, ld_out) = 0
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, int64_t ld_in, bf16* __restrict__ p,
+                                                           int64_t ld_out, int rows, int n, float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  const float* sr = s + static_cast<int64_t>(r) * ld_in;
+  float mx = -INFINITY;
+  for (int c = lane; c < n; c += 32) mx = fmaxf(mx, sr[c] * scale);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < n; c += 32) sum += __expf(sr[c] * scale - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  bf16* pr = p + static_cast<int64_t>(r) * ld_out;
+  for (int c = lane; c < ld_out; c += 32) pr[c] = __float2bfloat16_rn(c < n ? __expf(sr[c] * scale - mx) * inv : 0.f);
+}
+
+// DiagonalGaussian sample + scale/shift + 2x2 patchify (autoencoder.py:268-274,302-305; sampling.py:26):
+// moments fp32 NHWC [B,h,w,2z] , noise fp32 NCHW [B,z,h,w] -> x1 fp32 [B,(h/2)(w/2), z*4], inner index c*4+ph*2+pw
+__global__ void ae_sample_patchify_kernel(const float* __restrict__ mom, const float* __restrict__ noise,
+                                          float* __restrict__ x1, int B, int h, int w, int z, float scale_factor,
+                                          float shift_factor) {
+  const int64_t n = static_cast<int64_t>(B) * z * h * w;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // i indexes the OUTPUT (coalesced writes)
+  const int inner = static_cast<int>(i % (z * 4));
+  const int64_t tok = i / (z * 4);
+  const int w2 = w / 2, h2 = h / 2;
+  const int px = static_cast<int>(tok % w2), py = static_cast<int>((tok / w2) % h2);
+  const int b = static_cast<int>(tok / (static_cast<int64_t>(w2) * h2));
+  const int c = inner / 4, ph = (inner / 2) & 1, pw = inner & 1;
+  const int yy = py * 2 + ph, xx = px * 2 + pw;
+  const float* m = mom + ((static_cast<int64_t>(b) * h + yy) * w + xx) * (2 * z);
+  const float mean = m[c], logvar = m[z + c];
+  const float eps = noise[((static_cast<int64_t>(b) * z + c) * h + yy) * w + xx];
+  x1[i] = scale_factor * (mean + __expf(0.5f * logvar) * eps - shift_factor);
+}
+
+static inline int grid1d(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
+
+}  // namespace gh
+
+using namespace gh;
+
+extern "C" int gh_patch_im2col(const float* img, void* out_bf16, int32_t B, int32_t S, int32_t patch, int64_t ld,
+                               const float* mean3, const float* std3, void* stream) {
+  GH_REQUIRE(img && out_bf16, GH_ERR_NULL, "gh_patch_im2col: NULL pointer");
+  GH_REQUIRE(B > 0 && S > 0 && patch > 0 && S / patch > 0 && ld >= 3 * patch * patch, GH_ERR_BAD_SHAPE,
+             "gh_patch_im2col: bad shape");
+  const int G = S / patch;
+  float m[3] = {0, 0, 0}, is[3] = {1, 1, 1};
+  if (mean3 && std3)
+    for (int c = 0; c < 3; ++c) { m[c] = mean3[c]; is[c] = 1.f / std3[c]; }  // host pointers (3 floats)
+  patch_im2col_kernel<<<dim3(G, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, static_cast<bf16*>(out_bf16), S, patch, G, ld, m[0], m[1], m[2], is[0], is[1], is[2]);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+extern "C" int gh_im2col3x3_c3(const float* img, void* out_bf16, int32_t B, int32_t H, int32_t W, float mean,
+                               float std, void* stream) {
+  GH_REQUIRE(img && out_bf16 && aligned16(out_bf16), GH_ERR_NULL, "gh_im2col3x3_c3: NULL / misaligned pointer");
+  GH_REQUIRE(B > 0 && H > 0 && W > 0 && std != 0.f, GH_ERR_BAD_SHAPE, "gh_im2col3x3_c3: bad shape");
+  const int64_t n = static_cast<int64_t>(B) * H * W;
+  im2col3x3_c3_kernel<<<grid1d(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, static_cast<bf16*>(out_bf16), B, H, W, mean, 1.f / std);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+extern "C" int gh_embed_assemble(const void* patch_bf16, const float* cls, const float* pos, void* out_bf16, int32_t B,
+                                 int32_t T, int32_t D, int32_t has_cls, void* stream) {
+  GH_REQUIRE(patch_bf16 && pos && out_bf16 && (!has_cls || cls), GH_ERR_NULL, "gh_embed_assemble: NULL pointer");
+  GH_REQUIRE(B > 0 && T > has_cls && D % 8 == 0 && (has_cls == 0 || has_cls == 1), GH_ERR_BAD_SHAPE,
+             "gh_embed_assemble: bad shape");
+  const int64_t n8 = static_cast<int64_t>(B) * T * D / 8;
+  embed_assemble_kernel<<<grid1d(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(patch_bf16), cls, pos, static_cast<bf16*>(out_bf16), B, T, D, has_cls);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+extern "C" int gh_groupnorm_swish_nhwc(const void* x, void* y, int32_t B, int64_t HW, int32_t C, const float* weight,
+                                       const float* bias, float eps, int32_t swish, void* ws_stats_f64, void* stream) {
+  GH_REQUIRE(x && y && weight && bias && ws_stats_f64, GH_ERR_NULL, "gh_groupnorm_swish_nhwc: NULL pointer");
+  GH_REQUIRE(B > 0 && HW > 0 && C % 64 == 0 && C <= 2048, GH_ERR_BAD_SHAPE,
+             "gh_groupnorm_swish_nhwc: C=%d must be a multiple of 64 (32 groups of >= 2 channels), <= 2048", C);
+  GH_REQUIRE(aligned16(x) && aligned16(y), GH_ERR_ALIGN, "gh_groupnorm_swish_nhwc: 16B alignment");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GH_CHECK_CUDA(cudaMemsetAsync(ws_stats_f64, 0, static_cast<size_t>(B) * 32 * 2 * sizeof(double), s));
+  int pix_per_cta = 256;
+  while ((HW + pix_per_cta - 1) / pix_per_cta * B > 16L * num_sms() && pix_per_cta < 8192) pix_per_cta *= 2;
+  dim3 grid(static_cast<unsigned>((HW + pix_per_cta - 1) / pix_per_cta), B);
+  gn_stats_kernel<<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<double*>(ws_stats_f64), HW, C, pix_per_cta);
+  GH_CHECK_CUDA(cudaGetLastError());
+  const int64_t n8 = static_cast<int64_t>(B) * HW * C / 8;
+  const int64_t want = (n8 + 255) / 256;
+  const int g2 = static_cast<int>(want < 16L * num_sms() ? want : 16L * num_sms());
+  gn_apply_kernel<<<g2, 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<const double*>(ws_stats_f64), weight, bias,
+                                     static_cast<bf16*>(y), HW, C, eps, swish, n8);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+extern "C" int gh_softmax_rows(const float* s, int64_t ld_in, void* p_bf16, int64_t ld_out, int32_t rows, int32_t n,
+                               float scale, void* stream) {
+  GH_REQUIRE(s && p_bf16, GH_ERR_NULL, "gh_softmax_rows: NULL pointer");
+  GH_REQUIRE(rows > 0 && n > 0 && ld_in >= n && ld_out >= n, GH_ERR_BAD_SHAPE, "gh_softmax_rows: bad shape");
+  softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(s, ld_in, static_cast<bf16*>(p_bf16),
+                                                                                    ld_out, rows, n, scale);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+extern "C" int gh_ae_sample_patchify(const float* moments_nhwc, const float* noise_nchw, float* x1, int32_t B, int32_t h,
+                                     int32_t w, int32_t z, float scale_factor, float shift_factor, void* stream) {
+  GH_REQUIRE(moments_nhwc && noise_nchw && x1, GH_ERR_NULL, "gh_ae_sample_patchify: NULL pointer");
+  GH_REQUIRE(B > 0 && h > 0 && w > 0 && z > 0 && h % 2 == 0 && w % 2 == 0, GH_ERR_BAD_SHAPE,
+             "gh_ae_sample_patchify: latent extent must be even (got %dx%d)", h, w);
+  const int64_t n = static_cast<int64_t>(B) * z * h * w;
+  ae_sample_patchify_kernel<<<grid1d(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      moments_nhwc, noise_nchw, x1, B, h, w, z, scale_factor, shift_factor);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}

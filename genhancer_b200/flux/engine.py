@@ -42,9 +42,11 @@ class GradSink:
     """Where parameter gradients go.  ``big(name)`` returns the bf16/fp32 [N,K] grad tensor a wgrad GEMM writes
     (accumulating when ``accumulate``); ``small(name)`` returns an fp32 accumulator view flushed by ``flush()``."""
 
-    def __init__(self, params: dict[str, torch.Tensor], accumulate: bool):
+    def __init__(self, params: dict[str, torch.Tensor], accumulate: bool, on_ready=None):
         self.params = params
         self.accumulate = accumulate
+        self.on_ready = on_ready
+        self._flushed: set[str] = set()
         self._small: dict[str, torch.Tensor] = {}
         self._touched: set[str] = set()
         n_small = sum(p.numel() for n, p in params.items() if p.dim() == 1 and p.requires_grad)
@@ -71,13 +73,20 @@ class GradSink:
     def small(self, name: str) -> torch.Tensor:
         return self._small[name]
 
-    def flush(self) -> None:
+    def flush(self, prefix: str | None = None) -> None:
+        """Write the fp32 accumulators of the 1-D parameters under ``prefix`` (all when None) into ``.grad`` and
+        tell ``on_ready`` (the data-parallel bucket launcher) that every gradient under ``prefix`` is final."""
         for n, acc in self._small.items():
+            if n in self._flushed or (prefix is not None and not n.startswith(prefix)):
+                continue
+            self._flushed.add(n)
             p = self.params[n]
             first = p.grad is None or not self.accumulate
             if p.grad is None:
                 p.grad = torch.empty_like(p)
             K.accum_cast(acc, p.grad, 1.0, accumulate=not first)
+        if self.on_ready is not None and prefix is not None:
+            self.on_ready(prefix)
 
 
 def _lin_fwd(x2d, w, b, **kw):
@@ -263,6 +272,7 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
     dx = torch.zeros(B, L, C, dtype=BF16, device=dev)  # txt rows of the last single block get no gradient
     adaln_bwd("final.norm", dhf.view(B, Li, C), S["final.mod"], 0, dmodf, out=dx[:, Lt:])
     mod_bwd(dmodf, "final_layer.adaLN_modulation.1.weight", "final_layer.adaLN_modulation.1.bias")
+    sink.flush("final_layer.")
 
     # ---- single-stream blocks ----
     for bi in reversed(range(cfg.depth_single_blocks)):
@@ -298,6 +308,7 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
         dh = _lin_bwd(dl1, h.view(-1, C), f"{p}.linear1.weight", f"{p}.linear1.bias", P, sink)
         dx = adaln_bwd(f"{p}.pre_norm", dh.view(B, L, C), m, 0, dmod, dres=dx)
         mod_bwd(dmod, f"{p}.modulation.lin.weight", f"{p}.modulation.lin.bias")
+        sink.flush(p + ".")
 
     # ---- split back into the two streams ----
     dxs = {"txt": dx[:, :Lt], "img": dx[:, Lt:]}
@@ -339,6 +350,7 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
             dh = _lin_bwd(dqkv.view(-1, 3 * C), h.view(-1, C), f"{p}.{s}_attn.qkv.weight", f"{p}.{s}_attn.qkv.bias", P, sink)
             dxs[s] = adaln_bwd(f"{p}.{s}_norm1", dh.view(B, rpb, C), m, 0, dmods[s], dres=dx_mid[s])
             mod_bwd(dmods[s], f"{p}.{s}_mod.lin.weight", f"{p}.{s}_mod.lin.bias")
+        sink.flush(p + ".")
 
     # ---- input projections and the conditioning vector ----
     d_img = _lin_bwd(dxs["img"].reshape(-1, C), S["img2d"], "img_in.weight", "img_in.bias", P, sink, need_dx=need_dimg)
@@ -356,6 +368,6 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
                        need_dx=want_in)
         if want_in:
             d_y = din
-    sink.flush()
+    sink.flush("")
     return (d_img.view(B, Li, -1) if d_img is not None else None,
             d_txt.view(B, Lt, -1) if d_txt is not None else None, d_y)

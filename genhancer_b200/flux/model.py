@@ -44,7 +44,10 @@ class _FluxFn(torch.autograd.Function):
     def backward(ctx, dpred):
         model = ctx.model
         P = model._param_dict()
-        sink = engine.GradSink(P, accumulate=True)
+        # FusedAdamW.zero_grad() marks the flat gradient buffer "overwrite on next backward" instead of memsetting it
+        accumulate = not model._grad_overwrite
+        model._grad_overwrite = False
+        sink = engine.GradSink(P, accumulate=accumulate, on_ready=model._on_grads_ready)
         d_img, d_txt, d_y = engine.flux_backward(P, model.params, ctx.ectx, dpred, sink, need_dimg=ctx.needs[0],
                                                  need_dtxt=ctx.needs[1], need_dy=ctx.needs[2])
         ctx.ectx = None
@@ -81,6 +84,8 @@ class Flux(nn.Module):
             SingleStreamBlock(self.hidden_size, self.num_heads, mlp_ratio=params.mlp_ratio)
             for _ in range(params.depth_single_blocks)])
         self.final_layer = LastLayer(self.hidden_size, 1, self.out_channels)
+        self._grad_overwrite = False   # set by optim.FusedAdamW.zero_grad()
+        self._on_grads_ready = None    # set by parallel.DataParallel: fires a bucket all-reduce per finished block
         self.gradient_checkpointing = False  # reference's branch is dead code; nothing is recomputed
         if pe_dim != 128:
             raise NotImplementedError("the sm_100a attention / QK-norm kernels are built for head_dim 128 (flux-dev)")

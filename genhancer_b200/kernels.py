@@ -14,6 +14,7 @@ from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, ACT_SI
                    check)
 
 LAUNCHES = 0
+GEMM_TIMER = None  # bench.py: callable(flops) -> (start_event, stop_event) recorded around every tcgen05 GEMM/conv launch
 BF16 = torch.bfloat16
 F32 = torch.float32
 
@@ -92,7 +93,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if residual is not None:
         _rowmajor2d(residual, "gemm residual")
         g.residual, g.ld_res, g.res_dtype = residual.data_ptr(), residual.stride(0), _dt(residual)
+    tm = GEMM_TIMER
+    if tm is not None:
+        ev0, ev1 = tm(2.0 * M * N * K)
+        ev0.record()
     check(_lib.lib().gh_gemm_bf16(C.byref(g), _stream()))
+    if tm is not None:
+        ev1.record()
     _count()
     return out
 
@@ -337,6 +344,108 @@ def flash_attn_fwd(q, k, v, scale, out1, out0=None, n_split=0, want_lse=True):
     return lse
 
 
+def conv2d_nhwc(x, w, KH, KW, stride=1, pad=0, Ho=None, Wo=None, bias=None, act=ACT_NONE, residual=None,
+                out_dtype=BF16, out=None):
+    """x bf16 NHWC [B,H,W,Cin]; w bf16 [Cout, KH*KW*Cin] (k = (kh*KW+kw)*Cin + ci) -> [B,Ho,Wo,Cout]."""
+    from ._lib import ConvArgs
+    _ensure(x)
+    assert x.dtype == BF16 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == KH * KW * Cin
+    if Ho is None:
+        Ho = (H + 2 * pad - KH) // stride + 1
+        Wo = (W + 2 * pad - KW) // stride + 1
+    if out is None:
+        out = torch.empty(B, Ho, Wo, Cout, dtype=out_dtype, device=x.device)
+    a = ConvArgs()
+    a.x, a.w, a.y, a.y_dtype = x.data_ptr(), w.data_ptr(), out.data_ptr(), _dt(out)
+    a.B, a.H, a.W, a.Cin, a.Cout, a.KH, a.KW, a.stride, a.pad, a.Ho, a.Wo = B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo
+    if bias is not None:
+        a.bias, a.bias_dtype = bias.data_ptr(), _dt(bias)
+    a.act = act
+    if residual is not None:
+        assert residual.is_contiguous() and tuple(residual.shape) == tuple(out.shape)
+        a.residual, a.res_dtype = residual.data_ptr(), _dt(residual)
+    tm = GEMM_TIMER
+    if tm is not None:
+        ev0, ev1 = tm(2.0 * B * Ho * Wo * Cout * KH * KW * Cin)
+        ev0.record()
+    check(_lib.lib().gh_conv2d_nhwc(C.byref(a), _stream()))
+    if tm is not None:
+        ev1.record()
+    _count()
+    return out
+
+
+def patch_im2col(img, patch, ld, mean=None, std=None):
+    """img fp32 NCHW [B,3,S,S] -> bf16 [B*G*G, ld] view of width 3*p*p (row pitch ld)."""
+    _ensure(img)
+    assert img.dtype == F32 and img.is_contiguous()
+    B, _, S, _ = img.shape
+    G = S // patch
+    buf = torch.empty(B * G * G, ld, dtype=BF16, device=img.device)
+    m3 = (C.c_float * 3)(*mean) if mean is not None else None
+    s3 = (C.c_float * 3)(*std) if std is not None else None
+    check(_lib.lib().gh_patch_im2col(img.data_ptr(), buf.data_ptr(), B, S, patch, ld, m3, s3, _stream()))
+    _count()
+    return buf[:, : 3 * patch * patch]
+
+
+def im2col3x3_c3(img, mean=0.0, std=1.0):
+    _ensure(img)
+    assert img.dtype == F32 and img.is_contiguous()
+    B, _, H, W = img.shape
+    out = torch.empty(B * H * W, 32, dtype=BF16, device=img.device)
+    check(_lib.lib().gh_im2col3x3_c3(img.data_ptr(), out.data_ptr(), B, H, W, float(mean), float(std), _stream()))
+    _count()
+    return out
+
+
+def embed_assemble(patch, cls, pos, B, T, D):
+    _ensure(patch)
+    out = torch.empty(B, T, D, dtype=BF16, device=patch.device)
+    check(_lib.lib().gh_embed_assemble(patch.data_ptr(), _p(cls), pos.data_ptr(), out.data_ptr(), B, T, D,
+                                       0 if cls is None else 1, _stream()))
+    _count()
+    return out
+
+
+def groupnorm_swish_nhwc(x, weight, bias, eps=1e-6, swish=True):
+    _ensure(x)
+    assert x.dtype == BF16 and x.is_contiguous() and weight.dtype == F32 and bias.dtype == F32
+    B, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    ws = torch.empty(B * 64, dtype=torch.float64, device=x.device)
+    check(_lib.lib().gh_groupnorm_swish_nhwc(x.data_ptr(), y.data_ptr(), B, H * W, Cc, weight.data_ptr(), bias.data_ptr(),
+                                             eps, int(swish), ws.data_ptr(), _stream()))
+    _count(3)
+    return y
+
+
+def softmax_rows(s, n, scale, ld_out):
+    _ensure(s)
+    assert s.dtype == F32 and s.dim() == 2 and s.stride(1) == 1
+    rows = s.shape[0]
+    p = torch.empty(rows, ld_out, dtype=BF16, device=s.device)
+    check(_lib.lib().gh_softmax_rows(s.data_ptr(), s.stride(0), p.data_ptr(), ld_out, rows, n, float(scale), _stream()))
+    _count()
+    return p
+
+
+def ae_sample_patchify(moments_nhwc, noise_nchw, scale_factor, shift_factor):
+    _ensure(moments_nhwc)
+    assert moments_nhwc.dtype == F32 and noise_nchw.dtype == F32 and moments_nhwc.is_contiguous()
+    B, h, w, z2 = moments_nhwc.shape
+    z = z2 // 2
+    nz = noise_nchw.contiguous()
+    out = torch.empty(B, (h // 2) * (w // 2), z * 4, dtype=F32, device=moments_nhwc.device)
+    check(_lib.lib().gh_ae_sample_patchify(moments_nhwc.data_ptr(), nz.data_ptr(), out.data_ptr(), B, h, w, z,
+                                           float(scale_factor), float(shift_factor), _stream()))
+    _count()
+    return out
+
+
 def _attn_out(out1, out0, n_split) -> AttnOut:
     o = AttnOut()
     if out0 is not None and n_split > 0:
@@ -363,3 +472,22 @@ def flash_attn_bwd(q, k, v, lse, scale, o1, do1, dq, dk, dv, o0=None, do0=None, 
                                        lse.data_ptr(), B, H, Lq, Lk, D, float(scale), C.byref(at[3]), C.byref(at[4]),
                                        C.byref(at[5]), ws_do.data_ptr(), ws_delta.data_ptr(), _stream()))
     _count(3)
+
+
+def sumsq_accum(g: torch.Tensor, acc: torch.Tensor) -> None:
+    """acc[0] (fp32) += sum(g^2) over a flat contiguous bf16 / fp32 buffer."""
+    _ensure(g)
+    assert g.is_contiguous() and acc.dtype == F32
+    check(_lib.lib().gh_sumsq_accum(g.data_ptr(), _dt(g), g.numel(), acc.data_ptr(), _stream()))
+    _count()
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0):
+    """In-place AdamW on flat contiguous buffers of one dtype; optional fused clip-by-global-norm."""
+    _ensure(p)
+    assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    assert p.dtype == g.dtype == m.dtype == v.dtype and p.numel() == g.numel() == m.numel() == v.numel()
+    check(_lib.lib().gh_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _dt(p), p.numel(), lr, beta1,
+                                   beta2, eps, weight_decay, int(step), _p(gnorm_sq), float(max_norm),
+                                   float(grad_scale), _stream()))
+    _count()

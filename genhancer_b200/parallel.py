@@ -1,0 +1,98 @@
+"""Data-parallel gradient exchange: bucketed all-reduce over NCCL/NVLink, overlapped with the DiT backward.
+
+The reference gets data parallelism from accelerate -> DeepSpeed ZeRO-0 (``accelerator.backward``,
+/root/reference/Continuous/train_SigLIP_stage1.py:270; train_configs/accelerate_config_4gpu.yaml:5-19): coarse
+5e8-element buckets reduced after the fact.  Here the fused DiT engine knows its own backward schedule, so it
+tells the reducer the moment a block's gradients are final (``Flux._on_grads_ready(prefix)``, fired from
+``engine.flux_backward``); because ``optim.flatten`` lays the parameters out in module order, a block is ONE
+contiguous slice of the flat gradient buffer and its all-reduce is issued immediately, on NCCL's own stream,
+while the compute stream carries on with the next block's dgrad/wgrad GEMMs.  Only the last bucket (input
+embedders, ~0.1 % of the bytes) and the small fp32 projector group are exposed.
+
+One process per GPU; plumbing is ``torch.distributed`` (backend nccl on the GPUs, gloo in the CPU tests).
+The sum is NOT divided here: ``FusedAdamW.step(grad_scale=1/world)`` folds the mean into the update.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .optim import FlatGroup
+
+
+class GradReducer:
+    def __init__(self, groups: list[FlatGroup], engine_modules=(), process_group=None,
+                 bucket_cap_bytes: int = 256 << 20):
+        self.groups = groups
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.bucket_cap_bytes = bucket_cap_bytes
+        self.enabled = True          # False on gradient-accumulation micro-steps that do not synchronise
+        self._works = []
+        self._done: dict[int, list[tuple[int, int]]] = {}
+        self.log: list[tuple[str, int, int]] = []   # (prefix, lo, hi) in issue order, for tests / tracing
+        managed_dtypes = {p.dtype for m in engine_modules for p in m.parameters()}
+        self._managed = {id(g) for g in groups if g.dtype in managed_dtypes}
+        for m in engine_modules:
+            m._on_grads_ready = self.on_ready
+
+    # ---- called from the backward schedule -------------------------------------------------------------
+    def on_ready(self, prefix: str) -> None:
+        if not self.enabled or self.world == 1:
+            return
+        for gi, g in enumerate(self.groups):
+            if id(g) not in self._managed:
+                continue
+            if prefix == "":
+                self._reduce_rest(gi, g, prefix)
+                continue
+            rng = g.range_of(prefix)
+            if rng is not None:
+                self._issue(gi, g, rng[0], rng[1], prefix)
+
+    def _issue(self, gi: int, g: FlatGroup, lo: int, hi: int, prefix: str) -> None:
+        if hi <= lo:
+            return
+        self._done.setdefault(gi, []).append((lo, hi))
+        cap = max(1, self.bucket_cap_bytes // g.flat_g.element_size())
+        for s in range(lo, hi, cap):
+            e = min(hi, s + cap)
+            self.log.append((prefix, s, e))
+            self._works.append(dist.all_reduce(g.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def _reduce_rest(self, gi: int, g: FlatGroup, prefix: str = "") -> None:
+        """All-reduce every slice of group ``gi`` that has not been reduced yet."""
+        done = sorted(self._done.get(gi, []))
+        cur = 0
+        gaps = []
+        for lo, hi in done:
+            if lo > cur:
+                gaps.append((cur, lo))
+            cur = max(cur, hi)
+        if cur < g.numel:
+            gaps.append((cur, g.numel))
+        for lo, hi in gaps:
+            self._issue(gi, g, lo, hi, prefix or "<rest>")
+
+    # ---- called by the trainer after loss.backward() ---------------------------------------------------
+    def finish(self) -> None:
+        """Reduce whatever the backward schedule did not announce (autograd-managed groups such as the fp32
+        projectors / adapter), then make the current stream wait for every bucket."""
+        if self.enabled and self.world > 1:
+            for gi, g in enumerate(self.groups):
+                self._reduce_rest(gi, g)
+            for w in self._works:
+                w.wait()
+        self._works.clear()
+        self._done.clear()
+
+    @property
+    def grad_scale(self) -> float:
+        return 1.0 / self.world
+
+
+def broadcast_parameters(groups: list[FlatGroup], src: int = 0, process_group=None) -> None:
+    """Make every rank start from rank ``src``'s parameters (flat buffers -> one broadcast per dtype group)."""
+    if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        for g in groups:
+            dist.broadcast(g.flat_p, src=src, group=process_group)

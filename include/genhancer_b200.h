@@ -214,6 +214,66 @@ int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh
                       int32_t D, float scale, const gh_attn_tensor* dq, const gh_attn_tensor* dk,
                       const gh_attn_tensor* dv, void* ws_do_headmajor, float* ws_delta, void* stream);
 
+/* --------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05, NHWC bf16 activations (frozen FLUX AE encoder,
+ * src/flux/modules/autoencoder.py:62-67 ResnetBlock convs, :85-95 Downsample, :157 conv_out).
+ *   y[b,oh,ow,co] = act( sum_{kh,kw,ci} x[b, oh*stride+kh-pad, ow*stride+kw-pad, ci] * w[co,(kh*KW+kw)*Cin+ci] + bias[co] )
+ *                   + residual[b,oh,ow,co]
+ * Out-of-image taps read zero (TMA out-of-bounds fill): `pad` is the top/left padding; right/bottom padding
+ * is implied by (Ho, Wo).  Downsample = stride 2, pad 0, Ho = H/2.  Cin % 64 == 0, Cout % 8 == 0.
+ * -------------------------------------------------------------------------- */
+typedef struct {
+  const void* x; /* bf16 [B,H,W,Cin] */
+  const void* w; /* bf16 [Cout, KH*KW*Cin] */
+  void* y;       /* [B,Ho,Wo,Cout] */
+  int32_t y_dtype;
+  int32_t B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo;
+  const void* bias;
+  int32_t bias_dtype;
+  int32_t act;
+  const void* residual; /* [B,Ho,Wo,Cout] or NULL */
+  int32_t res_dtype;
+} gh_conv_args;
+int gh_conv2d_nhwc(const gh_conv_args* args, void* stream);
+
+/* patch-embed im2col (stride == kernel): img fp32 NCHW [B,3,S,S] -> bf16 [B*(S/p)^2, ld], k = c*p*p + i*p + j,
+ * optional (x-mean)/std with HOST pointers mean3/std3 (transforms.Normalize, train_SigLIP_stage1.py:58).
+ * Feeds gh_gemm_bf16 with the flattened Conv2d weight: HF CLIPVisionEmbeddings, modeling_clip.py:147-153,208. */
+int gh_patch_im2col(const float* img, void* out_bf16, int32_t B, int32_t S, int32_t patch, int64_t ld,
+                    const float* mean3, const float* std3, void* stream);
+/* 3x3/pad-1 im2col of a 3-channel image for the AE conv_in (autoencoder.py:126): -> bf16 [B*H*W, 32],
+ * k = (kh*3+kw)*3 + c, columns 27..31 zero; (x-mean)/std fused (NORMALIZE_VAE, train_SigLIP_stage1.py:59). */
+int gh_im2col3x3_c3(const float* img, void* out_bf16, int32_t B, int32_t H, int32_t W, float mean, float std,
+                    void* stream);
+/* out[b,t,:] = (t < has_cls ? cls : patch[b,t-has_cls,:]) + pos[t,:]   (modeling_clip.py:210-217) */
+int gh_embed_assemble(const void* patch_bf16, const float* cls, const float* pos, void* out_bf16, int32_t B, int32_t T,
+                      int32_t D, int32_t has_cls, void* stream);
+/* GroupNorm(32 groups) [+ swish] on NHWC bf16 (autoencoder.py:21-22,62-78).  ws_stats_f64: 64*B doubles. */
+int gh_groupnorm_swish_nhwc(const void* x, void* y, int32_t B, int64_t HW, int32_t C, const float* weight,
+                            const float* bias, float eps, int32_t swish, void* ws_stats_f64, void* stream);
+/* p[r,:n] = softmax(scale * s[r,:n]) fp32 -> bf16, pad columns zeroed (AE mid AttnBlock, autoencoder.py:37-52). */
+int gh_softmax_rows(const float* s, int64_t ld_in, void* p_bf16, int64_t ld_out, int32_t rows, int32_t n, float scale,
+                    void* stream);
+/* DiagonalGaussian sample (noise supplied by the host RNG) + scale/shift + 2x2 patchify
+ * (autoencoder.py:268-274,302-305; clip_models/sampling.py:26): -> x1 fp32 [B,(h/2)(w/2),4z]. */
+int gh_ae_sample_patchify(const float* moments_nhwc, const float* noise_nchw, float* x1, int32_t B, int32_t h, int32_t w,
+                          int32_t z, float scale_factor, float shift_factor, void* stream);
+
+/* --------------------------------------------------------------------------
+ * Optimizer step over FLAT buffers (one launch per dtype group instead of one per tensor).
+ * gh_sumsq_accum: *acc += sum(g^2) -- the global gradient norm of accelerator.clip_grad_norm_
+ *   (train_SigLIP_stage1.py:271-272); acc is ONE fp32 the caller zeroes.
+ * gh_adamw_step: torch.optim.AdamW semantics (train_SigLIP_stage1.py:147-153,273) with the clip
+ *   coefficient min(1, max_norm / (grad_scale * sqrt(*gnorm_sq) + 1e-6)) applied on the fly
+ *   (gnorm_sq NULL or max_norm <= 0: no clipping).  param/grad/exp_avg/exp_avg_sq share `dtype`
+ *   (bf16 DiT with bf16 states, fp32 projectors with fp32 states -- no fp32 master copy, as the
+ *   reference); fp32 arithmetic, one rounding on store.  step >= 1 is the bias-correction count.
+ * -------------------------------------------------------------------------- */
+int gh_sumsq_accum(const void* g, int32_t dtype, int64_t numel, float* acc, void* stream);
+int gh_adamw_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int32_t dtype, int64_t numel,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                  const float* gnorm_sq, float max_norm, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,134 @@
+"""GPU parity of the whole stage-1 image step (AE encode -> tower -> projectors -> flow-matching interpolation ->
+DiT fwd/bwd -> velocity-MSE) against the reference's own run of the same step (fixtures: oracle/make_golden.py),
+at reduced size and at BASELINE config 1's FULL size (ViT-L/14-224 + the 1.31 B-parameter DiT + the full AE)."""
+import pytest
+import torch
+
+from conftest import cosine, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+OPENAI_MEAN = (0.48145466, 0.4578275, 0.40821073)
+OPENAI_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def build_step(tower_cfg, flux_cfg, ae_cfg, key_shapes, seed, clip_dim, t5_dim):
+    from genhancer_b200.clip_models import CLIP_bank, vision_tower as vt
+    from genhancer_b200.flux.model import Flux, FluxParams
+    from genhancer_b200.flux.modules.autoencoder import AutoEncoder, AutoEncoderParams
+    from genhancer_b200.train_step import Stage1ImageStep
+    from oracle import genhancer_oracle as O
+    c = tower_cfg
+    cfg = vt.TowerConfig(c["kind"], c["hidden"], c["layers"], c["heads"], c["mlp"], c["image_size"], c["patch"],
+                         c["proj_dim"], c["eps"], "quick_gelu")
+    model = vt.VisionLanguageModel(cfg)
+    model.load_state_dict(O.synth_state_dict(key_shapes["tower"], seed), strict=False)
+
+    class Cfg:
+        pass
+    Cfg.clip_dim, Cfg.t5_dim = clip_dim, t5_dim
+    wrap = CLIP_bank._Wrapper()
+    wrap._finish(model, Cfg, c["proj_dim"])
+    wrap.load_state_dict(O.synth_state_dict(key_shapes["wrap"], seed + 1), strict=False)
+    for n, p in wrap.named_parameters():
+        p.requires_grad_("project_clip" in n or "project_t5" in n)
+    wrap = wrap.to("cuda").float()
+    fc = dict(flux_cfg)
+    fc["axes_dim"] = list(fc["axes_dim"])
+    dit = Flux(FluxParams(**fc))
+    dit.load_state_dict(O.synth_state_dict(key_shapes["dit"], seed + 2), strict=True)
+    dit = dit.to("cuda").to(torch.bfloat16)
+    ac = dict(ae_cfg)
+    ac["ch_mult"] = list(ac["ch_mult"])
+    ae = AutoEncoder(AutoEncoderParams(**ac))
+    ae.encoder.load_state_dict(O.synth_state_dict(key_shapes["ae"], seed + 3), strict=True)
+    ae = ae.to("cuda").requires_grad_(False)
+    return Stage1ImageStep(wrap, dit, ae, OPENAI_MEAN, OPENAI_STD, scale_factor=1.0), wrap, dit
+
+
+def test_stage1_step_small_matches_reference():
+    fx = load_golden("step_small.pt")
+    step, wrap, dit = build_step(fx["tower_cfg"], fx["flux_cfg"], fx["ae_cfg"], fx["key_shapes"], fx["seed"],
+                                 fx["clip_dim"], fx["t5_dim"])
+    dev = "cuda"
+    loss, parts = step(fx["img"].to(dev), ae_noise=fx["ae_noise"].to(dev), t=fx["t"].to(dev), x_0=fx["x_0"].to(dev),
+                       return_parts=True)
+    assert rel_err(parts["x_1"], fx["x_1"]) < 3e-2
+    assert rel_err(parts["x_t"], fx["x_t"]) < 3e-2
+    assert cosine(parts["vec"], fx["vec"]) >= 0.999 and cosine(parts["txt"], fx["txt"]) >= 0.999
+    assert rel_err(parts["pred"], fx["pred"]) < 5e-2
+    assert abs(loss.item() - fx["loss"].item()) / fx["loss"].item() < 1e-2     # north_star tolerance
+    loss.backward()
+    P = dict(dit.named_parameters())
+    assert cosine(P["txt_in.weight"].grad, fx["grad_txt_in_weight"]) > 0.98
+    assert cosine(P["final_layer.linear.weight"].grad, fx["grad_final_linear_weight"]) > 0.99
+    assert cosine(wrap.project_t5[3].weight.grad, fx["grad_project_t5_3_weight"]) > 0.98
+
+
+def test_stage1_step_rng_draws_are_the_references():
+    """Without explicit draws the step must consume the device RNG in the reference's order and shapes:
+    randn(B,16,h,w) -> randn(B) -> randn(B,L,64)."""
+    fx = load_golden("step_small.pt")
+    step, _, _ = build_step(fx["tower_cfg"], fx["flux_cfg"], fx["ae_cfg"], fx["key_shapes"], fx["seed"],
+                            fx["clip_dim"], fx["t5_dim"])
+    img = fx["img"].to("cuda")
+    torch.manual_seed(123)
+    with torch.no_grad():
+        _, parts = step(img, return_parts=True)
+    torch.manual_seed(123)
+    noise = torch.randn(2, 16, 14, 14, device="cuda")
+    t = torch.sigmoid(torch.randn((2,), device="cuda") * 1.0)
+    x_0 = torch.randn(2, 49, 64, device="cuda")
+    assert torch.equal(parts["t"], t) and torch.equal(parts["x_0"], x_0)
+    with torch.no_grad():
+        _, parts2 = step(img, ae_noise=noise, t=t, x_0=x_0, return_parts=True)
+    assert torch.equal(parts["x_1"], parts2["x_1"]) and torch.equal(parts["x_t"], parts2["x_t"])
+
+
+def test_cfg1_full_size_step_matches_reference():
+    """BASELINE.json configs[0]: OpenAI CLIP ViT-L/14-224 + the lightweight DiT, B=2, the reference ran it in fp32
+    on the CPU; the B200 path runs bf16 tensor-core math.  Gates: class-token cosine >= 0.999, loss within 1e-2."""
+    from oracle import genhancer_oracle as O
+    fx = load_golden("cfg1_full.pt")
+    tc, fc, ac = O.openai_vit_l14(224), O.FluxCfg(), O.AECfg()
+    ks = dict(tower=O.tower_key_shapes(tc), dit=O.flux_key_shapes(fc), ae=O.ae_encoder_key_shapes(ac),
+              wrap={**O.projector_key_shapes("project_clip", 768, 768), **O.projector_key_shapes("project_t5", 768, 4096)})
+    step, wrap, dit = build_step(tc.__dict__, fc.__dict__, ac.__dict__, ks, fx["seed"], 768, 4096)
+    dev = "cuda"
+    loss, parts = step(fx["img"].to(dev), ae_noise=fx["ae_noise"].to(dev), t=fx["t"].to(dev), x_0=fx["x_0"].to(dev),
+                       return_parts=True)
+    cls = wrap.class_token(fx["img"].to(dev), _norm=(OPENAI_MEAN, OPENAI_STD))
+    assert cosine(cls, fx["class_token"]) >= 0.999
+    assert cosine(parts["vec"], fx["vec"]) >= 0.999
+    assert rel_err(parts["x_1"], fx["x_1"]) < 3e-2
+    assert abs(loss.item() - fx["loss"].item()) / fx["loss"].item() < 1e-2
+    assert cosine(parts["pred"], fx["pred"]) > 0.995
+    loss.backward()
+    P = dict(dit.named_parameters())
+    assert cosine(P["final_layer.linear.weight"].grad, fx["grad_final_linear_weight"]) > 0.99
+    assert cosine(P["img_in.weight"].grad, fx["grad_img_in_weight"]) > 0.95
+    gn = wrap.project_t5[1].weight.grad.float().norm().item()
+    assert abs(gn - fx["grad_norm_project_t5_1_weight"].item()) / fx["grad_norm_project_t5_1_weight"].item() < 0.1
+
+
+def test_fused_adamw_matches_torch():
+    from genhancer_b200 import optim
+    torch.manual_seed(0)
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+        ps = [torch.nn.Parameter(torch.randn(s, device="cuda").to(dtype)) for s in ((37, 5), (1000,), (64, 64), (3,))]
+        ref = [torch.nn.Parameter(p.detach().clone().float()) for p in ps]
+        groups = optim.flatten([(f"p{i}", p) for i, p in enumerate(ps)])
+        opt = optim.FusedAdamW(groups, lr=1e-2, weight_decay=0.01, max_grad_norm=1.0)
+        topt = torch.optim.AdamW(ref, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+        for it in range(3):
+            for p, r in zip(ps, ref):
+                g = torch.randn(p.shape, device="cuda")
+                p.grad.copy_(g.to(dtype))
+                r.grad = p.grad.detach().float().clone()
+            torch.nn.utils.clip_grad_norm_(ref, 1.0)
+            topt.step()
+            opt.step()
+            tn = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in ps))
+            assert abs(opt.grad_norm().item() - tn.item()) / tn.item() < 1e-3
+        for p, r in zip(ps, ref):
+            assert rel_err(p, r) < tol

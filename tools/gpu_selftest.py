@@ -19,8 +19,12 @@ os.makedirs("gpurun_out", exist_ok=True)
 LOG = open("gpurun_out/selftest.log", "a")
 
 
+LINES: list[str] = []  # every line said, so tests/test_kernels_gpu.py can assert that none starts with FAIL
+
+
 def say(*a):
     s = " ".join(str(x) for x in a)
+    LINES.append(s)
     print(s, flush=True)
     LOG.write(s + "\n")
     LOG.flush()

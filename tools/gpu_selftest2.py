@@ -19,8 +19,12 @@ BF = torch.bfloat16
 dev = "cuda"
 
 
+LINES: list[str] = []  # every line said, so tests/test_kernels_gpu.py can assert that none starts with FAIL
+
+
 def say(*a):
     s = " ".join(str(x) for x in a)
+    LINES.append(s)
     print(s, flush=True)
     LOG.write(s + "\n")
     LOG.flush()
@@ -276,7 +280,7 @@ def main():
         attn_case(1, 1, 64, 64)
         attn_case(2, 4, 577, 64, fused_qkv=True)
         attn_case(2, 4, 257, 64, fused_qkv=True)
-    if "attnbwd" in which:
+    if "attnbwd" in which or "attnbwd_cases" in which:
         attn_bwd_case(1, 1, 64, 128)
         attn_bwd_case(1, 1, 128, 128)
         attn_bwd_case(1, 2, 200, 128)
@@ -284,6 +288,7 @@ def main():
         attn_bwd_case(2, 2, 1017, 128, n_split=576)
         attn_bwd_case(1, 1, 64, 64)
         attn_bwd_case(2, 4, 577, 64, fused_qkv=True)
+    if "attnbwd" in which:
         time_attn_bwd(32, 24, 442, 128)
         time_attn_bwd(32, 16, 577, 64)
     if "time" in which:
