@@ -97,15 +97,26 @@ class GemmTimer:
     def __init__(self):
         self.records = []  # (start, stop, flops)
 
-    def __call__(self, flops: float):
+    def __call__(self, flops: float, tag: str = ""):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        self.records.append((s, e, flops))
+        self.records.append((s, e, flops, tag))
         return s, e
 
     def summary(self) -> tuple[float, float, int]:
-        ms = sum(s.elapsed_time(e) for s, e, _ in self.records)
-        fl = sum(f for _, _, f in self.records)
+        ms = sum(s.elapsed_time(e) for s, e, _, _ in self.records)
+        fl = sum(f for _, _, f, _ in self.records)
         return fl, ms, len(self.records)
+
+    def by_shape(self) -> list[dict]:
+        agg: dict[str, list] = {}
+        for s, e, f, tag in self.records:
+            a = agg.setdefault(tag, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += s.elapsed_time(e)
+            a[2] += f
+        rows = [dict(shape=k, launches=v[0], ms_total=round(v[1], 3), tflops=round(v[2] / (v[1] * 1e-3) / 1e12, 1) if v[1] > 0 else None)
+                for k, v in agg.items()]
+        return sorted(rows, key=lambda r: -r["ms_total"])
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -224,6 +235,10 @@ def run_ours(args):
     launches = K.LAUNCHES - n0
     K.GEMM_TIMER = None
     gemm_flops, gemm_ms, gemm_n = timer.summary()
+    if rank == 0 and args.dump_shapes:
+        os.makedirs(os.path.dirname(os.path.abspath(args.dump_shapes)), exist_ok=True)
+        json.dump({"steps": args.steps, "ms_step": ms_value / args.steps, "rows": timer.by_shape()},
+                  open(args.dump_shapes, "w"), indent=1)
 
     # ---- end-to-end arm: pinned host batch -> H2D -> step -> loss read back, every step ------------------------
     last = {}
@@ -375,6 +390,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (BASELINE configs[1]: 32)")
     ap.add_argument("--image-size", type=int, default=336)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-shapes", default="", help="write the per-shape GEMM/conv timing table (JSON) here")
     ap.add_argument("--cpu-budget", type=float, default=45.0)
     ap.add_argument("--ref-budget", type=float, default=240.0)
     args = ap.parse_args()

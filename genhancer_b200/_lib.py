@@ -93,6 +93,7 @@ SIGNATURES: dict[str, list] = {
     "gh_patch_im2col": [_vp, _vp, _i32, _i32, _i32, _i64, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp],
     "gh_im2col3x3_c3": [_vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp],
     "gh_embed_assemble": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "gh_groupnorm_ws_bytes": [_i32, _i64],
     "gh_groupnorm_swish_nhwc": [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _f32, _i32, _vp, _vp],
     "gh_softmax_rows": [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp],
     "gh_ae_sample_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp],
@@ -109,7 +110,7 @@ def _declare(lib):
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == "gh_last_error" else C.c_int
+        fn.restype = (C.c_char_p if name == "gh_last_error" else C.c_int64 if name.endswith("_ws_bytes") else C.c_int)
 
 
 def lib():

@@ -46,24 +46,22 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
 }
 
 static int pick_bn(int M, int N) {
-  // minimise waves(BN) * BN (MMA time per tile is proportional to BN); ties -> larger tile
-  const int mb = (M + 127) / 128;
+  // Per-tile time ~ BN + c (MMA issue is proportional to BN; c = fixed per-tile cost), and narrow tiles re-read
+  // the A operand from L2 once per BN columns: 128x64 tiles run at about a third of the 128x256 rate
+  // (measured: wgrad M=21504 N=3072 K=14144 at 455 TFLOP/s with BN=64 vs 1350 with BN=256).  So: the widest tile
+  // the problem fills, dropping one notch only when that removes at least a quarter of the waves' work.
+  const long mb = (M + 127) / 128;
   const int sms = num_sms();
-  int best = 256;
-  long best_cost = -1;
-  const int cands[3] = {256, 128, 64};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    if (bn > 64 && bn / 2 >= N) continue;  // tile wider than 2x the problem
-    const long tiles = static_cast<long>(mb) * ((N + bn - 1) / bn);
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  auto cost = [&](int bn) {
+    const long tiles = mb * ((N + bn - 1) / bn);
     const long waves = (tiles + sms - 1) / sms;
-    const long cost = waves * bn;
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = bn;
-    }
-  }
-  return best;
+    return waves * (bn + 32);
+  };
+  const long c256 = cost(256), c128 = cost(128);
+  if (c128 * 4 <= c256 * 3) return 128;
+  return 256;
 }
 
 }  // namespace gh
@@ -111,6 +109,12 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
   p.ep.gate = static_cast<const __nv_bfloat16*>(a->gate); p.ep.gate_ld = a->gate_ld;
   p.ep.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : 1;
   p.ep.residual = a->residual; p.ep.ld_res = a->ld_res; p.ep.res_f32 = (a->res_dtype == GH_F32);
+  p.ep.vec8 = (a->N % 8 == 0) && (a->d_dtype == GH_F32 || (a->ldd % 8 == 0)) &&
+              (!a->bias || a->bias_dtype == GH_F32 || aligned16(a->bias)) &&
+              (!a->aux_in || (a->ld_aux_in % 8 == 0 && aligned16(a->aux_in))) &&
+              (!a->aux_out || (a->ld_aux_out % 8 == 0 && aligned16(a->aux_out))) &&
+              (!a->gate || (a->gate_ld % 8 == 0 && aligned16(a->gate))) &&
+              (!a->residual || a->res_dtype == GH_F32 || (a->ld_res % 8 == 0 && aligned16(a->residual)));
 
   CUtensorMap ta, tb;
   {

@@ -41,6 +41,7 @@ struct EpilogueParams {
   const void* residual;
   int64_t ld_res;
   int res_f32;
+  int vec8;  // every epilogue operand allows 16-byte bf16 vectors (N % 8 == 0, leading dimensions % 8 == 0)
 };
 
 struct ConvGeom {  // MODE_CONV only
@@ -87,61 +88,129 @@ __device__ __forceinline__ void decode_tile(int tile, int num_m_blocks, int num_
   n_blk = in_group / gsize;
 }
 
-// 4 consecutive outputs of one row: fused epilogue + store
-__device__ __forceinline__ void epilogue_store4(const EpilogueParams& ep, float4 acc, int64_t out_row, int gm,
-                                                int gn) {
-  float v[4] = {acc.x * ep.alpha, acc.y * ep.alpha, acc.z * ep.alpha, acc.w * ep.alpha};
-  if (ep.bias) {
+// ----------------------------------------------------------------------------------------------------------
+// Fused epilogue of one 32-row x 32-column accumulator chunk held by one warp (fp32, staged row-major in smem).
+// Lane l owns the 8 columns col8..col8+7 (col8 = 8*(l&3)) of rows it*8 + (l>>2), it = 0..3: one 16-byte bf16
+// vector per row and operand.  All global LOADS of the chunk (bias once; residual / aux_in / gate for the 4 rows)
+// are issued up front so that their latencies overlap; only then the math and the stores run.  (A load placed
+// after a store cannot be hoisted by the compiler -- possible aliasing -- which exposed one L2 round trip per row
+// in the first version of this epilogue: 195 TFLOP/s on the ViT's K=1024 GEMMs.)
+// ep.vec8 == 0 (N or a leading dimension not a multiple of 8): 8-byte accesses, upper half masked by `hi`.
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld8_bf16(const __nv_bfloat16* p, bool vec8, bool hi) {
+  if (vec8) return *reinterpret_cast<const uint4*>(p);
+  const uint2 a = *reinterpret_cast<const uint2*>(p);
+  uint2 b = make_uint2(0u, 0u);
+  if (hi) b = *reinterpret_cast<const uint2*>(p + 4);
+  return make_uint4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8], bool vec8, bool hi) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  if (vec8) {
+    *reinterpret_cast<uint4*>(p) = o;
+  } else {
+    *reinterpret_cast<uint2*>(p) = make_uint2(o.x, o.y);
+    if (hi) *reinterpret_cast<uint2*>(p + 4) = make_uint2(o.z, o.w);
+  }
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, const float* __restrict__ st, int ld_st,
+                                               const int (&rows)[4], uint32_t okmask, bool hi, int sub_row, int col8,
+                                               int gn) {
+  const bool vec8 = ep.vec8 != 0;
+  const int ACT = ep.act;           // warp-uniform runtime switches (one code path: keeps registers in check)
+  const bool ACT_GRAD = ep.act_grad != 0;
+  float b8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ep.bias && okmask) {
     if (ep.bias_f32) {
-      const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(ep.bias) + gn);
-      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+      const float* bp = static_cast<const float*>(ep.bias) + gn;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(bp));
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hi) y = __ldg(reinterpret_cast<const float4*>(bp + 4));
+      b8[0] = x.x; b8[1] = x.y; b8[2] = x.z; b8[3] = x.w; b8[4] = y.x; b8[5] = y.y; b8[6] = y.z; b8[7] = y.w;
     } else {
-      const uint2 b = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(ep.bias) + gn);
-      const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y);
-      v[0] += b0.x; v[1] += b0.y; v[2] += b1.x; v[3] += b1.y;
+      unpack8(ld8_bf16(static_cast<const __nv_bfloat16*>(ep.bias) + gn, vec8, hi), b8);
     }
   }
-  if (ep.aux_out) {
-    uint2 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    *reinterpret_cast<uint2*>(ep.aux_out + out_row * ep.ld_aux_out + gn) = o;
-  }
-  if (ep.act_grad) {
-    const uint2 x = *reinterpret_cast<const uint2*>(ep.aux_in + out_row * ep.ld_aux_in + gn);
-    const float2 x0 = unpack_bf16x2(x.x), x1 = unpack_bf16x2(x.y);
-    v[0] *= act_bwd(ep.act, x0.x); v[1] *= act_bwd(ep.act, x0.y);
-    v[2] *= act_bwd(ep.act, x1.x); v[3] *= act_bwd(ep.act, x1.y);
-  } else if (ep.act != ACT_NONE) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = act_fwd(ep.act, v[i]);
-  }
-  if (ep.gate) {
-    const int b = gm / ep.rows_per_batch;
-    const uint2 g = *reinterpret_cast<const uint2*>(ep.gate + static_cast<int64_t>(b) * ep.gate_ld + gn);
-    const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
-    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g1.x; v[3] *= g1.y;
-  }
+  uint4 res16[4], aux[4], gt[4];
+  float4 resf[4][2];
   if (ep.residual) {
     if (ep.res_f32) {
-      const float4 r = *reinterpret_cast<const float4*>(static_cast<const float*>(ep.residual) +
-                                                        out_row * ep.ld_res + gn);
-      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (okmask >> i & 1u) {
+          const float* rp = static_cast<const float*>(ep.residual) + static_cast<int64_t>(rows[i]) * ep.ld_res + gn;
+          resf[i][0] = *reinterpret_cast<const float4*>(rp);
+          resf[i][1] = hi ? *reinterpret_cast<const float4*>(rp + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     } else {
-      const uint2 r = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(ep.residual) +
-                                                      out_row * ep.ld_res + gn);
-      const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y);
-      v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (okmask >> i & 1u)
+          res16[i] = ld8_bf16(static_cast<const __nv_bfloat16*>(ep.residual) + static_cast<int64_t>(rows[i]) * ep.ld_res + gn,
+                              vec8, hi);
     }
   }
-  if (ep.d_f32) {
-    *reinterpret_cast<float4*>(static_cast<float*>(ep.d) + out_row * ep.ldd + gn) =
-        make_float4(v[0], v[1], v[2], v[3]);
-  } else {
-    uint2 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(ep.d) + out_row * ep.ldd + gn) = o;
+  if (ACT_GRAD) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (okmask >> i & 1u) aux[i] = ld8_bf16(ep.aux_in + static_cast<int64_t>(rows[i]) * ep.ld_aux_in + gn, vec8, hi);
+  }
+  if (ep.gate) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (okmask >> i & 1u)
+        gt[i] = ld8_bf16(ep.gate + static_cast<int64_t>(rows[i] / ep.rows_per_batch) * ep.gate_ld + gn, vec8, hi);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (!(okmask >> i & 1u)) continue;
+    const int64_t row = rows[i];
+    const float* sp = st + (i * 8 + sub_row) * ld_st + col8;
+    const float4 a0 = *reinterpret_cast<const float4*>(sp), a1 = *reinterpret_cast<const float4*>(sp + 4);
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = v[k] * ep.alpha + b8[k];
+    if (ep.aux_out) st8_bf16(ep.aux_out + row * ep.ld_aux_out + gn, v, vec8, hi);
+    if (ACT_GRAD) {
+      float x[8];
+      unpack8(aux[i], x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= act_bwd(ACT, x[k]);
+    } else if (ACT != ACT_NONE) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = act_fwd(ACT, v[k]);
+    }
+    if (ep.gate) {
+      float g[8];
+      unpack8(gt[i], g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= g[k];
+    }
+    if (ep.residual) {
+      if (ep.res_f32) {
+        v[0] += resf[i][0].x; v[1] += resf[i][0].y; v[2] += resf[i][0].z; v[3] += resf[i][0].w;
+        v[4] += resf[i][1].x; v[5] += resf[i][1].y; v[6] += resf[i][1].z; v[7] += resf[i][1].w;
+      } else {
+        float r[8];
+        unpack8(res16[i], r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += r[k];
+      }
+    }
+    if (ep.d_f32) {
+      float* dp = static_cast<float*>(ep.d) + row * ep.ldd + gn;
+      *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+      if (hi) *reinterpret_cast<float4*>(dp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      st8_bf16(static_cast<__nv_bfloat16*>(ep.d) + row * ep.ldd + gn, v, vec8, hi);
+    }
   }
 }
 
@@ -286,6 +355,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const int sub_row = lane >> 2;
+      const int col8 = (lane & 3) * 8;
+      // the 4 output rows this lane touches in every chunk of the tile (row index == logical GEMM row)
+      int rows[4];
+      uint32_t rowmask = 0;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int tr = ew * 32 + it * 8 + sub_row;  // row within the 128-row tile
+        bool ok;
+        if (MODE == MODE_CONV) {
+          const int tiles_per_img = p.cv.tiles_w * p.cv.tiles_h;
+          const int cb = m_blk / tiles_per_img;
+          const int rem = m_blk - cb * tiles_per_img;
+          const int oh = (rem / p.cv.tiles_w) * p.cv.TH + tr / p.cv.TW;
+          const int ow = (rem % p.cv.tiles_w) * p.cv.TW + tr % p.cv.TW;
+          ok = (tr < p.cv.TW * p.cv.TH) && (oh < p.cv.Ho) && (ow < p.cv.Wo);
+          rows[it] = (cb * p.cv.Ho + oh) * p.cv.Wo + ow;
+        } else {
+          rows[it] = m_blk * 128 + tr;
+          ok = rows[it] < p.M;
+        }
+        rowmask |= static_cast<uint32_t>(ok) << it;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         if (n_blk * BN + c * 32 >= p.N) break;  // warp-uniform
@@ -298,33 +390,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         __syncwarp();
-        const int sub_row = lane >> 3;
-        const int col4 = (lane & 7) * 4;
-        const int gn = n_blk * BN + c * 32 + col4;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 4 + sub_row;       // row within this warp's 32
-          const int tr = ew * 32 + row;            // row within the 128-row tile
-          const float4 a = *reinterpret_cast<const float4*>(st + row * Cfg::EPI_LD + col4);
-          bool ok = gn < p.N;
-          int64_t out_row;
-          int gm;
-          if (MODE == MODE_CONV) {
-            const int tiles_per_img = p.cv.tiles_w * p.cv.tiles_h;
-            const int cb = m_blk / tiles_per_img;
-            const int rr = m_blk - cb * tiles_per_img;
-            const int oh = (rr / p.cv.tiles_w) * p.cv.TH + tr / p.cv.TW;
-            const int ow = (rr % p.cv.tiles_w) * p.cv.TW + tr % p.cv.TW;
-            ok = ok && (tr < p.cv.TW * p.cv.TH) && (oh < p.cv.Ho) && (ow < p.cv.Wo);
-            out_row = (static_cast<int64_t>(cb) * p.cv.Ho + oh) * p.cv.Wo + ow;
-            gm = static_cast<int>(out_row);
-          } else {
-            gm = m_blk * 128 + tr;
-            ok = ok && (gm < p.M);
-            out_row = gm;
-          }
-          if (ok) epilogue_store4(p.ep, a, out_row, gm, gn);
-        }
+        const int gn = n_blk * BN + c * 32 + col8;
+        epilogue_chunk(p.ep, st, Cfg::EPI_LD, rows, gn < p.N ? rowmask : 0u, gn + 4 < p.N, sub_row, col8, gn);
         __syncwarp();
       }
       tc_fence_before();

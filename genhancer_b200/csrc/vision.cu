@@ -96,12 +96,12 @@ __global__ void embed_assemble_kernel(const bf16* __restrict__ patch, const floa
 // fp64 across blocks), pass 2 = normalise + affine (+ swish).  autoencoder.py:21-22,62-78,156,177-178.
 // algorithmic bytes / element: 2 (stats read) + 2 (apply read) + 2 (write)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats,
+// Deterministic: per-thread partials -> fixed-order in-block reduction -> per-CTA partial in the workspace ->
+// gn_finalize sums the CTA partials in fp64 in fixed order.  No atomics anywhere (run-to-run bit-identical).
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial,
                                                        int64_t HW, int C, int pix_per_cta) {
-  __shared__ float red[32][2];
+  __shared__ float sh[256][8];  // [thread][slot*2 + {sum, sumsq}]
   const int b = blockIdx.y;
-  if (threadIdx.x < 64) red[threadIdx.x >> 1][threadIdx.x & 1] = 0.f;
-  __syncthreads();
   const int c8 = C / 8;
   const int cpg = C / 32;
   const int tpp = c8;                       // threads per pixel
@@ -120,29 +120,43 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
       s[2] += e.x + e.y;   ss[2] += e.x * e.x + e.y * e.y;
       s[3] += g.x + g.y;   ss[3] += g.x * g.x + g.y * g.y;
     }
-    if (cpg >= 8) {  // all 8 channels of this thread sit in one group
-      atomicAdd(&red[my_c / cpg][0], s[0] + s[1] + s[2] + s[3]);
-      atomicAdd(&red[my_c / cpg][1], ss[0] + ss[1] + ss[2] + ss[3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        atomicAdd(&red[(my_c + 2 * j) / cpg][0], s[j]);
-        atomicAdd(&red[(my_c + 2 * j) / cpg][1], ss[j]);
-      }
-    }
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sh[threadIdx.x][2 * j] = s[j]; sh[threadIdx.x][2 * j + 1] = ss[j]; }
   __syncthreads();
-  if (threadIdx.x < 64)
-    atomicAdd(stats + (static_cast<int64_t>(b) * 32 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1),
-              static_cast<double>(red[threadIdx.x >> 1][threadIdx.x & 1]));
+  if (threadIdx.x < 64) {
+    const int grp = threadIdx.x >> 1, st = threadIdx.x & 1;
+    float acc = 0.f;
+    for (int p = 0; p < ppi; ++p)
+      for (int q = 0; q < cpg / 2; ++q) {
+        const int c = grp * cpg + 2 * q;
+        acc += sh[p * tpp + c / 8][((c % 8) / 2) * 2 + st];
+      }
+    partial[((static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * 32 + grp) * 2 + st] = acc;
+  }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ stats,
+// one thread per (sample, group): fixed-order fp64 sum of the CTA partials -> (mean, rstd)
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float2* __restrict__ mr, int B, int nblk,
+                                   double cnt, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 32) return;
+  const int b = i / 32, grp = i % 32;
+  double sm = 0.0, sq = 0.0;
+  for (int k = 0; k < nblk; ++k) {
+    const float* p = partial + ((static_cast<int64_t>(b) * nblk + k) * 32 + grp) * 2;
+    sm += static_cast<double>(p[0]);
+    sq += static_cast<double>(p[1]);
+  }
+  const double mean = sm / cnt;
+  const float var = fmaxf(static_cast<float>(sq / cnt - mean * mean), 0.f);
+  mr[i] = make_float2(static_cast<float>(mean), rsqrtf(var + eps));
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float2* __restrict__ mr,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                       bf16* __restrict__ y, int64_t HW, int C, float eps, int swish,
-                                                       int64_t n8) {
+                                                       bf16* __restrict__ y, int64_t HW, int C, int swish, int64_t n8) {
   const int cpg = C / 32;
-  const double cnt = static_cast<double>(HW) * cpg;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
     const int c = static_cast<int>((i * 8) % C);
@@ -150,17 +164,16 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
     const uint4 u = reinterpret_cast<const uint4*>(x)[i];
     const float2 a = unpack_bf16x2(u.x), c2 = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), g = unpack_bf16x2(u.w);
     float v[8] = {a.x, a.y, c2.x, c2.y, e.x, e.y, g.x, g.y};
+    const float4 w0 = *reinterpret_cast<const float4*>(w + c), w1 = *reinterpret_cast<const float4*>(w + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int grp = (c + q * 2) / cpg;
-      const double sm = stats[(static_cast<int64_t>(b) * 32 + grp) * 2], sq = stats[(static_cast<int64_t>(b) * 32 + grp) * 2 + 1];
-      const double mean = sm / cnt;
-      const float rstd = rsqrtf(fmaxf(static_cast<float>(sq / cnt - mean * mean), 0.f) + eps);
-      const float mu = static_cast<float>(mean);
+      const float2 st = __ldg(mr + b * 32 + (c + q * 2) / cpg);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int cc = c + q * 2 + j;
-        float t = (v[q * 2 + j] - mu) * rstd * w[cc] + bias[cc];
+        float t = (v[q * 2 + j] - st.x) * st.y * wv[q * 2 + j] + bv[q * 2 + j];
         if (swish) t = t * sigmoidf_(t);
         v[q * 2 + j] = t;
       }
@@ -255,24 +268,40 @@ extern "C" int gh_embed_assemble(const void* patch_bf16, const float* cls, const
   return GH_OK;
 }
 
+static void gn_plan(int B, int64_t HW, int* pix_per_cta, int* nblk) {
+  int ppc = 256;
+  while ((HW + ppc - 1) / ppc * B > 16L * num_sms() && ppc < (1 << 20)) ppc *= 2;
+  *pix_per_cta = ppc;
+  *nblk = static_cast<int>((HW + ppc - 1) / ppc);
+}
+
+extern "C" int64_t gh_groupnorm_ws_bytes(int32_t B, int64_t HW) {
+  if (B <= 0 || HW <= 0) return 0;
+  int ppc, nblk;
+  gn_plan(B, HW, &ppc, &nblk);
+  return static_cast<int64_t>(B) * nblk * 64 * sizeof(float) + static_cast<int64_t>(B) * 32 * sizeof(float2);
+}
+
 extern "C" int gh_groupnorm_swish_nhwc(const void* x, void* y, int32_t B, int64_t HW, int32_t C, const float* weight,
-                                       const float* bias, float eps, int32_t swish, void* ws_stats_f64, void* stream) {
-  GH_REQUIRE(x && y && weight && bias && ws_stats_f64, GH_ERR_NULL, "gh_groupnorm_swish_nhwc: NULL pointer");
+                                       const float* bias, float eps, int32_t swish, void* ws, void* stream) {
+  GH_REQUIRE(x && y && weight && bias && ws, GH_ERR_NULL, "gh_groupnorm_swish_nhwc: NULL pointer");
   GH_REQUIRE(B > 0 && HW > 0 && C % 64 == 0 && C <= 2048, GH_ERR_BAD_SHAPE,
              "gh_groupnorm_swish_nhwc: C=%d must be a multiple of 64 (32 groups of >= 2 channels), <= 2048", C);
-  GH_REQUIRE(aligned16(x) && aligned16(y), GH_ERR_ALIGN, "gh_groupnorm_swish_nhwc: 16B alignment");
+  GH_REQUIRE(aligned16(x) && aligned16(y) && aligned16(ws) && aligned16(weight) && aligned16(bias), GH_ERR_ALIGN,
+             "gh_groupnorm_swish_nhwc: 16B alignment");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  GH_CHECK_CUDA(cudaMemsetAsync(ws_stats_f64, 0, static_cast<size_t>(B) * 32 * 2 * sizeof(double), s));
-  int pix_per_cta = 256;
-  while ((HW + pix_per_cta - 1) / pix_per_cta * B > 16L * num_sms() && pix_per_cta < 8192) pix_per_cta *= 2;
-  dim3 grid(static_cast<unsigned>((HW + pix_per_cta - 1) / pix_per_cta), B);
-  gn_stats_kernel<<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<double*>(ws_stats_f64), HW, C, pix_per_cta);
+  int pix_per_cta, nblk;
+  gn_plan(B, HW, &pix_per_cta, &nblk);
+  float* partial = static_cast<float*>(ws);
+  float2* mr = reinterpret_cast<float2*>(partial + static_cast<int64_t>(B) * nblk * 64);
+  gn_stats_kernel<<<dim3(nblk, B), 256, 0, s>>>(static_cast<const bf16*>(x), partial, HW, C, pix_per_cta);
+  GH_CHECK_CUDA(cudaGetLastError());
+  gn_finalize_kernel<<<(B * 32 + 127) / 128, 128, 0, s>>>(partial, mr, B, nblk, static_cast<double>(HW) * (C / 32), eps);
   GH_CHECK_CUDA(cudaGetLastError());
   const int64_t n8 = static_cast<int64_t>(B) * HW * C / 8;
   const int64_t want = (n8 + 255) / 256;
   const int g2 = static_cast<int>(want < 16L * num_sms() ? want : 16L * num_sms());
-  gn_apply_kernel<<<g2, 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<const double*>(ws_stats_f64), weight, bias,
-                                     static_cast<bf16*>(y), HW, C, eps, swish, n8);
+  gn_apply_kernel<<<g2, 256, 0, s>>>(static_cast<const bf16*>(x), mr, weight, bias, static_cast<bf16*>(y), HW, C, swish, n8);
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
 }

@@ -95,7 +95,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         g.residual, g.ld_res, g.res_dtype = residual.data_ptr(), residual.stride(0), _dt(residual)
     tm = GEMM_TIMER
     if tm is not None:
-        ev0, ev1 = tm(2.0 * M * N * K)
+        ev0, ev1 = tm(2.0 * M * N * K, f"gemm M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} d={'f32' if out.dtype == F32 else 'bf16'}")
         ev0.record()
     check(_lib.lib().gh_gemm_bf16(C.byref(g), _stream()))
     if tm is not None:
@@ -369,7 +369,7 @@ def conv2d_nhwc(x, w, KH, KW, stride=1, pad=0, Ho=None, Wo=None, bias=None, act=
         a.residual, a.res_dtype = residual.data_ptr(), _dt(residual)
     tm = GEMM_TIMER
     if tm is not None:
-        ev0, ev1 = tm(2.0 * B * Ho * Wo * Cout * KH * KW * Cin)
+        ev0, ev1 = tm(2.0 * B * Ho * Wo * Cout * KH * KW * Cin, f"conv B={B} H={H} W={W} Cin={Cin} Cout={Cout} k={KH} s={stride}")
         ev0.record()
     check(_lib.lib().gh_conv2d_nhwc(C.byref(a), _stream()))
     if tm is not None:
@@ -416,7 +416,7 @@ def groupnorm_swish_nhwc(x, weight, bias, eps=1e-6, swish=True):
     assert x.dtype == BF16 and x.is_contiguous() and weight.dtype == F32 and bias.dtype == F32
     B, H, W, Cc = x.shape
     y = torch.empty_like(x)
-    ws = torch.empty(B * 64, dtype=torch.float64, device=x.device)
+    ws = torch.empty(_lib.lib().gh_groupnorm_ws_bytes(B, H * W) // 4, dtype=F32, device=x.device)
     check(_lib.lib().gh_groupnorm_swish_nhwc(x.data_ptr(), y.data_ptr(), B, H * W, Cc, weight.data_ptr(), bias.data_ptr(),
                                              eps, int(swish), ws.data_ptr(), _stream()))
     _count(3)

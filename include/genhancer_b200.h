@@ -248,9 +248,12 @@ int gh_im2col3x3_c3(const float* img, void* out_bf16, int32_t B, int32_t H, int3
 /* out[b,t,:] = (t < has_cls ? cls : patch[b,t-has_cls,:]) + pos[t,:]   (modeling_clip.py:210-217) */
 int gh_embed_assemble(const void* patch_bf16, const float* cls, const float* pos, void* out_bf16, int32_t B, int32_t T,
                       int32_t D, int32_t has_cls, void* stream);
-/* GroupNorm(32 groups) [+ swish] on NHWC bf16 (autoencoder.py:21-22,62-78).  ws_stats_f64: 64*B doubles. */
+/* GroupNorm(32 groups) [+ swish] on NHWC bf16 (autoencoder.py:21-22,62-78).  Three launches, no atomics
+ * (bit-reproducible): per-CTA partial sums -> fp64 finalize -> normalise + affine (+ swish).
+ * ws: gh_groupnorm_ws_bytes(B, HW) bytes of scratch, 16-byte aligned.  C % 64 == 0, C <= 2048. */
+int64_t gh_groupnorm_ws_bytes(int32_t B, int64_t HW);
 int gh_groupnorm_swish_nhwc(const void* x, void* y, int32_t B, int64_t HW, int32_t C, const float* weight,
-                            const float* bias, float eps, int32_t swish, void* ws_stats_f64, void* stream);
+                            const float* bias, float eps, int32_t swish, void* ws, void* stream);
 /* p[r,:n] = softmax(scale * s[r,:n]) fp32 -> bf16, pad columns zeroed (AE mid AttnBlock, autoencoder.py:37-52). */
 int gh_softmax_rows(const float* s, int64_t ld_in, void* p_bf16, int64_t ld_out, int32_t rows, int32_t n, float scale,
                     void* stream);
