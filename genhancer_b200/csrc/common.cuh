@@ -241,7 +241,12 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // ----------------------------------------------------------------------------
 enum Act : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_QUICK_GELU = 2, ACT_GELU_ERF = 3, ACT_SILU = 4 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));  // one MUFU op, max rel. error ~2^-11 (outputs are bf16)
+  return y;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
 __device__ __forceinline__ float act_fwd(int act, float x) {
   switch (act) {
@@ -277,6 +282,71 @@ __device__ __forceinline__ float act_bwd(int act, float x) {  // d act(x) / dx
       return s + x * s * (1.f - s);
     }
     default: return 1.f;
+  }
+}
+
+// 8-wide forms for the GEMM epilogue: ONE switch per vector so the 8 independent chains interleave (a switch per
+// element serialises them: a lone warp per scheduler then runs at instruction latency, not throughput).
+__device__ __forceinline__ void act_fwd8(int act, float (&v)[8]) {
+  switch (act) {
+    case ACT_GELU_TANH:
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float x = v[k];
+        const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+        v[k] = 0.5f * x * (1.f + tanh_approx(u));
+      }
+      break;
+    case ACT_QUICK_GELU:
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] * fmaf(0.5f, tanh_approx(0.851f * v[k]), 0.5f);
+      break;
+    case ACT_SILU:
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] * fmaf(0.5f, tanh_approx(0.5f * v[k]), 0.5f);
+      break;
+    case ACT_GELU_ERF:
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.5f * v[k] * (1.f + erff(v[k] * 0.7071067811865476f));
+      break;
+    default: break;
+  }
+}
+// v[k] *= act'(x[k])
+__device__ __forceinline__ void act_bwd_mul8(int act, const float (&x)[8], float (&v)[8]) {
+  switch (act) {
+    case ACT_GELU_TANH:
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xx = x[k];
+        const float u = 0.7978845608028654f * fmaf(0.044715f * xx * xx, xx, xx);
+        const float t = tanh_approx(u);
+        const float du = 0.7978845608028654f * fmaf(0.134145f * xx, xx, 1.f);
+        v[k] *= 0.5f * (1.f + t) + 0.5f * xx * (1.f - t * t) * du;
+      }
+      break;
+    case ACT_QUICK_GELU:
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float s = fmaf(0.5f, tanh_approx(0.851f * x[k]), 0.5f);
+        v[k] *= s + 1.702f * x[k] * s * (1.f - s);
+      }
+      break;
+    case ACT_SILU:
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float s = fmaf(0.5f, tanh_approx(0.5f * x[k]), 0.5f);
+        v[k] *= s + x[k] * s * (1.f - s);
+      }
+      break;
+    case ACT_GELU_ERF:
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float cdf = 0.5f * (1.f + erff(x[k] * 0.7071067811865476f));
+        v[k] *= cdf + x[k] * 0.3989422804014327f * __expf(-0.5f * x[k] * x[k]);
+      }
+      break;
+    default: break;
   }
 }
 

@@ -31,7 +31,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM>
-      <<<grid, 256, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
+      <<<grid, GemmCfg<BN>::THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
 }

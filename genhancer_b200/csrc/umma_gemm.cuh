@@ -70,8 +70,10 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_LD = 36;  // floats per staged row (32 + 4 pad, keeps 16B alignment)
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+  static constexpr int EPI_WARPS = 8;   // two per TMEM lane quadrant: they take alternate 16-column slices
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int EPI_LD = 20;     // floats per staged row (16 + 4 pad: conflict-free float4 access)
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + align slack
@@ -120,86 +122,94 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, const float* __restrict__ st, int ld_st,
-                                               const int (&rows)[4], uint32_t okmask, bool hi, int sub_row, int col8,
-                                               int gn) {
+// Operands of one 32-row x 16-column slice, as loaded from global memory (lane = 8 columns of 2 rows).
+struct SliceLoads {
+  float b8[8];
+  uint4 res16[2], aux[2], gt[2];
+  float4 resf[2][2];
+};
+
+__device__ __forceinline__ void slice_issue_loads(const EpilogueParams& ep, const int (&rows)[2], uint32_t okmask,
+                                                  bool hi, int gn, SliceLoads& L) {
   const bool vec8 = ep.vec8 != 0;
-  const int ACT = ep.act;           // warp-uniform runtime switches (one code path: keeps registers in check)
-  const bool ACT_GRAD = ep.act_grad != 0;
-  float b8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) L.b8[k] = 0.f;
   if (ep.bias && okmask) {
     if (ep.bias_f32) {
       const float* bp = static_cast<const float*>(ep.bias) + gn;
       const float4 x = __ldg(reinterpret_cast<const float4*>(bp));
       float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
       if (hi) y = __ldg(reinterpret_cast<const float4*>(bp + 4));
-      b8[0] = x.x; b8[1] = x.y; b8[2] = x.z; b8[3] = x.w; b8[4] = y.x; b8[5] = y.y; b8[6] = y.z; b8[7] = y.w;
+      L.b8[0] = x.x; L.b8[1] = x.y; L.b8[2] = x.z; L.b8[3] = x.w;
+      L.b8[4] = y.x; L.b8[5] = y.y; L.b8[6] = y.z; L.b8[7] = y.w;
     } else {
-      unpack8(ld8_bf16(static_cast<const __nv_bfloat16*>(ep.bias) + gn, vec8, hi), b8);
+      unpack8(ld8_bf16(static_cast<const __nv_bfloat16*>(ep.bias) + gn, vec8, hi), L.b8);
     }
   }
-  uint4 res16[4], aux[4], gt[4];
-  float4 resf[4][2];
   if (ep.residual) {
     if (ep.res_f32) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
         if (okmask >> i & 1u) {
           const float* rp = static_cast<const float*>(ep.residual) + static_cast<int64_t>(rows[i]) * ep.ld_res + gn;
-          resf[i][0] = *reinterpret_cast<const float4*>(rp);
-          resf[i][1] = hi ? *reinterpret_cast<const float4*>(rp + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          L.resf[i][0] = *reinterpret_cast<const float4*>(rp);
+          L.resf[i][1] = hi ? *reinterpret_cast<const float4*>(rp + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
         if (okmask >> i & 1u)
-          res16[i] = ld8_bf16(static_cast<const __nv_bfloat16*>(ep.residual) + static_cast<int64_t>(rows[i]) * ep.ld_res + gn,
-                              vec8, hi);
+          L.res16[i] = ld8_bf16(static_cast<const __nv_bfloat16*>(ep.residual) +
+                                static_cast<int64_t>(rows[i]) * ep.ld_res + gn, vec8, hi);
     }
   }
-  if (ACT_GRAD) {
+  if (ep.act_grad) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (okmask >> i & 1u) aux[i] = ld8_bf16(ep.aux_in + static_cast<int64_t>(rows[i]) * ep.ld_aux_in + gn, vec8, hi);
+    for (int i = 0; i < 2; ++i)
+      if (okmask >> i & 1u) L.aux[i] = ld8_bf16(ep.aux_in + static_cast<int64_t>(rows[i]) * ep.ld_aux_in + gn, vec8, hi);
   }
   if (ep.gate) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
       if (okmask >> i & 1u)
-        gt[i] = ld8_bf16(ep.gate + static_cast<int64_t>(rows[i] / ep.rows_per_batch) * ep.gate_ld + gn, vec8, hi);
+        L.gt[i] = ld8_bf16(ep.gate + static_cast<int64_t>(rows[i] / ep.rows_per_batch) * ep.gate_ld + gn, vec8, hi);
   }
+}
+
+__device__ __forceinline__ void slice_finish(const EpilogueParams& ep, const float* __restrict__ st, int ld_st,
+                                             const int (&rows)[2], uint32_t okmask, bool hi, int sub_row, int col8,
+                                             int gn, const SliceLoads& L) {
+  const bool vec8 = ep.vec8 != 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 2; ++i) {
     if (!(okmask >> i & 1u)) continue;
     const int64_t row = rows[i];
-    const float* sp = st + (i * 8 + sub_row) * ld_st + col8;
+    const float* sp = st + (i * 16 + sub_row) * ld_st + col8;
     const float4 a0 = *reinterpret_cast<const float4*>(sp), a1 = *reinterpret_cast<const float4*>(sp + 4);
     float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = v[k] * ep.alpha + b8[k];
+    for (int k = 0; k < 8; ++k) v[k] = v[k] * ep.alpha + L.b8[k];
     if (ep.aux_out) st8_bf16(ep.aux_out + row * ep.ld_aux_out + gn, v, vec8, hi);
-    if (ACT_GRAD) {
+    if (ep.act_grad) {
       float x[8];
-      unpack8(aux[i], x);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] *= act_bwd(ACT, x[k]);
-    } else if (ACT != ACT_NONE) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = act_fwd(ACT, v[k]);
+      unpack8(L.aux[i], x);
+      act_bwd_mul8(ep.act, x, v);
+    } else if (ep.act != ACT_NONE) {
+      act_fwd8(ep.act, v);
     }
     if (ep.gate) {
       float g[8];
-      unpack8(gt[i], g);
+      unpack8(L.gt[i], g);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] *= g[k];
     }
     if (ep.residual) {
       if (ep.res_f32) {
-        v[0] += resf[i][0].x; v[1] += resf[i][0].y; v[2] += resf[i][0].z; v[3] += resf[i][0].w;
-        v[4] += resf[i][1].x; v[5] += resf[i][1].y; v[6] += resf[i][1].z; v[7] += resf[i][1].w;
+        v[0] += L.resf[i][0].x; v[1] += L.resf[i][0].y; v[2] += L.resf[i][0].z; v[3] += L.resf[i][0].w;
+        v[4] += L.resf[i][1].x; v[5] += L.resf[i][1].y; v[6] += L.resf[i][1].z; v[7] += L.resf[i][1].w;
       } else {
         float r[8];
-        unpack8(res16[i], r);
+        unpack8(L.res16[i], r);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] += r[k];
       }
@@ -215,7 +225,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, const f
 }
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -252,8 +262,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], 4);  // one arrive per epilogue warp
-    mbar_init(&tempty_bar[1], 4);
+    mbar_init(&tempty_bar[0], Cfg::EPI_WARPS);  // one arrive per epilogue warp
+    mbar_init(&tempty_bar[1], Cfg::EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
@@ -345,24 +355,27 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quadrant
+    // 8 warps: warp (4 + q) and (8 + q) both own TMEM lane quadrant q (rows 32q..32q+31 of the tile) and take
+    // alternate 16-column slices.  Per slice: tcgen05.ld -> fp32 staging in smem (row-major) -> each lane handles
+    // 8 consecutive columns of 2 rows with 16-byte global accesses.  The global operands of slice s+2 are
+    // requested before slice s is processed (software prefetch), so L2 latency overlaps the math.
+    const int ew = warp - 4;
+    const int quad = ew & 3;
+    const int half = ew >> 2;
     float* st = epi_buf + ew * (32 * Cfg::EPI_LD);
+    const int sub_row = lane & 15;        // 8 consecutive lanes read 8 consecutive staged rows: conflict-free
+    const int col8 = (lane >> 4) * 8;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       decode_tile(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      const int sub_row = lane >> 2;
-      const int col8 = (lane & 3) * 8;
-      // the 4 output rows this lane touches in every chunk of the tile (row index == logical GEMM row)
-      int rows[4];
+      // the 2 output rows this lane touches in every slice of the tile (row index == logical GEMM row)
+      int rows[2];
       uint32_t rowmask = 0;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int tr = ew * 32 + it * 8 + sub_row;  // row within the 128-row tile
+      for (int it = 0; it < 2; ++it) {
+        const int tr = quad * 32 + it * 16 + sub_row;  // row within the 128-row tile
         bool ok;
         if (MODE == MODE_CONV) {
           const int tiles_per_img = p.cv.tiles_w * p.cv.tiles_h;
@@ -378,21 +391,37 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         rowmask |= static_cast<uint32_t>(ok) << it;
       }
+      const int n0 = n_blk * BN;
+      int ns = (p.N - n0 + 15) / 16;   // slices of this tile that hold real columns
+      if (ns > BN / 16) ns = BN / 16;
+      SliceLoads cur;
+      {
+        const int gn = n0 + half * 16 + col8;
+        if (half < ns) slice_issue_loads(p.ep, rows, gn < p.N ? rowmask : 0u, gn + 4 < p.N, gn, cur);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        if (n_blk * BN + c * 32 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
+      for (int sl = half; sl < ns; sl += 2) {
+        uint32_t r[16];
+        tmem_ld_32x16(t_row + sl * 16, r);
+        SliceLoads nxt;
+        if (sl + 2 < ns) {
+          const int gn2 = n0 + (sl + 2) * 16 + col8;
+          slice_issue_loads(p.ep, rows, gn2 < p.N ? rowmask : 0u, gn2 + 4 < p.N, gn2, nxt);
+        }
         tmem_ld_wait();
         float4* dst = reinterpret_cast<float4*>(st + lane * Cfg::EPI_LD);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 4; ++j)
           dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         __syncwarp();
-        const int gn = n_blk * BN + c * 32 + col8;
-        epilogue_chunk(p.ep, st, Cfg::EPI_LD, rows, gn < p.N ? rowmask : 0u, gn + 4 < p.N, sub_row, col8, gn);
+        const int gn = n0 + sl * 16 + col8;
+        slice_finish(p.ep, st, Cfg::EPI_LD, rows, gn < p.N ? rowmask : 0u, gn + 4 < p.N, sub_row, col8, gn, cur);
         __syncwarp();
+        if (sl + 2 < ns) cur = nxt;
       }
       tc_fence_before();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
