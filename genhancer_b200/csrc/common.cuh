@@ -71,10 +71,23 @@ static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar_addr, uint32_
          threadIdx.x, bar_addr, parity);
   __trap();
 }
+// try_wait with a suspend-time hint: the hardware parks the warp (no issue slots burned by a spin loop, which
+// matters when a waiting warp shares its scheduler with a working one) until the phase flips or ~hint_ns pass.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
     if (clock64() - t0 > 20000000000LL) mbar_timeout_trap(smem_u32(bar), parity);
   }
 }

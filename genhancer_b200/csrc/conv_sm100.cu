@@ -85,6 +85,7 @@ extern "C" int gh_conv2d_nhwc(const gh_conv_args* a, void* stream) {
   p.ep.rows_per_batch = 1;
   p.ep.residual = a->residual; p.ep.ld_res = a->Cout; p.ep.res_f32 = (a->res_dtype == GH_F32);
   p.ep.vec8 = (!a->bias || a->bias_dtype == GH_F32 || aligned16(a->bias)) && (!a->residual || aligned16(a->residual));
+  finalize_epilogue(p.ep);
 
   CUtensorMap ta, tb;
   {

@@ -115,6 +115,7 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
               (!a->aux_out || (a->ld_aux_out % 8 == 0 && aligned16(a->aux_out))) &&
               (!a->gate || (a->gate_ld % 8 == 0 && aligned16(a->gate))) &&
               (!a->residual || a->res_dtype == GH_F32 || (a->ld_res % 8 == 0 && aligned16(a->residual)));
+  finalize_epilogue(p.ep);
 
   CUtensorMap ta, tb;
   {

@@ -42,7 +42,12 @@ struct EpilogueParams {
   int64_t ld_res;
   int res_f32;
   int vec8;  // every epilogue operand allows 16-byte bf16 vectors (N % 8 == 0, leading dimensions % 8 == 0)
+  int fast;  // bf16 out = act(alpha*acc + bias) [+ bf16 residual], vec8: the lean path (set by finalize_epilogue)
 };
+
+inline void finalize_epilogue(EpilogueParams& ep) {
+  ep.fast = ep.vec8 && !ep.d_f32 && !ep.aux_out && !ep.act_grad && !ep.gate && (!ep.residual || !ep.res_f32);
+}
 
 struct ConvGeom {  // MODE_CONV only
   int B, Ho, Wo;   // output extent
@@ -73,7 +78,8 @@ struct GemmCfg {
   static constexpr int EPI_WARPS = 8;   // two per TMEM lane quadrant: they take alternate 16-column slices
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int EPI_LD = 20;     // floats per staged row (16 + 4 pad: conflict-free float4 access)
-  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
+  static constexpr int EPI_BIAS_FLOATS = BN / 2;  // per epilogue warp: fp32 bias of the columns that warp owns
+  static constexpr int EPI_BYTES = EPI_WARPS * (32 * EPI_LD + EPI_BIAS_FLOATS) * 4;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + align slack
@@ -125,8 +131,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 // Operands of one 32-row x 16-column slice, as loaded from global memory (lane = 8 columns of 2 rows).
 struct SliceLoads {
   float b8[8];
-  uint4 res16[2], aux[2], gt[2];
-  float4 resf[2][2];
+  uint4 res16[2], aux[2], gt[2];  // (an fp32 residual -- wgrad accumulation -- is loaded at its use instead)
 };
 
 __device__ __forceinline__ void slice_issue_loads(const EpilogueParams& ep, const int (&rows)[2], uint32_t okmask,
@@ -146,22 +151,12 @@ __device__ __forceinline__ void slice_issue_loads(const EpilogueParams& ep, cons
       unpack8(ld8_bf16(static_cast<const __nv_bfloat16*>(ep.bias) + gn, vec8, hi), L.b8);
     }
   }
-  if (ep.residual) {
-    if (ep.res_f32) {
+  if (ep.residual && !ep.res_f32) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
-        if (okmask >> i & 1u) {
-          const float* rp = static_cast<const float*>(ep.residual) + static_cast<int64_t>(rows[i]) * ep.ld_res + gn;
-          L.resf[i][0] = *reinterpret_cast<const float4*>(rp);
-          L.resf[i][1] = hi ? *reinterpret_cast<const float4*>(rp + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-        if (okmask >> i & 1u)
-          L.res16[i] = ld8_bf16(static_cast<const __nv_bfloat16*>(ep.residual) +
-                                static_cast<int64_t>(rows[i]) * ep.ld_res + gn, vec8, hi);
-    }
+    for (int i = 0; i < 2; ++i)
+      if (okmask >> i & 1u)
+        L.res16[i] = ld8_bf16(static_cast<const __nv_bfloat16*>(ep.residual) +
+                              static_cast<int64_t>(rows[i]) * ep.ld_res + gn, vec8, hi);
   }
   if (ep.act_grad) {
 #pragma unroll
@@ -205,8 +200,11 @@ __device__ __forceinline__ void slice_finish(const EpilogueParams& ep, const flo
     }
     if (ep.residual) {
       if (ep.res_f32) {
-        v[0] += L.resf[i][0].x; v[1] += L.resf[i][0].y; v[2] += L.resf[i][0].z; v[3] += L.resf[i][0].w;
-        v[4] += L.resf[i][1].x; v[5] += L.resf[i][1].y; v[6] += L.resf[i][1].z; v[7] += L.resf[i][1].w;
+        const float* rp = static_cast<const float*>(ep.residual) + row * ep.ld_res + gn;
+        const float4 f0 = *reinterpret_cast<const float4*>(rp);
+        const float4 f1 = hi ? *reinterpret_cast<const float4*>(rp + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[0] += f0.x; v[1] += f0.y; v[2] += f0.z; v[3] += f0.w;
+        v[4] += f1.x; v[5] += f1.y; v[6] += f1.z; v[7] += f1.w;
       } else {
         float r[8];
         unpack8(L.res16[i], r);
@@ -221,6 +219,89 @@ __device__ __forceinline__ void slice_finish(const EpilogueParams& ep, const flo
     } else {
       st8_bf16(static_cast<__nv_bfloat16*>(ep.d) + row * ep.ldd + gn, v, vec8, hi);
     }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Lean epilogue of one warp for one full-width tile:  bf16 out = act(alpha*acc + bias) [+ bf16 residual].
+// Compile-time activation / residual so the slice loop has no option branches; TMEM -> registers runs one slice
+// ahead of the math; the residual of slice j+1 is requested before slice j is computed.
+// ----------------------------------------------------------------------------------------------------------
+template <int BN, int ACT, bool HAS_RES>
+__device__ __forceinline__ void lean_tile(const EpilogueParams& ep, float* __restrict__ st, const float* __restrict__ bias_s,
+                                          uint32_t t_row, int half, int lane, int sub_row, int col8, int n0,
+                                          const int (&rows)[2], uint32_t rowmask) {
+  constexpr int LD = GemmCfg<BN>::EPI_LD;
+  constexpr int NJ = BN / 32;  // slices per warp
+  const bool ok0 = rowmask & 1u, ok1 = (rowmask >> 1) & 1u;
+  __nv_bfloat16* d0 = static_cast<__nv_bfloat16*>(ep.d) + static_cast<int64_t>(rows[0]) * ep.ldd + n0 + col8 + half * 16;
+  __nv_bfloat16* d1 = static_cast<__nv_bfloat16*>(ep.d) + static_cast<int64_t>(rows[1]) * ep.ldd + n0 + col8 + half * 16;
+  const __nv_bfloat16* r0 = nullptr;
+  const __nv_bfloat16* r1 = nullptr;
+  uint4 res0 = make_uint4(0, 0, 0, 0), res1 = res0;
+  if (HAS_RES) {
+    r0 = static_cast<const __nv_bfloat16*>(ep.residual) + static_cast<int64_t>(rows[0]) * ep.ld_res + n0 + col8 + half * 16;
+    r1 = static_cast<const __nv_bfloat16*>(ep.residual) + static_cast<int64_t>(rows[1]) * ep.ld_res + n0 + col8 + half * 16;
+    if (ok0) res0 = *reinterpret_cast<const uint4*>(r0);
+    if (ok1) res1 = *reinterpret_cast<const uint4*>(r1);
+  }
+  const float alpha = ep.alpha;
+  const float* sp0 = st + sub_row * LD + col8;
+  const float* sp1 = sp0 + 16 * LD;
+  float4* dst = reinterpret_cast<float4*>(st + lane * LD);
+  uint32_t treg[16];
+  tmem_ld_32x16(t_row + half * 16, treg);
+  tmem_ld_wait();
+#pragma unroll 1
+  for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      dst[q] = make_float4(__uint_as_float(treg[4 * q]), __uint_as_float(treg[4 * q + 1]),
+                           __uint_as_float(treg[4 * q + 2]), __uint_as_float(treg[4 * q + 3]));
+    __syncwarp();
+    if (j + 1 < NJ) tmem_ld_32x16(t_row + half * 16 + (j + 1) * 32, treg);
+    const float4 bb0 = *reinterpret_cast<const float4*>(bias_s + j * 16 + col8);
+    const float4 bb1 = *reinterpret_cast<const float4*>(bias_s + j * 16 + col8 + 4);
+    float v0[8], v1[8];
+    {
+      const float4 a0 = *reinterpret_cast<const float4*>(sp0), a1 = *reinterpret_cast<const float4*>(sp0 + 4);
+      const float4 c0 = *reinterpret_cast<const float4*>(sp1), c1 = *reinterpret_cast<const float4*>(sp1 + 4);
+      v0[0] = fmaf(a0.x, alpha, bb0.x); v0[1] = fmaf(a0.y, alpha, bb0.y); v0[2] = fmaf(a0.z, alpha, bb0.z); v0[3] = fmaf(a0.w, alpha, bb0.w);
+      v0[4] = fmaf(a1.x, alpha, bb1.x); v0[5] = fmaf(a1.y, alpha, bb1.y); v0[6] = fmaf(a1.z, alpha, bb1.z); v0[7] = fmaf(a1.w, alpha, bb1.w);
+      v1[0] = fmaf(c0.x, alpha, bb0.x); v1[1] = fmaf(c0.y, alpha, bb0.y); v1[2] = fmaf(c0.z, alpha, bb0.z); v1[3] = fmaf(c0.w, alpha, bb0.w);
+      v1[4] = fmaf(c1.x, alpha, bb1.x); v1[5] = fmaf(c1.y, alpha, bb1.y); v1[6] = fmaf(c1.z, alpha, bb1.z); v1[7] = fmaf(c1.w, alpha, bb1.w);
+    }
+    if (ACT != ACT_NONE) {
+      act_fwd8(ACT, v0);
+      act_fwd8(ACT, v1);
+    }
+    if (HAS_RES) {
+      float r[8];
+      unpack8(res0, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v0[k] += r[k];
+      unpack8(res1, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v1[k] += r[k];
+      if (j + 1 < NJ) {  // next slice's residual: in flight during the stores and the next staging
+        if (ok0) res0 = *reinterpret_cast<const uint4*>(r0 + (j + 1) * 32);
+        if (ok1) res1 = *reinterpret_cast<const uint4*>(r1 + (j + 1) * 32);
+      }
+    }
+    if (ok0) {
+      uint4 o;
+      o.x = pack_bf16x2(v0[0], v0[1]); o.y = pack_bf16x2(v0[2], v0[3]);
+      o.z = pack_bf16x2(v0[4], v0[5]); o.w = pack_bf16x2(v0[6], v0[7]);
+      *reinterpret_cast<uint4*>(d0 + j * 32) = o;
+    }
+    if (ok1) {
+      uint4 o;
+      o.x = pack_bf16x2(v1[0], v1[1]); o.y = pack_bf16x2(v1[2], v1[3]);
+      o.z = pack_bf16x2(v1[4], v1[5]); o.w = pack_bf16x2(v1[6], v1[7]);
+      *reinterpret_cast<uint4*>(d1 + j * 32) = o;
+    }
+    __syncwarp();
+    if (j + 1 < NJ) tmem_ld_wait();
   }
 }
 
@@ -363,8 +444,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quad = ew & 3;
     const int half = ew >> 2;
     float* st = epi_buf + ew * (32 * Cfg::EPI_LD);
+    float* bias_s = epi_buf + Cfg::EPI_WARPS * (32 * Cfg::EPI_LD) + ew * Cfg::EPI_BIAS_FLOATS;
     const int sub_row = lane & 15;        // 8 consecutive lanes read 8 consecutive staged rows: conflict-free
     const int col8 = (lane >> 4) * 8;
+    const EpilogueParams& ep = p.ep;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -392,36 +475,72 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         rowmask |= static_cast<uint32_t>(ok) << it;
       }
       const int n0 = n_blk * BN;
-      int ns = (p.N - n0 + 15) / 16;   // slices of this tile that hold real columns
-      if (ns > BN / 16) ns = BN / 16;
-      SliceLoads cur;
-      {
-        const int gn = n0 + half * 16 + col8;
-        if (half < ns) slice_issue_loads(p.ep, rows, gn < p.N ? rowmask : 0u, gn + 4 < p.N, gn, cur);
-      }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
-#pragma unroll 1
-      for (int sl = half; sl < ns; sl += 2) {
-        uint32_t r[16];
-        tmem_ld_32x16(t_row + sl * 16, r);
-        SliceLoads nxt;
-        if (sl + 2 < ns) {
-          const int gn2 = n0 + (sl + 2) * 16 + col8;
-          slice_issue_loads(p.ep, rows, gn2 < p.N ? rowmask : 0u, gn2 + 4 < p.N, gn2, nxt);
+      if (ep.fast && n0 + BN <= p.N) {
+        // ---------------- lean path: bf16 out = act(alpha*acc + bias) [+ bf16 residual], full-width tile ----------------
+        // bias of this warp's columns -> smem (fp32) while the accumulator is still being produced
+        for (int idx = lane; idx < Cfg::EPI_BIAS_FLOATS; idx += 32) {
+          const int col = n0 + (half + 2 * (idx >> 4)) * 16 + (idx & 15);
+          float bv = 0.f;
+          if (ep.bias)
+            bv = ep.bias_f32 ? __ldg(static_cast<const float*>(ep.bias) + col)
+                             : __bfloat162float(static_cast<const __nv_bfloat16*>(ep.bias)[col]);
+          bias_s[idx] = bv;
         }
-        tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(st + lane * Cfg::EPI_LD);
+        __syncwarp();
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#define GH_LEAN(A, R) lean_tile<BN, A, R>(ep, st, bias_s, t_row, half, lane, sub_row, col8, n0, rows, rowmask)
+        if (ep.residual) {
+          switch (ep.act) {
+            case ACT_GELU_TANH: GH_LEAN(ACT_GELU_TANH, true); break;
+            case ACT_QUICK_GELU: GH_LEAN(ACT_QUICK_GELU, true); break;
+            case ACT_SILU: GH_LEAN(ACT_SILU, true); break;
+            case ACT_GELU_ERF: GH_LEAN(ACT_GELU_ERF, true); break;
+            default: GH_LEAN(ACT_NONE, true); break;
+          }
+        } else {
+          switch (ep.act) {
+            case ACT_GELU_TANH: GH_LEAN(ACT_GELU_TANH, false); break;
+            case ACT_QUICK_GELU: GH_LEAN(ACT_QUICK_GELU, false); break;
+            case ACT_SILU: GH_LEAN(ACT_SILU, false); break;
+            case ACT_GELU_ERF: GH_LEAN(ACT_GELU_ERF, false); break;
+            default: GH_LEAN(ACT_NONE, false); break;
+          }
+        }
+#undef GH_LEAN
+      } else {
+        // ---------------- general path (every epilogue option, edge tiles) ----------------
+        int ns = (p.N - n0 + 15) / 16;   // slices of this tile that hold real columns
+        if (ns > BN / 16) ns = BN / 16;
+        SliceLoads LA, LB;
+        auto issue = [&](int sl, SliceLoads& L) {
+          const int gn = n0 + sl * 16 + col8;
+          slice_issue_loads(ep, rows, gn < p.N ? rowmask : 0u, gn + 4 < p.N, gn, L);
+        };
+        auto run = [&](int sl, const SliceLoads& L, int next_sl, SliceLoads& Lnext) {
+          uint32_t r[16];
+          tmem_ld_32x16(t_row + sl * 16, r);
+          if (next_sl < ns) issue(next_sl, Lnext);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(st + lane * Cfg::EPI_LD);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        __syncwarp();
-        const int gn = n0 + sl * 16 + col8;
-        slice_finish(p.ep, st, Cfg::EPI_LD, rows, gn < p.N ? rowmask : 0u, gn + 4 < p.N, sub_row, col8, gn, cur);
-        __syncwarp();
-        if (sl + 2 < ns) cur = nxt;
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                 __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          __syncwarp();
+          const int gn = n0 + sl * 16 + col8;
+          slice_finish(ep, st, Cfg::EPI_LD, rows, gn < p.N ? rowmask : 0u, gn + 4 < p.N, sub_row, col8, gn, L);
+          __syncwarp();
+        };
+        if (half < ns) issue(half, LA);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int sl = half; sl < ns; sl += 4) {
+          run(sl, LA, sl + 2, LB);
+          if (sl + 2 < ns) run(sl + 2, LB, sl + 4, LA);
+        }
       }
       tc_fence_before();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);

@@ -112,13 +112,22 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
   const int64_t p1 = min(p0 + pix_per_cta, HW);
   float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};  // one slot per channel pair (cpg >= 2)
   if (my_p < ppi) {
-    for (int64_t pix = p0 + my_p; pix < p1; pix += ppi) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(b) * HW + pix) * C + my_c);
-      const float2 a = unpack_bf16x2(u.x), c2 = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), g = unpack_bf16x2(u.w);
-      s[0] += a.x + a.y;   ss[0] += a.x * a.x + a.y * a.y;
-      s[1] += c2.x + c2.y; ss[1] += c2.x * c2.x + c2.y * c2.y;
-      s[2] += e.x + e.y;   ss[2] += e.x * e.x + e.y * e.y;
-      s[3] += g.x + g.y;   ss[3] += g.x * g.x + g.y * g.y;
+    const bf16* xb = x + static_cast<int64_t>(b) * HW * C + my_c;
+    for (int64_t pix = p0 + my_p; pix < p1; pix += 4 * ppi) {
+      uint4 u[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t pp = pix + static_cast<int64_t>(q) * ppi;
+        u[q] = pp < p1 ? *reinterpret_cast<const uint4*>(xb + pp * C) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a = unpack_bf16x2(u[q].x), c2 = unpack_bf16x2(u[q].y), e = unpack_bf16x2(u[q].z), g = unpack_bf16x2(u[q].w);
+        s[0] += a.x + a.y;   ss[0] += a.x * a.x + a.y * a.y;
+        s[1] += c2.x + c2.y; ss[1] += c2.x * c2.x + c2.y * c2.y;
+        s[2] += e.x + e.y;   ss[2] += e.x * e.x + e.y * e.y;
+        s[3] += g.x + g.y;   ss[3] += g.x * g.x + g.y * g.y;
+      }
     }
   }
 #pragma unroll
@@ -153,34 +162,54 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, float2* __
   mr[i] = make_float2(static_cast<float>(mean), rsqrtf(var + eps));
 }
 
+// Each thread owns 8 fixed channels (its scale/shift live in registers for the whole kernel) and walks over
+// pixels, 4 independent 16-byte loads in flight per thread.  y = x * (rstd*w) + (b - mean*rstd*w), then swish.
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float2* __restrict__ mr,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                       bf16* __restrict__ y, int64_t HW, int C, int swish, int64_t n8) {
+                                                       bf16* __restrict__ y, int64_t HW, int C, int swish,
+                                                       int pix_per_cta) {
+  const int b = blockIdx.y;
+  const int tpp = C / 8;
+  const int ppi = blockDim.x / tpp;
+  const int my_c = (threadIdx.x % tpp) * 8;
+  const int my_p = threadIdx.x / tpp;
+  if (my_p >= ppi) return;
   const int cpg = C / 32;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    const int c = static_cast<int>((i * 8) % C);
-    const int b = static_cast<int>(i * 8 / (HW * C));
-    const uint4 u = reinterpret_cast<const uint4*>(x)[i];
-    const float2 a = unpack_bf16x2(u.x), c2 = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), g = unpack_bf16x2(u.w);
-    float v[8] = {a.x, a.y, c2.x, c2.y, e.x, e.y, g.x, g.y};
-    const float4 w0 = *reinterpret_cast<const float4*>(w + c), w1 = *reinterpret_cast<const float4*>(w + c + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
-    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float2 st = __ldg(mr + b * 32 + (my_c + k) / cpg);
+    const float wk = __ldg(w + my_c + k), bk = __ldg(bias + my_c + k);
+    sc[k] = st.y * wk;
+    sh[k] = fmaf(-st.x, sc[k], bk);
+  }
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_cta;
+  const int64_t p1 = min(p0 + pix_per_cta, HW);
+  const bf16* xb = x + static_cast<int64_t>(b) * HW * C + my_c;
+  bf16* yb = y + static_cast<int64_t>(b) * HW * C + my_c;
+  for (int64_t pix = p0 + my_p; pix < p1; pix += 4 * ppi) {
+    uint4 u[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 st = __ldg(mr + b * 32 + (c + q * 2) / cpg);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float t = (v[q * 2 + j] - st.x) * st.y * wv[q * 2 + j] + bv[q * 2 + j];
-        if (swish) t = t * sigmoidf_(t);
-        v[q * 2 + j] = t;
-      }
+      const int64_t pp = pix + static_cast<int64_t>(q) * ppi;
+      if (pp < p1) u[q] = __ldcs(reinterpret_cast<const uint4*>(xb + pp * C));
     }
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    reinterpret_cast<uint4*>(y)[i] = o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t pp = pix + static_cast<int64_t>(q) * ppi;
+      if (pp >= p1) continue;
+      const float2 a = unpack_bf16x2(u[q].x), c2 = unpack_bf16x2(u[q].y), e = unpack_bf16x2(u[q].z), g = unpack_bf16x2(u[q].w);
+      float v[8] = {a.x, a.y, c2.x, c2.y, e.x, e.y, g.x, g.y};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float t = fmaf(v[k], sc[k], sh[k]);
+        if (swish) t = t * sigmoidf_(t);
+        v[k] = t;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(yb + pp * C) = o;
+    }
   }
 }
 
@@ -298,10 +327,8 @@ extern "C" int gh_groupnorm_swish_nhwc(const void* x, void* y, int32_t B, int64_
   GH_CHECK_CUDA(cudaGetLastError());
   gn_finalize_kernel<<<(B * 32 + 127) / 128, 128, 0, s>>>(partial, mr, B, nblk, static_cast<double>(HW) * (C / 32), eps);
   GH_CHECK_CUDA(cudaGetLastError());
-  const int64_t n8 = static_cast<int64_t>(B) * HW * C / 8;
-  const int64_t want = (n8 + 255) / 256;
-  const int g2 = static_cast<int>(want < 16L * num_sms() ? want : 16L * num_sms());
-  gn_apply_kernel<<<g2, 256, 0, s>>>(static_cast<const bf16*>(x), mr, weight, bias, static_cast<bf16*>(y), HW, C, swish, n8);
+  gn_apply_kernel<<<dim3(nblk, B), 256, 0, s>>>(static_cast<const bf16*>(x), mr, weight, bias, static_cast<bf16*>(y), HW, C,
+                                                swish, pix_per_cta);
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
 }
