@@ -259,7 +259,7 @@ def projector_key_shapes(prefix: str, in_dim: int, out_dim: int) -> dict:
 
 def adapter_key_shapes(in_dim: int = 1024, out_dim: int = 4096) -> dict:
     """VisualPromptAdapter, R/train_OpenAICLIP_video_stage1.py:85-97."""
-    mid = out_dim // 2
+    mid = in_dim * 2  # nn.Linear(in_dim, in_dim * 2), train_OpenAICLIP_video_stage1.py:90
     return {"proj.0.weight": (mid, in_dim), "proj.0.bias": (mid,), "proj.2.weight": (out_dim, mid),
             "proj.2.bias": (out_dim,), "proj.3.weight": (out_dim,), "proj.3.bias": (out_dim,)}
 
@@ -643,6 +643,39 @@ def stage1_image_step(sd_tower, sd_wrap, sd_dit, sd_ae, img01, tcfg: TowerCfg, f
                         torch.full((B,), 4.0, device=dev, dtype=wd))
     loss = F.mse_loss(pred.float(), (x_0 - x_1).float(), reduction="mean")
     return StepOut(loss, pred, x_t, x_1, cls, vec, txt)
+
+
+def stage1_video_step(sd_tower, sd_adapter, sd_dit, sd_ae, cond_frames, target, tcfg: TowerCfg, fcfg: FluxCfg,
+                      acfg: AECfg, clip_mean, clip_std, cond_times, target_time, ae_noise, t, x_0,
+                      dit_dtype=torch.float32, lora=None) -> StepOut:
+    """One video-mode micro-step (R/train_OpenAICLIP_video_stage1.py:355-452 and the nextpredic / use2frames /
+    sliding-window variants): per-patch tokens of the conditioning frames -> VisualPromptAdapter ->
+    the DiT's txt stream with (time,row,col) ids; vec = mean over frames of visual_projection(pooler_output);
+    the target frame's latent gets time index `target_time`."""
+    dev = target.device
+    mean = torch.as_tensor(clip_mean, dtype=torch.float32, device=dev).view(1, -1, 1, 1)
+    std = torch.as_tensor(clip_std, dtype=torch.float32, device=dev).view(1, -1, 1, 1)
+    with torch.no_grad():
+        x_1 = ae_encode(sd_ae, ((target - 0.5) / 0.5).float(), acfg, ae_noise)
+    patches, vecs = [], []
+    for f in cond_frames:
+        lhs, pooled = tower_forward(sd_tower, (f - mean) / std, tcfg, lora)
+        patches.append(lhs[:, 1:, :])
+        vecs.append(F.linear(pooled, sd_tower["visual_projection.weight"]))
+    vec = sum(vecs) / len(vecs)
+    txt = adapter_forward(sd_adapter, torch.cat(patches, dim=1))
+    B, _, h, w = x_1.shape
+    g = int(round(patches[0].shape[1] ** 0.5))
+    txt_ids = torch.cat([create_spatio_temporal_ids(B, tt, g, g) for tt in cond_times], dim=1).to(dev)
+    img_ids = make_img_ids(B, h // 2, w // 2, float(target_time)).to(dev)
+    x_1 = patchify(x_1)
+    x_t = fm_interp(x_1, x_0, t)
+    wd = dit_dtype
+    sd_d = sd_dit if wd == torch.float32 else {k: v.to(wd) for k, v in sd_dit.items()}
+    pred = flux_forward(sd_d, fcfg, x_t.to(wd), img_ids.to(wd), txt.to(wd), txt_ids.to(wd), t.to(wd), vec.to(wd),
+                        torch.full((B,), 4.0, device=dev, dtype=wd))
+    loss = F.mse_loss(pred.float(), (x_0 - x_1).float(), reduction="mean")
+    return StepOut(loss, pred, x_t, x_1, vecs[0], vec, txt, extras=dict(txt_ids=txt_ids, img_ids=img_ids))
 
 
 def lora_merge(w: torch.Tensor, A: torch.Tensor, Bm: torch.Tensor, scaling: float) -> torch.Tensor:

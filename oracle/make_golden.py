@@ -310,6 +310,118 @@ def golden_step_small(seed=41):
                os.path.join(GOLD, "step_small.pt"))
 
 
+def extract_from_reference(script: str, names: list[str]) -> dict:
+    """exec the named top-level classes / functions of a reference train script WITHOUT importing the script
+    (importing needs accelerate / diffusers / peft / omegaconf, none of which are installed)."""
+    import ast
+    import random
+    import torch.nn as nn
+    src = open(os.path.join(REF, script)).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "nn": nn, "random": random, "F": F}
+    for node in tree.body:
+        if isinstance(node, (ast.ClassDef, ast.FunctionDef)) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), script, "exec"), ns)
+    missing = [n for n in names if n not in ns]
+    assert not missing, missing
+    return ns
+
+
+def golden_video_small(seed=51):
+    """Video-mode stage-1 step at reduced size through the reference's OWN pieces: AutoEncoder, HF CLIPModel inside
+    the reference OpenAICLIP wrapper, Flux, prepare_clip (for img_ids), and VisualPromptAdapter /
+    create_spatio_temporal_ids / build_windows_with_mask lifted out of the reference train scripts by AST.
+    Wiring = use2frames next-frame prediction (cond frames t=0,1 -> target t=2), the step body of
+    train_OpenAICLIP_use2frames_nextpredic_stage1.py:355-452."""
+    print("[video step (use2frames wiring), reduced sizes]")
+    ns = extract_from_reference("train_OpenAICLIP_use2frames_nextpredic_stage1.py",
+                                ["VisualPromptAdapter", "create_spatio_temporal_ids"])
+    ns_w = extract_from_reference("train_OpenAICLIP_sliding_windows_nextpredic_stage1.py", ["build_windows_with_mask"])
+    tc = O.TowerCfg("clip", 128, 2, 2, 512, 112, 14, 64, 1e-5, "quick_gelu")
+    fc = O.FluxCfg(vec_in_dim=64, context_in_dim=96, hidden_size=256, num_heads=2, depth=1, depth_single_blocks=1)
+    ac = O.AECfg(ch=64)
+    wrap, sd_t, sd_w, ks_t, ks_w = build_reference_wrapper(tc, 32, 48, seed)
+    adapter = ns["VisualPromptAdapter"](in_dim=128, out_dim=96)
+    ks_ad = O.adapter_key_shapes(128, 96)
+    sd_ad = O.synth_state_dict(ks_ad, seed + 4)
+    adapter.load_state_dict(sd_ad, strict=True)
+    dit = ref_flux(fc)
+    ks_d = O.flux_key_shapes(fc)
+    sd_d = O.synth_state_dict(ks_d, seed + 2)
+    dit.load_state_dict(sd_d, strict=True)
+    ae = AutoEncoder(AutoEncoderParams(resolution=256, in_channels=3, ch=ac.ch, out_ch=3, ch_mult=list(ac.ch_mult),
+                                       num_res_blocks=2, z_channels=16, scale_factor=ac.scale_factor,
+                                       shift_factor=ac.shift_factor))
+    ks_a = O.ae_encoder_key_shapes(ac)
+    sd_a = O.synth_state_dict(ks_a, seed + 3)
+    ae.encoder.load_state_dict(sd_a, strict=True)
+    wrap.requires_grad_(False)
+    ae.requires_grad_(False)
+    g = torch.Generator().manual_seed(seed)
+    B, T, S = 2, 5, 112
+    frames = torch.rand(B, T, 3, S, S, generator=g)
+    frame_mask = torch.tensor([[1, 1, 1, 1, 1], [1, 1, 1, 1, 0]], dtype=torch.bool)
+    # --- window builder (sliding script) ---
+    import random
+    random.seed(seed)
+    c0, c1, c2, tgt, avg_nw, bs_eff = ns_w["build_windows_with_mask"](frames, frame_mask, 3, 1, 8)
+    random.seed(seed)
+    conds_o, tgt_o, counts = O.build_windows_with_mask(frames, frame_mask.long(), 3, 1, 8, rng=random)
+    assert torch.equal(conds_o[0], c0) and torch.equal(conds_o[2], c2) and torch.equal(tgt_o, tgt)
+    assert sum(counts) == bs_eff
+    # --- the use2frames step body: cond = frames 0 and 1 of each clip, target = frame 2 ---
+    cond0, cond1, target = frames[:, 0], frames[:, 1], frames[:, 2]
+    mean = torch.tensor(OPENAI_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(OPENAI_STD).view(1, 3, 1, 1)
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        x_1 = ae.encode(((target - 0.5) / 0.5).float())
+        out0 = wrap.model.vision_model((cond0 - mean) / std, output_hidden_states=True)
+        out1 = wrap.model.vision_model((cond1 - mean) / std, output_hidden_states=True)
+        p0, p1 = out0.last_hidden_state[:, 1:, :], out1.last_hidden_state[:, 1:, :]
+        vec = (wrap.model.visual_projection(out0.pooler_output) + wrap.model.visual_projection(out1.pooler_output)) / 2
+    txt = adapter(torch.cat([p0, p1], dim=1))
+    side = int(p0.shape[1] ** 0.5)
+    ids0 = ns["create_spatio_temporal_ids"](side, side, time_step=0, device="cpu")
+    ids1 = ns["create_spatio_temporal_ids"](side, side, time_step=1, device="cpu")
+    txt_ids = torch.cat([ids0, ids1], dim=0)[None].repeat(B, 1, 1).float()
+    dummy = prepare_clip(wrap, (cond0 - mean) / std, x_1)
+    img_ids = dummy["img_ids"].clone()  # on the GPU the reference's .to(device) materialises the expanded view
+    img_ids[..., 0] = 2.0
+    x_1p = rearrange(x_1, "b c (h ph) (w pw) -> b (h w) (c ph pw)", ph=2, pw=2)
+    t = torch.sigmoid(torch.randn((B,)) * 1.0)
+    x_0 = torch.randn_like(x_1p)
+    x_t = (1 - t[:, None, None]) * x_1p + t[:, None, None] * x_0
+    pred = dit(img=x_t, img_ids=img_ids, txt=txt, txt_ids=txt_ids, y=vec, timesteps=t, guidance=torch.full((B,), 4.0))
+    loss = F.mse_loss(pred.float(), (x_0 - x_1p).float(), reduction="mean")
+    loss.backward()
+    # --- oracle ---
+    torch.manual_seed(seed)
+    noise = torch.randn(B, 16, S // 8, S // 8)
+    sda = {k: v.clone().requires_grad_(True) for k, v in sd_ad.items()}
+    sdd = {k: v.clone().requires_grad_(True) for k, v in sd_d.items()}
+    out = O.stage1_video_step(sd_t, sda, sdd, sd_a, [cond0, cond1], target, tc, fc, ac, OPENAI_MEAN, OPENAI_STD,
+                              (0, 1), 2, noise, t, x_0)
+    out.loss.backward()
+    close(out.extras["txt_ids"], txt_ids, 0, "txt_ids")
+    close(out.extras["img_ids"], img_ids, 0, "img_ids")
+    close(out.txt, txt, 5e-5, "txt (adapter output)")
+    close(out.vec, vec, 2e-5, "vec")
+    close(out.pred, pred, 5e-5, "pred")
+    close(out.loss, loss, 1e-5, "loss")
+    close(sda["proj.2.weight"].grad, adapter.proj[2].weight.grad, 5e-4, "d adapter.proj.2.weight")
+    close(sdd["txt_in.weight"].grad, dit.txt_in.weight.grad, 5e-4, "d txt_in.weight")
+    torch.save(dict(kind="video_step", tower_cfg=tc.__dict__, flux_cfg=fc.__dict__, ae_cfg=ac.__dict__, seed=seed,
+                    key_shapes=dict(tower=ks_t, adapter=ks_ad, dit=ks_d, ae=ks_a), frames=frames, frame_mask=frame_mask,
+                    windows=dict(cond0=c0, cond2=c2, target=tgt, avg_nw=avg_nw, bs_eff=bs_eff),
+                    cond_times=(0, 1), target_time=2, ae_noise=noise, t=t, x_0=x_0, x_1=x_1p.detach(), txt=txt.detach(),
+                    txt_ids=txt_ids, img_ids=img_ids, vec=vec.detach(), pred=pred.detach(), loss=loss.detach(),
+                    grad_adapter_proj2_weight=adapter.proj[2].weight.grad.clone(),
+                    grad_adapter_proj3_bias=adapter.proj[3].bias.grad.clone(),
+                    grad_txt_in_weight=dit.txt_in.weight.grad.clone()),
+               os.path.join(GOLD, "video_step_small.pt"))
+
+
 def golden_cfg1_full(seed=0):
     """BASELINE config 1 at FULL size (ViT-L/14-224 + full DiT + full AE, B=2, fp32, CPU) through the reference."""
     print("[cfg-1 full-size step through the reference -- ~1 min]")
@@ -360,16 +472,25 @@ def golden_cfg1_full(seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="", help="comma-separated subset: tower,ae,flux,step,video")
     ap.add_argument("--full", action="store_true", help="also run BASELINE config 1 at full size (~1-2 min, ~12 GB)")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    golden_tower("clip_small", O.TowerCfg("clip", 128, 2, 2, 512, 56, 14, 64, 1e-5, "quick_gelu"))
-    golden_tower("siglip_small", O.TowerCfg("siglip", 144, 2, 2, 304, 56, 14, 144, 1e-6, "gelu_tanh"))
-    golden_ae()
-    golden_flux("img", n_txt=1)
-    golden_flux("video", n_txt=8, video_ids=True)
-    golden_step_small()
+    only = set(filter(None, args.only.split(",")))
+    want = lambda k: not only or k in only
+    if want("tower"):
+        golden_tower("clip_small", O.TowerCfg("clip", 128, 2, 2, 512, 56, 14, 64, 1e-5, "quick_gelu"))
+        golden_tower("siglip_small", O.TowerCfg("siglip", 144, 2, 2, 304, 56, 14, 144, 1e-6, "gelu_tanh"))
+    if want("ae"):
+        golden_ae()
+    if want("flux"):
+        golden_flux("img", n_txt=1)
+        golden_flux("video", n_txt=8, video_ids=True)
+    if want("step"):
+        golden_step_small()
+    if want("video"):
+        golden_video_small()
     if args.full:
         golden_cfg1_full()
     print("golden fixtures written to", GOLD)

@@ -119,3 +119,43 @@ def test_window_builder_and_ids():
     ids = O.create_spatio_temporal_ids(2, 2, 3, 4)
     assert ids.shape == (2, 12, 3) and ids[0, 5].tolist() == [2.0, 1.0, 1.0]
     assert O.lora_merge(torch.zeros(4, 3), torch.ones(2, 3), torch.ones(4, 2), 0.5).eq(1.0).all()
+
+
+def test_oracle_video_step_and_window_builder():
+    import random
+    fx = load_golden("video_step_small.pt")
+    tc, fc, ac = O.TowerCfg(**fx["tower_cfg"]), O.FluxCfg(**fx["flux_cfg"]), O.AECfg(**fx["ae_cfg"])
+    ks, seed = fx["key_shapes"], fx["seed"]
+    sd_t = O.synth_state_dict(ks["tower"], seed)
+    sd_ad = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(ks["adapter"], seed + 4).items()}
+    sd_d = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(ks["dit"], seed + 2).items()}
+    sd_a = O.synth_state_dict(ks["ae"], seed + 3)
+    fr = fx["frames"]
+    out = O.stage1_video_step(sd_t, sd_ad, sd_d, sd_a, [fr[:, 0], fr[:, 1]], fr[:, 2], tc, fc, ac, OPENAI_MEAN, OPENAI_STD,
+                              fx["cond_times"], fx["target_time"], fx["ae_noise"], fx["t"], fx["x_0"])
+    out.loss.backward()
+    assert torch.equal(out.extras["txt_ids"], fx["txt_ids"]) and torch.equal(out.extras["img_ids"], fx["img_ids"])
+    assert rel_err(out.txt, fx["txt"]) < 1e-5 and rel_err(out.vec, fx["vec"]) < 1e-5
+    assert rel_err(out.pred, fx["pred"]) < 5e-5
+    assert abs(out.loss.item() - fx["loss"].item()) / fx["loss"].item() < 1e-5
+    assert rel_err(sd_ad["proj.2.weight"].grad, fx["grad_adapter_proj2_weight"]) < 5e-4
+    assert rel_err(sd_d["txt_in.weight"].grad, fx["grad_txt_in_weight"]) < 5e-4
+    # window builder vs the reference's own function (fixture) -- oracle and product host code
+    conds, tgt, counts = O.build_windows_with_mask(fr, fx["frame_mask"].long(), 3, 1, 8, rng=random)
+    w = fx["windows"]
+    assert torch.equal(conds[0], w["cond0"]) and torch.equal(conds[2], w["cond2"]) and torch.equal(tgt, w["target"])
+    from genhancer_b200.video import build_windows_with_mask, create_spatio_temporal_ids
+    c0, c1, c2, t2, avg_nw, bs_eff = build_windows_with_mask(fr, fx["frame_mask"], 3, 1, 8)
+    assert torch.equal(c0, w["cond0"]) and torch.equal(c2, w["cond2"]) and torch.equal(t2, w["target"])
+    assert avg_nw == w["avg_nw"] and bs_eff == w["bs_eff"]
+    assert build_windows_with_mask(fr[:, :3], fx["frame_mask"][:, :3], 3, 1, 8) is None      # too short for a window
+    g = int(round((fx["txt_ids"].shape[1] // 2) ** 0.5))
+    ids = torch.cat([create_spatio_temporal_ids(g, g, t, "cpu") for t in fx["cond_times"]], 0).float()
+    assert torch.equal(ids, fx["txt_ids"][0])
+    # more windows than the cap: random.sample with the caller's RNG state, then sorted (reference semantics)
+    long_fr = torch.arange(14).float().view(1, 14, 1, 1, 1).expand(1, 14, 3, 2, 2)
+    random.seed(3)
+    a = build_windows_with_mask(long_fr, torch.ones(1, 14, dtype=torch.bool), 3, 1, 4)
+    random.seed(3)
+    starts = sorted(random.sample(list(range(0, 11)), k=4))
+    assert a[3][:, 0, 0, 0].tolist() == [float(s + 3) for s in starts] and a[5] == 4
