@@ -58,6 +58,29 @@ def siglip_so400m(image_size: int) -> TowerConfig:
     return TowerConfig("siglip", 1152, 27, 16, 4304, image_size, 14, 1152, 1e-6, "gelu_pytorch_tanh")
 
 
+def _pad_heads_out(t: torch.Tensor, n_heads: int, d: int, dp: int) -> torch.Tensor:
+    """Rows (or entries) grouped as n_heads blocks of d -> blocks of dp with zero rows appended per head: the output
+    features of a q/k/v projection laid out for the attention kernel's head_dim (72 / 80 -> 128 with zero lanes,
+    SURVEY.md R3; exact: zero q/k lanes add nothing to the scores, zero v lanes give zero outputs)."""
+    if d == dp:
+        return t.detach()
+    t = t.detach()
+    shp = t.shape
+    out = torch.zeros((n_heads, dp) + tuple(shp[1:]), dtype=t.dtype, device=t.device)
+    out[:, :d] = t.reshape((n_heads, d) + tuple(shp[1:]))
+    return out.reshape((n_heads * dp,) + tuple(shp[1:]))
+
+
+def _pad_heads_in(w: torch.Tensor, n_heads: int, d: int, dp: int) -> torch.Tensor:
+    """[N, n_heads*d] -> [N, n_heads*dp]: the input features of the out-projection, zero columns for the pad lanes."""
+    if d == dp:
+        return w.detach()
+    w = w.detach()
+    out = torch.zeros(w.shape[0], n_heads, dp, dtype=w.dtype, device=w.device)
+    out[:, :, :d] = w.reshape(w.shape[0], n_heads, d)
+    return out.reshape(w.shape[0], n_heads * dp)
+
+
 class _Attn(nn.Module):
     def __init__(self, d):
         super().__init__()
@@ -120,6 +143,15 @@ class VisionTransformer(nn.Module):
         self._cache_key = None
         self._init_weights()
 
+    @property
+    def head_dim_padded(self) -> int:
+        d = self.config.hidden_size // self.config.num_attention_heads
+        if d in (64, 128):
+            return d
+        if d < 128 and d % 8 == 0:
+            return 128
+        raise NotImplementedError(f"head_dim {d}: the sm_100a attention kernels take 64 or 128 (72 / 80 are zero-padded)")
+
     def _init_weights(self):  # HF _init_weights flavour (modeling_clip.py:403-459): small normal, unit LayerNorm
         c = self.config
         std = c.hidden_size ** -0.5
@@ -157,15 +189,28 @@ class VisionTransformer(nn.Module):
         b16 = lambda t: t.detach().to(BF16).contiguous()
         if c.kind == "clip":
             W["pre_ln"] = (f(self.pre_layrnorm.weight), f(self.pre_layrnorm.bias))
+        H = c.num_attention_heads
+        d = D // H
+        dp = self.head_dim_padded
         W["layers"] = []
         for l in self.encoder.layers:
             a = l.self_attn
             W["layers"].append(dict(
                 ln1=(f(l.layer_norm1.weight), f(l.layer_norm1.bias)), ln2=(f(l.layer_norm2.weight), f(l.layer_norm2.bias)),
-                wqkv=b16(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)),
-                bqkv=f(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0)),
-                wo=b16(a.out_proj.weight), bo=f(a.out_proj.bias),
+                wqkv=b16(_pad_heads_out(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0), 3 * H, d, dp)),
+                bqkv=f(_pad_heads_out(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0), 3 * H, d, dp)),
+                wo=b16(_pad_heads_in(a.out_proj.weight, H, d, dp)), bo=f(a.out_proj.bias),
                 w1=b16(l.mlp.fc1.weight), b1=f(l.mlp.fc1.bias), w2=b16(l.mlp.fc2.weight), b2=f(l.mlp.fc2.bias)))
+        if c.kind == "siglip":  # MAP head: nn.MultiheadAttention packs q,k,v in in_proj_{weight,bias}
+            hd = self.head
+            Wi, bi = hd.attention.in_proj_weight, hd.attention.in_proj_bias
+            W["head"] = dict(
+                probe=b16(hd.probe.reshape(1, D)),
+                wq=b16(_pad_heads_out(Wi[:D], H, d, dp)), bq=f(_pad_heads_out(bi[:D], H, d, dp)),
+                wkv=b16(_pad_heads_out(Wi[D:], 2 * H, d, dp)), bkv=f(_pad_heads_out(bi[D:], 2 * H, d, dp)),
+                wo=b16(_pad_heads_in(hd.attention.out_proj.weight, H, d, dp)), bo=f(hd.attention.out_proj.bias),
+                ln=(f(hd.layernorm.weight), f(hd.layernorm.bias)),
+                w1=b16(hd.mlp.fc1.weight), b1=f(hd.mlp.fc1.bias), w2=b16(hd.mlp.fc2.weight), b2=f(hd.mlp.fc2.bias))
         W["post_ln"] = (f(self.post_layernorm.weight), f(self.post_layernorm.bias))
         self._cache, self._cache_key = W, key
         return W
@@ -174,37 +219,47 @@ class VisionTransformer(nn.Module):
         """pixel_values: normalised images [B,3,S,S] (any float dtype).  `_norm=(mean3, std3)` lets the fused
         training step hand over raw [0,1] images and fold transforms.Normalize into the im2col gather."""
         c = self.config
-        if c.hidden_size // c.num_attention_heads != 64:
-            raise NotImplementedError(
-                f"head_dim {c.hidden_size // c.num_attention_heads}: the sm_100a ViT attention kernel is built for 64 "
-                "(OpenAI / MetaCLIP ViT-L/14); SigLIP-so400m (72) and ViT-H (80) are the next rows of SURVEY.md 8(a)")
         W = self._prepared()
         B = pixel_values.shape[0]
         D, H, T = c.hidden_size, c.num_attention_heads, c.num_tokens
-        d = D // H
+        d, dp = D // H, self.head_dim_padded
         act = ACT_QUICK_GELU if c.hidden_act == "quick_gelu" else ACT_GELU_TANH
+        eps = c.layer_norm_eps
         img = pixel_values.float().contiguous()
         mean, std = _norm if _norm is not None else (None, None)
         A = K.patch_im2col(img, c.patch_size, W["patch_ld"], mean, std)
         patch = K.gemm(A, W["patch_w"], bias=W["patch_b"])
         x = K.embed_assemble(patch, W["cls"], W["pos"], B, T, D)
         if c.kind == "clip":
-            x, _, _ = K.layernorm_fwd(x, weight=W["pre_ln"][0], bias=W["pre_ln"][1], eps=c.layer_norm_eps, save_stats=False)
+            x, _, _ = K.layernorm_fwd(x, weight=W["pre_ln"][0], bias=W["pre_ln"][1], eps=eps, save_stats=False)
         for L in W["layers"]:
-            h, _, _ = K.layernorm_fwd(x, weight=L["ln1"][0], bias=L["ln1"][1], eps=c.layer_norm_eps, save_stats=False)
-            qkv = K.gemm(h.view(-1, D), L["wqkv"], bias=L["bqkv"]).view(B, T, 3, H, d)
+            h, _, _ = K.layernorm_fwd(x, weight=L["ln1"][0], bias=L["ln1"][1], eps=eps, save_stats=False)
+            qkv = K.gemm(h.view(-1, D), L["wqkv"], bias=L["bqkv"]).view(B, T, 3, H, dp)
             q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
-            attn = torch.empty(B, T, D, dtype=BF16, device=x.device)
+            attn = torch.empty(B, T, H * dp, dtype=BF16, device=x.device)
             K.flash_attn_fwd(q, k, v, d ** -0.5, attn, want_lse=False)
-            x = K.gemm(attn.view(-1, D), L["wo"], bias=L["bo"], residual=x.view(-1, D)).view(B, T, D)
-            h, _, _ = K.layernorm_fwd(x, weight=L["ln2"][0], bias=L["ln2"][1], eps=c.layer_norm_eps, save_stats=False)
+            x = K.gemm(attn.view(-1, H * dp), L["wo"], bias=L["bo"], residual=x.view(-1, D)).view(B, T, D)
+            h, _, _ = K.layernorm_fwd(x, weight=L["ln2"][0], bias=L["ln2"][1], eps=eps, save_stats=False)
             a = K.gemm(h.view(-1, D), L["w1"], bias=L["b1"], act=act)
             x = K.gemm(a, L["w2"], bias=L["b2"], residual=x.view(-1, D)).view(B, T, D)
-        if c.kind == "clip":
-            pooled, _, _ = K.layernorm_fwd(x[:, 0:1], weight=W["post_ln"][0], bias=W["post_ln"][1], eps=c.layer_norm_eps,
+        if c.kind == "clip":  # last_hidden_state is NOT post-layernormed; pooler = post_layernorm(h[:, 0])
+            pooled, _, _ = K.layernorm_fwd(x[:, 0:1], weight=W["post_ln"][0], bias=W["post_ln"][1], eps=eps,
                                            save_stats=False)
             return SimpleNamespace(last_hidden_state=x, pooler_output=pooled[:, 0], hidden_states=None)
-        raise NotImplementedError("SigLIP MAP pooling head: next row of SURVEY.md 8(a)")
+        # SigLIP: post_layernorm on all tokens, then the MAP pooling head (modeling_siglip.py:586-654)
+        x, _, _ = K.layernorm_fwd(x, weight=W["post_ln"][0], bias=W["post_ln"][1], eps=eps, save_stats=False)
+        Hd = W["head"]
+        q1 = K.gemm(Hd["probe"], Hd["wq"], bias=Hd["bq"])                                   # [1, H*dp], same for all samples
+        q = q1.view(1, 1, H, dp).expand(B, 1, H, dp).contiguous().permute(0, 2, 1, 3)      # [B, H, 1, dp]
+        kv = K.gemm(x.view(-1, D), Hd["wkv"], bias=Hd["bkv"]).view(B, T, 2, H, dp)
+        k, v = (kv[:, :, i].permute(0, 2, 1, 3) for i in range(2))
+        o = torch.empty(B, 1, H * dp, dtype=BF16, device=x.device)
+        K.flash_attn_fwd(q, k, v, d ** -0.5, o, want_lse=False)
+        a = K.gemm(o.view(B, H * dp), Hd["wo"], bias=Hd["bo"])                               # [B, D]
+        y, _, _ = K.layernorm_fwd(a, weight=Hd["ln"][0], bias=Hd["ln"][1], eps=eps, save_stats=False)
+        y = K.gemm(y, Hd["w1"], bias=Hd["b1"], act=act)
+        pooled = K.gemm(y, Hd["w2"], bias=Hd["b2"], residual=a)
+        return SimpleNamespace(last_hidden_state=x, pooler_output=pooled, hidden_states=None)
 
 
 class VisionLanguageModel(nn.Module):

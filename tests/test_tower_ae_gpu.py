@@ -60,9 +60,29 @@ def test_clip_tower_and_projectors_match_reference():
     assert cosine(cls2, cls) >= 0.9999
 
 
+def test_siglip_tower_map_head_and_projectors_match_reference():
+    """SigLIP: biased patch conv, no CLS / pre-LN, tanh-GELU, eps 1e-6, post-LN on all tokens, MAP pooling head;
+    head_dim 72 runs zero-padded to 128 lanes (fixture: HF SiglipModel inside the reference's SigLIP wrapper)."""
+    fx = load_golden("tower_siglip_small.pt")
+    assert fx["cfg"]["hidden"] // fx["cfg"]["heads"] == 72
+    wrap = _build_wrapper(fx)
+    x = ((fx["img"] - 0.5) / 0.5).to("cuda")
+    out = wrap.model.vision_model(x, output_hidden_states=True)
+    assert out.last_hidden_state.shape == fx["last_hidden_state"].shape
+    assert cosine(out.last_hidden_state, fx["last_hidden_state"]) >= 0.999
+    assert cosine(out.pooler_output, fx["pooler_output"]) >= 0.999
+    cls, pc, pt5 = wrap(x)
+    assert cosine(cls, fx["class_token"]) >= 0.999
+    assert cosine(pc, fx["projection_clip"]) >= 0.999 and cosine(pt5, fx["projection_t5"]) >= 0.999
+    (pc.float().square().mean() + pt5.float().square().mean()).backward()
+    assert cosine(wrap.project_t5[1].weight.grad, fx["grad_project_t5_1_weight"]) >= 0.99
+    cls2, _, _ = wrap(fx["img"].to("cuda"), _norm=((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)))
+    assert cosine(cls2, cls) >= 0.9999
+
+
 def test_tower_rejects_unsupported_head_dim_loudly():
     from genhancer_b200.clip_models import vision_tower as vt
-    m = vt.VisionLanguageModel(vt.TowerConfig("clip", 96, 1, 2, 128, 28, 14, 32)).to("cuda")
+    m = vt.VisionLanguageModel(vt.TowerConfig("clip", 72, 1, 2, 128, 28, 14, 32)).to("cuda")  # head_dim 36
     with pytest.raises(NotImplementedError):
         m.vision_model(torch.zeros(1, 3, 28, 28, device="cuda"))
 
