@@ -34,7 +34,18 @@ class GemmArgs(C.Structure):
         ("aux_out", C.c_void_p), ("ld_aux_out", C.c_int64),
         ("gate", C.c_void_p), ("gate_ld", C.c_int64), ("rows_per_batch", C.c_int32),
         ("residual", C.c_void_p), ("ld_res", C.c_int64), ("res_dtype", C.c_int32),
+        ("a2", C.c_void_p), ("lda2", C.c_int64), ("b2", C.c_void_p), ("ldb2", C.c_int64), ("K2", C.c_int32),
     ]
+
+
+class CopyDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("src_ld", C.c_int64), ("dst_ld", C.c_int64), ("src_dtype", C.c_int32), ("dst_dtype", C.c_int32),
+                ("src_row_group", C.c_int32), ("src_row_pitch", C.c_int32),
+                ("src_col_group", C.c_int32), ("src_col_pitch", C.c_int32),
+                ("dst_row_group", C.c_int32), ("dst_row_pitch", C.c_int32),
+                ("dst_col_group", C.c_int32), ("dst_col_pitch", C.c_int32),
+                ("scale", C.c_float), ("accumulate", C.c_int32)]
 
 
 class RowsView(C.Structure):
@@ -86,6 +97,7 @@ SIGNATURES: dict[str, list] = {
     "gh_act_fwd": [_vp, _vp, _i64, _i32, _vp],
     "gh_act_bwd": [_vp, _vp, _vp, _i64, _i32, _vp],
     "gh_accum_cast": [_vp, _vp, _i32, _i64, _f32, _i32, _vp],
+    "gh_batched_copy": [_vp, _i32, _i32, _vp],
     "gh_flash_attn_fwd": [_at, _at, _at, _i32, _i32, _i32, _i32, _i32, _f32, _ao, _vp, _vp],
     "gh_flash_attn_bwd": [_at, _at, _at, _ao, _ao, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _at, _at, _at, _vp, _vp,
                           _vp],

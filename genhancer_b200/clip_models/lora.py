@@ -11,7 +11,7 @@ Restated semantics (peft's published LoRA layer): for every targeted ``nn.Linear
 ``y = W x + b + (lora_alpha / r) * B(A(dropout(x)))``; ``A`` [r, in] ~ kaiming_uniform(a=sqrt(5)), ``B`` [out, r] = 0;
 the base model is frozen; ``bias="lora_only"`` leaves the biases of the wrapped layers trainable; merging is
 ``W += (lora_alpha / r) * B @ A``.  The arithmetic itself runs in ``tower_engine`` with the rank-r branch folded into
-the base GEMM (one extra K-slice), not as two extra GEMMs.
+the base GEMM (a second operand pair: one extra MMA k-step), not as two extra GEMMs.
 """
 from __future__ import annotations
 
@@ -54,7 +54,7 @@ def _targets(model, cfg: LoraConfig):
             continue
         leaf = name.rsplit(".", 1)[-1]
         if name.startswith("vision_model.head.attention"):
-            continue  # nn.MultiheadAttention internals: peft edge case, left frozen
+            continue  # inside nn.MultiheadAttention, whose forward reads .weight/.bias directly: a pair there never acts
         if all_linear or leaf in cfg.target_modules:
             out.append((name, m))
     return out
@@ -73,11 +73,13 @@ def get_peft_model(model, cfg: LoraConfig):
         model.lora[name.replace(".", "/")] = LoraPair(lin.in_features, lin.out_features, cfg.r).to(dev)
         if cfg.bias in ("lora_only", "all") and lin.bias is not None:
             lin.bias.requires_grad_(True)
+    head = getattr(model.vision_model, "head", None)
+    if head is not None and cfg.bias in ("lora_only", "all") and (cfg.target_modules == "all-linear" or "out_proj" in cfg.target_modules):
+        head.attention.out_proj.bias.requires_grad_(True)  # peft wraps that module too, so its bias trains
     if cfg.bias == "all":
         for n, p in model.named_parameters():
             if n.endswith("bias"):
                 p.requires_grad_(True)
-    model.vision_model._cache = None
     return model
 
 

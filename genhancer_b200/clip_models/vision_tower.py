@@ -14,6 +14,7 @@ copies are cached until the parameters change.
 """
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass
 from types import SimpleNamespace
 
@@ -139,8 +140,6 @@ class VisionTransformer(nn.Module):
         self.post_layernorm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
         if c.kind == "siglip":
             self.head = _MapHead(c)
-        self._cache = None
-        self._cache_key = None
         self._init_weights()
 
     @property
@@ -168,98 +167,41 @@ class VisionTransformer(nn.Module):
                 else:
                     p.normal_(0, std * (2 * c.num_hidden_layers) ** -0.5 if ("out_proj" in n or "fc2" in n) else std)
 
-    # ---- bf16 operand cache -------------------------------------------------------------------
-    def _prepared(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if self._cache is not None and self._cache_key == key:
-            return self._cache
-        c = self.config
-        D, p = c.hidden_size, c.patch_size
-        kdim = 3 * p * p
-        ld = (kdim + 7) // 8 * 8
-        W = {}
-        pw = torch.zeros(D, ld, dtype=BF16, device=self.embeddings.patch_embedding.weight.device)
-        pw[:, :kdim] = self.embeddings.patch_embedding.weight.detach().reshape(D, kdim).to(BF16)
-        W["patch_w"], W["patch_ld"] = pw[:, :kdim], ld
-        W["patch_b"] = (self.embeddings.patch_embedding.bias.detach().float().contiguous()
-                        if self.embeddings.patch_embedding.bias is not None else None)
-        W["cls"] = self.embeddings.class_embedding.detach().float().contiguous() if c.kind == "clip" else None
-        W["pos"] = self.embeddings.position_embedding.weight.detach().float().contiguous()
-        f = lambda t: t.detach().float().contiguous()
-        b16 = lambda t: t.detach().to(BF16).contiguous()
-        if c.kind == "clip":
-            W["pre_ln"] = (f(self.pre_layrnorm.weight), f(self.pre_layrnorm.bias))
-        H = c.num_attention_heads
-        d = D // H
-        dp = self.head_dim_padded
-        W["layers"] = []
-        for l in self.encoder.layers:
-            a = l.self_attn
-            W["layers"].append(dict(
-                ln1=(f(l.layer_norm1.weight), f(l.layer_norm1.bias)), ln2=(f(l.layer_norm2.weight), f(l.layer_norm2.bias)),
-                wqkv=b16(_pad_heads_out(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0), 3 * H, d, dp)),
-                bqkv=f(_pad_heads_out(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0), 3 * H, d, dp)),
-                wo=b16(_pad_heads_in(a.out_proj.weight, H, d, dp)), bo=f(a.out_proj.bias),
-                w1=b16(l.mlp.fc1.weight), b1=f(l.mlp.fc1.bias), w2=b16(l.mlp.fc2.weight), b2=f(l.mlp.fc2.bias)))
-        if c.kind == "siglip":  # MAP head: nn.MultiheadAttention packs q,k,v in in_proj_{weight,bias}
-            hd = self.head
-            Wi, bi = hd.attention.in_proj_weight, hd.attention.in_proj_bias
-            W["head"] = dict(
-                probe=b16(hd.probe.reshape(1, D)),
-                wq=b16(_pad_heads_out(Wi[:D], H, d, dp)), bq=f(_pad_heads_out(bi[:D], H, d, dp)),
-                wkv=b16(_pad_heads_out(Wi[D:], 2 * H, d, dp)), bkv=f(_pad_heads_out(bi[D:], 2 * H, d, dp)),
-                wo=b16(_pad_heads_in(hd.attention.out_proj.weight, H, d, dp)), bo=f(hd.attention.out_proj.bias),
-                ln=(f(hd.layernorm.weight), f(hd.layernorm.bias)),
-                w1=b16(hd.mlp.fc1.weight), b1=f(hd.mlp.fc1.bias), w2=b16(hd.mlp.fc2.weight), b2=f(hd.mlp.fc2.bias))
-        W["post_ln"] = (f(self.post_layernorm.weight), f(self.post_layernorm.bias))
-        self._cache, self._cache_key = W, key
-        return W
-
     def forward(self, pixel_values, output_hidden_states: bool = False, _norm=None, **_):
         """pixel_values: normalised images [B,3,S,S] (any float dtype).  `_norm=(mean3, std3)` lets the fused
-        training step hand over raw [0,1] images and fold transforms.Normalize into the im2col gather."""
-        c = self.config
-        W = self._prepared()
-        B = pixel_values.shape[0]
-        D, H, T = c.hidden_size, c.num_attention_heads, c.num_tokens
-        d, dp = D // H, self.head_dim_padded
-        act = ACT_QUICK_GELU if c.hidden_act == "quick_gelu" else ACT_GELU_TANH
-        eps = c.layer_norm_eps
-        img = pixel_values.float().contiguous()
-        mean, std = _norm if _norm is not None else (None, None)
-        A = K.patch_im2col(img, c.patch_size, W["patch_ld"], mean, std)
-        patch = K.gemm(A, W["patch_w"], bias=W["patch_b"])
-        x = K.embed_assemble(patch, W["cls"], W["pos"], B, T, D)
-        if c.kind == "clip":
-            x, _, _ = K.layernorm_fwd(x, weight=W["pre_ln"][0], bias=W["pre_ln"][1], eps=eps, save_stats=False)
-        for L in W["layers"]:
-            h, _, _ = K.layernorm_fwd(x, weight=L["ln1"][0], bias=L["ln1"][1], eps=eps, save_stats=False)
-            qkv = K.gemm(h.view(-1, D), L["wqkv"], bias=L["bqkv"]).view(B, T, 3, H, dp)
-            q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
-            attn = torch.empty(B, T, H * dp, dtype=BF16, device=x.device)
-            K.flash_attn_fwd(q, k, v, d ** -0.5, attn, want_lse=False)
-            x = K.gemm(attn.view(-1, H * dp), L["wo"], bias=L["bo"], residual=x.view(-1, D)).view(B, T, D)
-            h, _, _ = K.layernorm_fwd(x, weight=L["ln2"][0], bias=L["ln2"][1], eps=eps, save_stats=False)
-            a = K.gemm(h.view(-1, D), L["w1"], bias=L["b1"], act=act)
-            x = K.gemm(a, L["w2"], bias=L["b2"], residual=x.view(-1, D)).view(B, T, D)
-        if c.kind == "clip":  # last_hidden_state is NOT post-layernormed; pooler = post_layernorm(h[:, 0])
-            pooled, _, _ = K.layernorm_fwd(x[:, 0:1], weight=W["post_ln"][0], bias=W["post_ln"][1], eps=eps,
-                                           save_stats=False)
-            return SimpleNamespace(last_hidden_state=x, pooler_output=pooled[:, 0], hidden_states=None)
-        # SigLIP: post_layernorm on all tokens, then the MAP pooling head (modeling_siglip.py:586-654)
-        x, _, _ = K.layernorm_fwd(x, weight=W["post_ln"][0], bias=W["post_ln"][1], eps=eps, save_stats=False)
-        Hd = W["head"]
-        q1 = K.gemm(Hd["probe"], Hd["wq"], bias=Hd["bq"])                                   # [1, H*dp], same for all samples
-        q = q1.view(1, 1, H, dp).expand(B, 1, H, dp).contiguous().permute(0, 2, 1, 3)      # [B, H, 1, dp]
-        kv = K.gemm(x.view(-1, D), Hd["wkv"], bias=Hd["bkv"]).view(B, T, 2, H, dp)
-        k, v = (kv[:, :, i].permute(0, 2, 1, 3) for i in range(2))
-        o = torch.empty(B, 1, H * dp, dtype=BF16, device=x.device)
-        K.flash_attn_fwd(q, k, v, d ** -0.5, o, want_lse=False)
-        a = K.gemm(o.view(B, H * dp), Hd["wo"], bias=Hd["bo"])                               # [B, D]
-        y, _, _ = K.layernorm_fwd(a, weight=Hd["ln"][0], bias=Hd["ln"][1], eps=eps, save_stats=False)
-        y = K.gemm(y, Hd["w1"], bias=Hd["b1"], act=act)
-        pooled = K.gemm(y, Hd["w2"], bias=Hd["b2"], residual=a)
-        return SimpleNamespace(last_hidden_state=x, pooler_output=pooled, hidden_states=None)
+        training step hand over raw [0,1] images and fold transforms.Normalize into the im2col gather.
+        The schedule itself (frozen forward, or forward + saved activations + LoRA backward in stage 2) lives in
+        ``tower_engine``."""
+        from . import tower_engine
+        self.head_dim_padded  # raises NotImplementedError for head dims the attention kernels cannot take
+        owner = _OWNER.get(self)
+        model = owner() if owner is not None else None
+        if model is None:
+            model = _Standalone(self)
+        lhs, pooled = tower_engine.run_tower(model, pixel_values, _norm)
+        return SimpleNamespace(last_hidden_state=lhs, pooler_output=pooled, hidden_states=None)
+
+
+class _Standalone:
+    """A bare ``VisionTransformer`` seen through the interface the engine expects of a ``VisionLanguageModel``."""
+
+    def __init__(self, vm):
+        self.vision_model = vm
+        eng = _ENGINES.get(vm)
+        if eng is not None:
+            self._engine = eng
+
+    def parameters(self):
+        return self.vision_model.parameters()
+
+    def __setattr__(self, k, v):
+        object.__setattr__(self, k, v)
+        if k == "_engine":
+            _ENGINES[self.vision_model] = v
+
+
+_OWNER: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()    # vision_model -> weakref(VisionLanguageModel)
+_ENGINES: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()  # standalone vision_model -> TowerEngine
 
 
 class VisionLanguageModel(nn.Module):
@@ -271,6 +213,7 @@ class VisionLanguageModel(nn.Module):
         super().__init__()
         self.config = c
         self.vision_model = VisionTransformer(c)
+        _OWNER[self.vision_model] = weakref.ref(self)
         if c.kind == "clip":
             self.visual_projection = nn.Linear(c.hidden_size, c.projection_dim, bias=False)
             self.text_projection = nn.Linear(8, c.projection_dim, bias=False)  # placeholder: text tower unused
@@ -308,6 +251,6 @@ class VisionLanguageModel(nn.Module):
 
 
 def project(model: VisionLanguageModel, pooled: torch.Tensor) -> torch.Tensor:
-    """visual_projection (no bias) on the tcgen05 GEMM; frozen in stage 1."""
-    w = model.visual_projection.weight
-    return K.gemm(pooled.to(BF16).contiguous(), w.detach().to(BF16).contiguous())
+    """visual_projection (no bias) on the tcgen05 GEMM; frozen in stage 1, LoRA-wrapped under 'all-linear'."""
+    from . import tower_engine
+    return tower_engine.run_projection(model, pooled)

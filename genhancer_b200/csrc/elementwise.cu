@@ -59,6 +59,33 @@ __global__ void __launch_bounds__(256) fm_mse_kernel(const uint2* __restrict__ p
   }
 }
 
+// Batched strided cast-copy: one launch moves a whole table of small matrices (LoRA A/B packs fp32 -> bf16 before the
+// step, LoRA / bias gradients fp32 temp -> .grad after backward).  blockIdx.y = descriptor, blockIdx.x strides over
+// its elements; consecutive threads touch consecutive columns (coalesced on both sides).
+__device__ __forceinline__ int64_t grouped_row(int r, int group, int pitch) {
+  return group > 0 ? static_cast<int64_t>(r / group) * pitch + r % group : r;
+}
+__global__ void __launch_bounds__(256) batched_copy_kernel(const gh_copy_desc* __restrict__ descs) {
+  const gh_copy_desc d = descs[blockIdx.y];
+  const int64_t n = static_cast<int64_t>(d.rows) * d.cols;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int r = static_cast<int>(i / d.cols), c = static_cast<int>(i - static_cast<int64_t>(r) * d.cols);
+    const int64_t so = grouped_row(r, d.src_row_group, d.src_row_pitch) * d.src_ld + grouped_row(c, d.src_col_group, d.src_col_pitch);
+    const int64_t dof = grouped_row(r, d.dst_row_group, d.dst_row_pitch) * d.dst_ld + grouped_row(c, d.dst_col_group, d.dst_col_pitch);
+    float v = d.src_dtype == GH_F32 ? static_cast<const float*>(d.src)[so]
+                                    : __bfloat162float(static_cast<const __nv_bfloat16*>(d.src)[so]);
+    v *= d.scale;
+    if (d.dst_dtype == GH_F32) {
+      float* o = static_cast<float*>(d.dst) + dof;
+      *o = d.accumulate ? *o + v : v;
+    } else {
+      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(d.dst) + dof;
+      *o = __float2bfloat16(d.accumulate ? __bfloat162float(*o) + v : v);
+    }
+  }
+}
+
 static inline int ew_grid(int64_t n_items, int block) {
   const int64_t want = (n_items + block - 1) / block;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;  // 8 resident CTAs of 256 threads per SM
@@ -97,6 +124,17 @@ extern "C" int gh_fm_mse_loss_fwdbwd(const void* pred_bf16, const float* x0, con
       reinterpret_cast<const uint2*>(pred_bf16), reinterpret_cast<const float4*>(x0),
       reinterpret_cast<const float4*>(x1), loss_accum, reinterpret_cast<uint2*>(dpred_bf16), grad_scale,
       1.0f / static_cast<float>(numel), n4);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+extern "C" int gh_batched_copy(const gh_copy_desc* descs_device, int32_t n_desc, int32_t blocks_per_desc, void* stream) {
+  using namespace gh;
+  GH_REQUIRE(n_desc >= 0 && blocks_per_desc > 0, GH_ERR_BAD_SHAPE, "gh_batched_copy: bad launch shape");
+  if (n_desc == 0) return GH_OK;
+  GH_REQUIRE(descs_device != nullptr, GH_ERR_NULL, "gh_batched_copy: NULL descriptor table");
+  GH_REQUIRE(n_desc <= 65535, GH_ERR_BAD_SHAPE, "gh_batched_copy: at most 65535 descriptors per launch");
+  batched_copy_kernel<<<dim3(blocks_per_desc, n_desc), 256, 0, static_cast<cudaStream_t>(stream)>>>(descs_device);
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
 }

@@ -27,22 +27,42 @@ int gemm_init() {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launch(const CUtensorMap* tm, const GemmParams& p, cudaStream_t stream) {
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM>
-      <<<grid, GemmCfg<BN>::THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
+      <<<grid, GemmCfg<BN>::THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
 }
 
 template <int BN>
-static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                          cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, p, s);
-  if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, p, s);
-  if (a_mn && !b_mn) return launch<BN, true, false>(ta, tb, p, s);
-  return launch<BN, true, true>(ta, tb, p, s);
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* tm, const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(tm, p, s);
+  if (!a_mn && b_mn) return launch<BN, false, true>(tm, p, s);
+  if (a_mn && !b_mn) return launch<BN, true, false>(tm, p, s);
+  return launch<BN, true, true>(tm, p, s);
+}
+
+// tensor maps of one (A, B) operand pair with reduction length K
+static int make_pair(CUtensorMap* ta, CUtensorMap* tb, const void* a, int64_t lda, bool a_mn, const void* b, int64_t ldb,
+                     bool b_mn, int M, int N, int K, int bn) {
+  {
+    // A: K-major -> dims (K, M) box (64, 128); MN-major -> dims (M, K) box (64, 64)
+    uint64_t dims[2], strides[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2];
+    if (!a_mn) { dims[0] = K; dims[1] = M; box[0] = 64; box[1] = 128; }
+    else       { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = 64; }
+    if (int e = make_tmap_bf16(ta, a, 2, dims, strides, box, nullptr)) return e;
+  }
+  {
+    uint64_t dims[2], strides[1] = {static_cast<uint64_t>(ldb) * 2};
+    uint32_t box[2];
+    if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = static_cast<uint32_t>(bn); }
+    else       { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64; }
+    if (int e = make_tmap_bf16(tb, b, 2, dims, strides, box, nullptr)) return e;
+  }
+  return GH_OK;
 }
 
 static int pick_bn(int M, int N) {
@@ -80,6 +100,10 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
              "gh_gemm_bf16: a/b/d must be 16-byte aligned");
   GH_REQUIRE(a->lda >= (a->a_mn_major ? a->M : a->K) && a->ldb >= (a->b_mn_major ? a->N : a->K) && a->ldd >= a->N,
              GH_ERR_BAD_SHAPE, "gh_gemm_bf16: leading dimension smaller than the row length");
+  GH_REQUIRE(a->K2 >= 0 && (a->K2 == 0 || (a->a2 && a->b2)), GH_ERR_NULL, "gh_gemm_bf16: K2 > 0 needs a2 and b2");
+  GH_REQUIRE(a->K2 == 0 || (a->lda2 % 8 == 0 && a->ldb2 % 8 == 0 && aligned16(a->a2) && aligned16(a->b2) &&
+                            a->lda2 >= (a->a_mn_major ? a->M : a->K2) && a->ldb2 >= (a->b_mn_major ? a->N : a->K2)),
+             GH_ERR_ALIGN, "gh_gemm_bf16: a2/b2 need 16-byte alignment, lda2/ldb2 multiples of 8 and >= the row length");
   GH_REQUIRE(a->act >= 0 && a->act <= 4, GH_ERR_UNSUPPORTED, "gh_gemm_bf16: unknown act %d", a->act);
   GH_REQUIRE(!a->act_grad || a->aux_in, GH_ERR_NULL, "gh_gemm_bf16: act_grad needs aux_in");
   GH_REQUIRE(!a->gate || a->rows_per_batch > 0, GH_ERR_BAD_SHAPE, "gh_gemm_bf16: gate needs rows_per_batch > 0");
@@ -117,27 +141,22 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
               (!a->residual || a->res_dtype == GH_F32 || (a->ld_res % 8 == 0 && aligned16(a->residual)));
   finalize_epilogue(p.ep);
 
-  CUtensorMap ta, tb;
-  {
-    // A: K-major -> dims (K, M) box (64, 128); MN-major -> dims (M, K) box (64, 64)
-    uint64_t dims[2], strides[1] = {static_cast<uint64_t>(a->lda) * 2};
-    uint32_t box[2];
-    if (!a->a_mn_major) { dims[0] = a->K; dims[1] = a->M; box[0] = 64; box[1] = 128; }
-    else                { dims[0] = a->M; dims[1] = a->K; box[0] = 64; box[1] = 64; }
-    if (int e = make_tmap_bf16(&ta, a->a, 2, dims, strides, box, nullptr)) return e;
-  }
-  {
-    uint64_t dims[2], strides[1] = {static_cast<uint64_t>(a->ldb) * 2};
-    uint32_t box[2];
-    if (!a->b_mn_major) { dims[0] = a->K; dims[1] = a->N; box[0] = 64; box[1] = static_cast<uint32_t>(bn); }
-    else                { dims[0] = a->N; dims[1] = a->K; box[0] = 64; box[1] = 64; }
-    if (int e = make_tmap_bf16(&tb, a->b, 2, dims, strides, box, nullptr)) return e;
+  const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
+  CUtensorMap tm[4];
+  if (int e = make_pair(&tm[0], &tm[1], a->a, a->lda, amn, a->b, a->ldb, bmn, a->M, a->N, a->K, bn)) return e;
+  if (a->K2 > 0) {
+    if (int e = make_pair(&tm[2], &tm[3], a->a2, a->lda2, amn, a->b2, a->ldb2, bmn, a->M, a->N, a->K2, bn)) return e;
+    p.num_k_blocks2 = (a->K2 + 63) / 64;
+    const int tail = a->K2 - (p.num_k_blocks2 - 1) * 64;
+    p.k2_last_steps = (tail + 15) / 16;
+  } else {
+    tm[2] = tm[0];
+    tm[3] = tm[1];
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
   switch (bn) {
-    case 256: return dispatch_major<256>(amn, bmn, ta, tb, p, s);
-    case 128: return dispatch_major<128>(amn, bmn, ta, tb, p, s);
-    default: return dispatch_major<64>(amn, bmn, ta, tb, p, s);
+    case 256: return dispatch_major<256>(amn, bmn, tm, p, s);
+    case 128: return dispatch_major<128>(amn, bmn, tm, p, s);
+    default: return dispatch_major<64>(amn, bmn, tm, p, s);
   }
 }

@@ -61,6 +61,10 @@ struct ConvGeom {  // MODE_CONV only
 struct GemmParams {
   int M, N, K;
   int num_m_blocks, num_n_blocks, num_k_blocks;
+  // Second operand pair (LoRA branch folded into the base GEMM): D = A*B^T + A2*B2^T.  The K loop simply runs
+  // num_k_blocks2 more 64-wide steps that pull from (tmap_a2, tmap_b2); the last of them issues only
+  // k2_last_steps of the four 16-deep MMAs (rank 16 -> one MMA, the rest of the box is TMA zero fill).
+  int num_k_blocks2, k2_last_steps;
   uint32_t a_stage_tx_bytes;  // bytes TMA deposits for the A tile of one stage
   uint32_t mn_lbo, mn_sbo, mn_kstep;  // MN-major descriptor geometry (bytes); see common.cuh
   EpilogueParams ep;
@@ -308,6 +312,7 @@ __device__ __forceinline__ void lean_tile(const EpilogueParams& ep, float* __res
 template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b2,
                  const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -330,11 +335,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-  const int nkb = p.num_k_blocks;
+  const int nkb1 = p.num_k_blocks;
+  const int nkb = nkb1 + (MODE == MODE_GEMM ? p.num_k_blocks2 : 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (MODE == MODE_GEMM && p.num_k_blocks2 > 0) {
+      tma_prefetch_desc(&tmap_a2);
+      tma_prefetch_desc(&tmap_b2);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -381,18 +391,30 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int kh = tap / p.cv.KW, kw = tap - kh * p.cv.KW;
             tma_load_4d(sA, &tmap_a, &full_bar[stage], cc * 64, cw0 * p.cv.stride + kw - p.cv.pad,
                         ch0 * p.cv.stride + kh - p.cv.pad, cb);
-          } else if (!A_MN) {
-            tma_load_2d(sA, &tmap_a, &full_bar[stage], kb * 64, m_blk * 128);
           } else {
-            tma_load_2d(sA, &tmap_a, &full_bar[stage], m_blk * 128, kb * 64);
-            tma_load_2d(sA + 8192, &tmap_a, &full_bar[stage], m_blk * 128 + 64, kb * 64);
+            const bool second = kb >= nkb1;
+            const CUtensorMap* ma = second ? &tmap_a2 : &tmap_a;
+            const int kc = (second ? kb - nkb1 : kb) * 64;
+            if (!A_MN) {
+              tma_load_2d(sA, ma, &full_bar[stage], kc, m_blk * 128);
+            } else {
+              tma_load_2d(sA, ma, &full_bar[stage], m_blk * 128, kc);
+              tma_load_2d(sA + 8192, ma, &full_bar[stage], m_blk * 128 + 64, kc);
+            }
           }
-          if (!B_MN) {
+          if (MODE == MODE_CONV) {
             tma_load_2d(sB, &tmap_b, &full_bar[stage], kb * 64, n_blk * BN);
           } else {
+            const bool second = kb >= nkb1;
+            const CUtensorMap* mb = second ? &tmap_b2 : &tmap_b;
+            const int kc = (second ? kb - nkb1 : kb) * 64;
+            if (!B_MN) {
+              tma_load_2d(sB, mb, &full_bar[stage], kc, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(sB + i * 8192, &tmap_b, &full_bar[stage], n_blk * BN + i * 64, kb * 64);
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(sB + i * 8192, mb, &full_bar[stage], n_blk * BN + i * 64, kc);
+            }
           }
         }
         __syncwarp();
@@ -420,10 +442,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
           const uint32_t sA = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
           const uint32_t sB = sA + Cfg::A_BYTES;
+          const int ksteps = (kb == nkb - 1 && kb >= nkb1) ? p.k2_last_steps : 4;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_ss(d_tmem, umma_desc_at(a_desc_base, sA + k * A_KSTEP), umma_desc_at(b_desc_base, sB + k * B_KSTEP),
-                    idesc, (kb | k) != 0 ? 1u : 0u);
+            if (k < ksteps)
+              umma_ss(d_tmem, umma_desc_at(a_desc_base, sA + k * A_KSTEP), umma_desc_at(b_desc_base, sB + k * B_KSTEP),
+                      idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);              // smem slot free once these MMAs retire
           if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete

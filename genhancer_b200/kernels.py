@@ -52,8 +52,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          bias: torch.Tensor | None = None, act: int = ACT_NONE, act_grad: bool = False,
          aux_in: torch.Tensor | None = None, aux_out: torch.Tensor | None = None,
          gate: torch.Tensor | None = None, rows_per_batch: int = 0,
-         residual: torch.Tensor | None = None) -> torch.Tensor:
-    """D[M,N] = epilogue(alpha * A @ B^T).
+         residual: torch.Tensor | None = None, a2: torch.Tensor | None = None,
+         b2: torch.Tensor | None = None) -> torch.Tensor:
+    """D[M,N] = epilogue(alpha * (A @ B^T + A2 @ B2^T)).
+
+    ``a2`` / ``b2`` (same majors as ``a`` / ``b``, reduction length K2 = the LoRA rank) fold a low-rank branch into
+    the base GEMM: one extra 16-deep MMA per tile instead of a second GEMM and a second pass over the output.
 
     ``a`` is [M,K] (or [K,M] when ``a_mn``), ``b`` is [N,K] (or [K,N] when ``b_mn``); both bf16 with unit
     inner stride (row pitch may exceed the row length).  See ``gh_gemm_bf16`` in include/genhancer_b200.h.
@@ -93,9 +97,20 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if residual is not None:
         _rowmajor2d(residual, "gemm residual")
         g.residual, g.ld_res, g.res_dtype = residual.data_ptr(), residual.stride(0), _dt(residual)
+    K2 = 0
+    if a2 is not None:
+        _rowmajor2d(a2, "gemm a2")
+        _rowmajor2d(b2, "gemm b2")
+        if a2.dtype != BF16 or b2.dtype != BF16:
+            raise _lib.GhError("gemm a2/b2 must be bf16")
+        M2, K2 = (a2.shape[1], a2.shape[0]) if a_mn else (a2.shape[0], a2.shape[1])
+        N2, K2b = (b2.shape[1], b2.shape[0]) if b_mn else (b2.shape[0], b2.shape[1])
+        if (M2, N2) != (M, N) or K2 != K2b:
+            raise _lib.GhError(f"gemm: second operand pair is {M2}x{K2} / {N2}x{K2b}, expected M={M} N={N}")
+        g.a2, g.lda2, g.b2, g.ldb2, g.K2 = a2.data_ptr(), a2.stride(0), b2.data_ptr(), b2.stride(0), K2
     tm = GEMM_TIMER
     if tm is not None:
-        ev0, ev1 = tm(2.0 * M * N * K, f"gemm M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} d={'f32' if out.dtype == F32 else 'bf16'}")
+        ev0, ev1 = tm(2.0 * M * N * (K + K2), f"gemm M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} d={'f32' if out.dtype == F32 else 'bf16'}")
         ev0.record()
     check(_lib.lib().gh_gemm_bf16(C.byref(g), _stream()))
     if tm is not None:
@@ -491,3 +506,52 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=N
                                    beta2, eps, weight_decay, int(step), _p(gnorm_sq), float(max_norm),
                                    float(grad_scale), _stream()))
     _count()
+
+
+class CopyTable:
+    """A device-resident table of ``gh_copy_desc`` built once (pointers are stable: parameters and gradients live in
+    the flat buffers of ``optim.flatten``); ``run()`` is ONE launch for all of them."""
+
+    def __init__(self, device):
+        self.device = device
+        self._descs: list = []
+        self._dev = None
+        self._keep: list = []
+
+    def add(self, src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, scale: float = 1.0,
+            accumulate: bool = False, src_rows=None, src_cols=None, dst_rows=None, dst_cols=None) -> None:
+        """Logical [rows, cols] matrix from ``src`` to ``dst`` (2-D views, unit inner stride; the storage of a side may
+        be wider / taller than the logical matrix when that side is grouped: ``*_rows`` / ``*_cols`` = (group, pitch))."""
+        from ._lib import CopyDesc
+        for t in (src, dst):
+            if t.dim() != 2 or (t.stride(1) != 1 and t.shape[1] != 1):
+                raise _lib.GhError("CopyTable: 2-D views with unit inner stride expected")
+        d = CopyDesc()
+        d.src, d.dst, d.rows, d.cols = src.data_ptr(), dst.data_ptr(), rows, cols
+        d.src_ld, d.dst_ld = src.stride(0), dst.stride(0)
+        d.src_dtype, d.dst_dtype = _dt(src), _dt(dst)
+        d.src_row_group, d.src_row_pitch = src_rows or (0, 0)
+        d.src_col_group, d.src_col_pitch = src_cols or (0, 0)
+        d.dst_row_group, d.dst_row_pitch = dst_rows or (0, 0)
+        d.dst_col_group, d.dst_col_pitch = dst_cols or (0, 0)
+        d.scale, d.accumulate = scale, int(accumulate)
+        self._descs.append(d)
+        self._keep += [src, dst]
+        self._dev = None
+
+    def __len__(self):
+        return len(self._descs)
+
+    def run(self, blocks_per_desc: int = 4) -> None:
+        if not self._descs:
+            return
+        from ._lib import CopyDesc
+        if self._dev is None:
+            arr = (CopyDesc * len(self._descs))(*self._descs)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._dev = host.to(self.device)
+        _lib.init(self._dev.device.index if self._dev.device.index is not None else torch.cuda.current_device())
+        for i in range(0, len(self._descs), 65535):
+            n = min(65535, len(self._descs) - i)
+            check(_lib.lib().gh_batched_copy(self._dev.data_ptr() + i * C.sizeof(CopyDesc), n, blocks_per_desc, _stream()))
+            _count()

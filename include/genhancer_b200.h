@@ -89,6 +89,15 @@ typedef struct {
   const void* residual;
   int64_t ld_res;
   int32_t res_dtype;
+  /* Optional second operand pair, same majors as a/b:  acc += sum over k < K2 of A2(m,k) * B2(n,k)  (before alpha).
+   * This is how LoRA (peft r=16, train_SigLIP_stage2_all.py:134-142) is folded into the base GEMM: forward
+   * y = x W^T + u B^T with u = (alpha/r) x A^T [M,r]; dgrad dx = dy W + du A with du = (alpha/r) dy B.
+   * The rank-r slice costs one extra 16-deep MMA per tile, no second pass over y.  K2 = 0: absent. */
+  const void* a2;
+  int64_t lda2;
+  const void* b2;
+  int64_t ldb2;
+  int32_t K2;
 } gh_gemm_args;
 int gh_gemm_bf16(const gh_gemm_args* args, void* stream);
 
@@ -179,6 +188,24 @@ int gh_act_bwd(const void* dy, const void* x, void* dx, int64_t numel, int32_t a
 /* dst (bf16|fp32) = scale * src_fp32 (+ dst): flush of the fp32 small-gradient scratch into .grad. */
 int gh_accum_cast(const float* src, void* dst, int32_t dst_dtype, int64_t numel, float scale, int32_t accumulate,
                   void* stream);
+
+/* Batched strided cast-copy: dst = scale * src (+ dst) for a DEVICE-resident table of small matrices, one launch.
+ * Logical row (column) i of a matrix lives at storage row (column) (i / group) * pitch + i % group when group > 0
+ * (heads of 72 / 80 features stored in 128-wide slots for the attention kernels), else at i.  Used to refresh the bf16 operand
+ * copies of the fp32 LoRA A / B parameters once per step and to scatter LoRA / bias gradients from the fp32 GEMM
+ * outputs into .grad (peft LoRA layer + torch.autograd, train_SigLIP_stage2_all.py:134-142,290). */
+typedef struct {
+  const void* src;
+  void* dst;
+  int32_t rows, cols;
+  int64_t src_ld, dst_ld;
+  int32_t src_dtype, dst_dtype;
+  int32_t src_row_group, src_row_pitch, src_col_group, src_col_pitch;
+  int32_t dst_row_group, dst_row_pitch, dst_col_group, dst_col_pitch;
+  float scale;
+  int32_t accumulate;
+} gh_copy_desc;
+int gh_batched_copy(const gh_copy_desc* descs_device, int32_t n_desc, int32_t blocks_per_desc, void* stream);
 
 /* --------------------------------------------------------------------------
  * Flash attention (tcgen05 S/O accumulators in TMEM, TMA-staged tiles, online softmax).

@@ -361,12 +361,57 @@ def projector_forward(sd: dict, prefix: str, x: torch.Tensor) -> torch.Tensor:
     return F.linear(y, sd[f"{prefix}.3.weight"], sd[f"{prefix}.3.bias"])
 
 
+def visual_projection(sd_model: dict, pooled: torch.Tensor, lora=None) -> torch.Tensor:
+    """visual_projection (no bias); wrapped by peft under target_modules='all-linear'
+    (R/train_OpenAICLIP_use2frames_nextpredic_stage2_all.py:174-182)."""
+    y = F.linear(pooled, sd_model["visual_projection.weight"])
+    if lora and "visual_projection.weight" in lora:
+        A, Bm, sc = lora["visual_projection.weight"]
+        y = y + sc * F.linear(F.linear(pooled, A), Bm)
+    return y
+
+
+LORA_SIGLIP_TARGETS = ("k_proj", "v_proj", "q_proj", "out_proj", "fc1", "fc2")  # R/train_SigLIP_stage2_all.py:137
+
+
+def lora_key_shapes(c: TowerCfg, r: int = 16, all_linear: bool = False) -> dict:
+    """{"<linear>.lora_A": [r, in], "<linear>.lora_B": [out, r]} for every nn.Linear peft wraps on the vision side.
+    The MAP head's out_proj sits inside nn.MultiheadAttention, whose forward reads .weight/.bias directly, so a
+    LoRA pair there never takes part in the arithmetic (left out)."""
+    vm, D = "vision_model", c.hidden
+    ks = {}
+    def add(name, out_f, in_f):
+        ks[f"{name}.lora_A"] = [r, in_f]
+        ks[f"{name}.lora_B"] = [out_f, r]
+    for i in range(c.layers):
+        q = f"{vm}.encoder.layers.{i}"
+        for leaf in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            add(f"{q}.self_attn.{leaf}", D, D)
+        add(f"{q}.mlp.fc1", c.mlp, D)
+        add(f"{q}.mlp.fc2", D, c.mlp)
+    if c.kind == "siglip":
+        add(f"{vm}.head.mlp.fc1", c.mlp, D)
+        add(f"{vm}.head.mlp.fc2", D, c.mlp)
+    elif all_linear:
+        add("visual_projection", c.proj_dim, D)
+    return ks
+
+
+def synth_lora(c: TowerCfg, seed: int, r: int = 16, alpha: float = 16.0, all_linear: bool = False, b_scale: float = 0.3):
+    """-> ({weight key: (A, B, scaling)}, flat {name: tensor}).  B is random (not zero) so that the branch and both of
+    its gradients are exercised (SURVEY.md 8d cfg 4)."""
+    flat = synth_state_dict(lora_key_shapes(c, r, all_linear), seed)
+    flat = {k: (v * b_scale if k.endswith("lora_B") else v) for k, v in flat.items()}
+    names = sorted({k.rsplit(".", 1)[0] for k in flat})
+    return {f"{n}.weight": (flat[f"{n}.lora_A"], flat[f"{n}.lora_B"], alpha / r) for n in names}, flat
+
+
 def clip_wrapper_forward(sd_model: dict, sd_wrap: dict, images: torch.Tensor, c: TowerCfg, lora=None):
     """OpenAICLIP/MetaCLIP.forward (R/clip_models/CLIP_bank.py:32-40,115-122) and SigLIP.forward (:67-73).
 
     Returns (class_token, projection_clip, projection_t5[:, None, :])."""
     _, pooled = tower_forward(sd_model, images, c, lora)
-    cls = F.linear(pooled, sd_model["visual_projection.weight"]) if c.kind == "clip" else pooled
+    cls = visual_projection(sd_model, pooled, lora) if c.kind == "clip" else pooled
     return cls, projector_forward(sd_wrap, "project_clip", cls), projector_forward(sd_wrap, "project_t5", cls[:, None, :])
 
 
@@ -661,7 +706,7 @@ def stage1_video_step(sd_tower, sd_adapter, sd_dit, sd_ae, cond_frames, target, 
     for f in cond_frames:
         lhs, pooled = tower_forward(sd_tower, (f - mean) / std, tcfg, lora)
         patches.append(lhs[:, 1:, :])
-        vecs.append(F.linear(pooled, sd_tower["visual_projection.weight"]))
+        vecs.append(visual_projection(sd_tower, pooled, lora))
     vec = sum(vecs) / len(vecs)
     txt = adapter_forward(sd_adapter, torch.cat(patches, dim=1))
     B, _, h, w = x_1.shape

@@ -140,6 +140,77 @@ def golden_tower(name: str, tc: O.TowerCfg, clip_dim=48, t5_dim=96, B=2, seed=11
     torch.save(fx, os.path.join(GOLD, f"tower_{name}.pt"))
 
 
+def golden_tower_lora(name: str, tc: O.TowerCfg, all_linear: bool, clip_dim=48, t5_dim=96, B=2, seed=61, r=16, alpha=16.0):
+    """Stage-2 tower: the reference wrapper (HF model inside) with peft's LoRA layer restated as forward hooks on the
+    wrapped nn.Linear modules (peft 0.14.0 is not installed: y = base(x) + (alpha/r) B(A(x)), dropout off,
+    bias='lora_only' -> the wrapped linears' biases train; train_SigLIP_stage2_all.py:134-142).  Gradients of the LoRA
+    pairs / biases / projectors from torch autograd over the HF modules are the golden values; the oracle's own LoRA
+    path must agree."""
+    print(f"[tower_lora:{name}]")
+    wrap, sd_t, sd_w, ks_t, ks_w = build_reference_wrapper(tc, clip_dim, t5_dim, seed)
+    lora, flat = O.synth_lora(tc, seed + 2, r, alpha, all_linear)
+    for p_ in wrap.parameters():
+        p_.requires_grad_(False)
+    for n_, p_ in wrap.named_parameters():
+        if "project_clip" in n_ or "project_t5" in n_:
+            p_.requires_grad_(True)
+    params = {}
+    mods = dict(wrap.model.named_modules())
+    for wkey, (A, Bm, sc) in lora.items():
+        lin = mods[wkey[:-len(".weight")]]
+        A_, B_ = A.clone().requires_grad_(True), Bm.clone().requires_grad_(True)
+        params[wkey[:-len(".weight")]] = (A_, B_)
+        lin.register_forward_hook(lambda m, inp, out, A_=A_, B_=B_, sc=sc: out + sc * F.linear(F.linear(inp[0], A_), B_))
+        if lin.bias is not None:
+            lin.bias.requires_grad_(True)
+    if tc.kind == "siglip":  # peft also marks the MAP head's out_proj bias trainable (wrapped module, bias='lora_only')
+        wrap.model.vision_model.head.attention.out_proj.bias.requires_grad_(True)
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(B, 3, tc.image_size, tc.image_size, generator=g)
+    mean = torch.tensor(OPENAI_MEAN if tc.kind == "clip" else (0.5,) * 3).view(1, 3, 1, 1)
+    std = torch.tensor(OPENAI_STD if tc.kind == "clip" else (0.5,) * 3).view(1, 3, 1, 1)
+    x = (img - mean) / std
+    out = wrap.model.vision_model(x, output_hidden_states=True)
+    lhs_ref = out.last_hidden_state.detach().clone()
+    pooled_ref = out.pooler_output.detach().clone()
+    cls, pc, pt5 = wrap(x)
+    out2 = wrap.model.vision_model(x, output_hidden_states=True)
+    loss = pc.square().mean() + pt5.square().mean() + 0.1 * out2.last_hidden_state[:, 1:].square().mean()
+    loss.backward()
+    # the oracle's LoRA path on the same tensors
+    lo_o = {k: (A.clone().requires_grad_(True), Bm.clone().requires_grad_(True), sc) for k, (A, Bm, sc) in lora.items()}
+    sdt = {k: v.clone() for k, v in sd_t.items()}
+    bias_keys = [f"{n}.bias" for n in params if f"{n}.bias" in sdt]
+    if tc.kind == "siglip":
+        bias_keys.append("vision_model.head.attention.out_proj.bias")
+    for k in bias_keys:
+        sdt[k].requires_grad_(True)
+    sdw = {k: v.clone().requires_grad_(True) for k, v in sd_w.items()}
+    ocls, opc, opt5 = O.clip_wrapper_forward(sdt, sdw, x, tc, lo_o)
+    olhs, _ = O.tower_forward(sdt, x, tc, lo_o)
+    (opc.square().mean() + opt5.square().mean() + 0.1 * olhs[:, 1:].square().mean()).backward()
+    close(olhs, lhs_ref, 2e-5, "last_hidden_state (LoRA)")
+    close(ocls, cls, 2e-5, "class_token (LoRA)")
+    close(opt5, pt5, 2e-5, "projection_t5 (LoRA)")
+    grads = {}
+    for n, (A_, B_) in params.items():
+        close(lo_o[f"{n}.weight"][0].grad, A_.grad, 2e-4, f"grad {n}.lora_A")
+        close(lo_o[f"{n}.weight"][1].grad, B_.grad, 2e-4, f"grad {n}.lora_B")
+        grads[f"{n}.lora_A"], grads[f"{n}.lora_B"] = A_.grad.clone(), B_.grad.clone()
+    for k in bias_keys:
+        gref = mods[k[:-len(".bias")]].bias.grad
+        close(sdt[k].grad, gref, 2e-4, f"grad {k}")
+        grads[k] = gref.clone()
+    grads["project_t5.1.weight"] = wrap.project_t5[1].weight.grad.clone()
+    grads["project_clip.3.bias"] = wrap.project_clip[3].bias.grad.clone()
+    fx = dict(kind="tower_lora", cfg=tc.__dict__, clip_dim=clip_dim, t5_dim=t5_dim, seed=seed, key_shapes_tower=ks_t,
+              key_shapes_wrap=ks_w, key_shapes_lora=O.lora_key_shapes(tc, r, all_linear), r=r, alpha=alpha,
+              all_linear=all_linear, b_scale=0.3, img=img, last_hidden_state=lhs_ref, pooler_output=pooled_ref,
+              class_token=cls.detach(), projection_clip=pc.detach(), projection_t5=pt5.detach(), loss=loss.detach(),
+              grads=grads)
+    torch.save(fx, os.path.join(GOLD, f"tower_lora_{name}.pt"))
+
+
 def golden_ae(seed=21):
     print("[ae encoder]")
     ac = O.AECfg(ch=64)
@@ -472,7 +543,7 @@ def golden_cfg1_full(seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="", help="comma-separated subset: tower,ae,flux,step,video")
+    ap.add_argument("--only", default="", help="comma-separated subset: tower,lora,ae,flux,step,video")
     ap.add_argument("--full", action="store_true", help="also run BASELINE config 1 at full size (~1-2 min, ~12 GB)")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -482,6 +553,9 @@ def main():
     if want("tower"):
         golden_tower("clip_small", O.TowerCfg("clip", 128, 2, 2, 512, 56, 14, 64, 1e-5, "quick_gelu"))
         golden_tower("siglip_small", O.TowerCfg("siglip", 144, 2, 2, 304, 56, 14, 144, 1e-6, "gelu_tanh"))
+    if want("lora"):
+        golden_tower_lora("clip_small", O.TowerCfg("clip", 128, 2, 2, 512, 56, 14, 64, 1e-5, "quick_gelu"), all_linear=True)
+        golden_tower_lora("siglip_small", O.TowerCfg("siglip", 144, 2, 2, 304, 56, 14, 144, 1e-6, "gelu_tanh"), all_linear=False)
     if want("ae"):
         golden_ae()
     if want("flux"):

@@ -41,7 +41,7 @@ def test_struct_layouts_match_header_field_order():
     src = open(HEADER).read()
     for cname, cls in (("gh_gemm_args", _lib.GemmArgs), ("gh_rows_view", _lib.RowsView),
                        ("gh_attn_tensor", _lib.AttnTensor), ("gh_attn_out", _lib.AttnOut),
-                       ("gh_conv_args", _lib.ConvArgs)):
+                       ("gh_conv_args", _lib.ConvArgs), ("gh_copy_desc", _lib.CopyDesc)):
         body = re.search(r"typedef struct \{([^{}]*)\} " + cname + ";", src, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []

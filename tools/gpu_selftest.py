@@ -95,6 +95,53 @@ def gemm_case(M, N, Kd, a_mn=False, b_mn=False, pad=0, seed=0, **epi):
     return ok
 
 
+def lora_gemm_case(M, N, Kd, R, a_mn=False, b_mn=False, seed=0, f32=False, **kw):
+    """D = A B^T + A2 B2^T (second operand pair of reduction length R: the LoRA branch folded into the base GEMM)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    mk = lambda r, c: torch.randn(r, c, device="cuda", generator=g).to(torch.bfloat16)
+    A, B, A2, B2 = mk(M, Kd), mk(N, Kd), mk(M, R), mk(N, R)
+    ref = A.float() @ B.float().t() + A2.float() @ B2.float().t()
+    ta = (lambda t: t.t().contiguous()) if a_mn else (lambda t: t)
+    tb = (lambda t: t.t().contiguous()) if b_mn else (lambda t: t)
+    if kw.get("residual"):
+        res = mk(M, N)
+        ref = ref + res.float()
+        kw["residual"] = res
+    out = K.gemm(ta(A), tb(B), a_mn=a_mn, b_mn=b_mn, a2=ta(A2), b2=tb(B2), out_dtype=torch.float32 if f32 else torch.bfloat16,
+                 **kw)
+    torch.cuda.synchronize()
+    e = relerr(out, ref)
+    say("PASS" if e < 1e-2 else "FAIL", f"lora_gemm M={M} N={N} K={Kd} R={R} a_mn={int(a_mn)} b_mn={int(b_mn)} f32={f32}",
+        f"relerr={e:.3e}")
+
+
+def copy_table_cases():
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(5)
+    tab = K.CopyTable(dev)
+    # fp32 [6*72, 16] -> bf16 head slots of 128 rows inside a wider block-diagonal operand
+    src = torch.randn(6 * 72, 16, device=dev, generator=g)
+    dst = torch.zeros(6 * 128, 48, device=dev, dtype=torch.bfloat16)
+    tab.add(src, dst[:, 16:32], 6 * 72, 16, dst_rows=(72, 128), scale=0.5)
+    # fp32 [16, 6*72] -> bf16 column slots
+    src2 = torch.randn(16, 6 * 72, device=dev, generator=g)
+    dst2 = torch.zeros(16, 6 * 128, device=dev, dtype=torch.bfloat16)
+    tab.add(src2, dst2, 16, 6 * 72, dst_cols=(72, 128))
+    # gradient scatter: fp32 slots -> fp32 dense, accumulating
+    src3 = torch.randn(6 * 128, device=dev, generator=g)
+    dst3 = torch.ones(6 * 72, device=dev)
+    tab.add(src3.unsqueeze(1), dst3.unsqueeze(1), 6 * 72, 1, accumulate=True, src_rows=(72, 128))
+    tab.run()
+    torch.cuda.synchronize()
+    r1 = torch.zeros_like(dst)
+    r1.view(6, 128, 48)[:, :72, 16:32] = (0.5 * src).view(6, 72, 16).to(torch.bfloat16)
+    r2 = torch.zeros_like(dst2)
+    r2.view(16, 6, 128)[:, :, :72] = src2.view(16, 6, 72).to(torch.bfloat16)
+    r3 = 1.0 + src3.view(6, 128)[:, :72].reshape(-1)
+    ok = torch.equal(dst, r1) and torch.equal(dst2, r2) and torch.equal(dst3, r3)
+    say("PASS" if ok else "FAIL", "batched_copy: row slots / column slots / accumulate (bit-exact)")
+
+
 def time_gemm(M, N, Kd, a_mn=False, b_mn=False, iters=20):
     dev = "cuda"
     A = torch.randn((Kd, M) if a_mn else (M, Kd), device=dev).to(torch.bfloat16)
@@ -185,6 +232,20 @@ def main():
         gemm_case(300, 512, 256, act=1, act_grad=True)
         gemm_case(300, 512, 256, bias=True, gate=100, residual=True)
         gemm_case(300, 512, 256, bias=True, f32=True)
+    if "lora" in which:
+        lora_gemm_case(300, 512, 256, 16)
+        lora_gemm_case(300, 512, 256, 48, residual=True)
+        lora_gemm_case(1000, 3456 // 8 * 8, 1152, 48)
+        lora_gemm_case(392, 1152, 4304, 16, residual=True)
+        lora_gemm_case(300, 520, 256, 16, b_mn=True)            # dgrad: dx = dy W + du A
+        lora_gemm_case(300, 1152, 432, 48, b_mn=True)
+        lora_gemm_case(300, 512, 256, 80, b_mn=True)            # rank spilling into a second 64-wide k block
+        lora_gemm_case(16, 1152, 392, 16, a_mn=True, b_mn=True, f32=True)   # wgrad shapes dA = du^T x (no second pair needed,
+        gemm_case(16, 1152, 392, a_mn=True, b_mn=True, f32=True)            #  but the skinny M = 16 / N = 16 tiles are new)
+        gemm_case(432, 16, 392, a_mn=True, b_mn=True, f32=True)
+        gemm_case(392, 16, 1152)
+        gemm_case(392, 48, 432, b_mn=True)
+        copy_table_cases()
     if "time" in which:
         time_gemm(4096, 4096, 4096)
         time_gemm(8192, 8192, 8192)

@@ -213,6 +213,29 @@ def attn_bwd_case(B, H, L, D, n_split=0, fused_qkv=False, seed=7):
         f"dq={e[0]:.3e} dk={e[1]:.3e} dv={e[2]:.3e}")
 
 
+def attn_cross_bwd_case(B, H, Lq, Lk, D, seed=9):
+    """Lq != Lk (SigLIP MAP head: one probe query over all tokens), k/v read off a fused [B, Lk, 2, H, D] buffer."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    q = torch.randn(B, H, Lq, D, device=dev, generator=g).to(BF)
+    kv = torch.randn(B, Lk, 2, H, D, device=dev, generator=g).to(BF)
+    k, v = (kv[:, :, i].permute(0, 2, 1, 3) for i in range(2))
+    dkv = torch.full_like(kv, float("nan"))
+    dk, dv = (dkv[:, :, i].permute(0, 2, 1, 3) for i in range(2))
+    dq = torch.full((B, H, Lq, D), float("nan"), device=dev, dtype=BF)
+    scale = D ** -0.5
+    out = torch.empty(B, Lq, H * D, device=dev, dtype=BF)
+    lse = K.flash_attn_fwd(q, k, v, scale, out)
+    do = torch.randn(B, Lq, H * D, device=dev, generator=g).to(BF)
+    K.flash_attn_bwd(q, k, v, lse, scale, out, do, dq, dk, dv)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Lq, H * D)
+    ref.backward(do.float())
+    e = [rel(out, ref), rel(dq, qf.grad), rel(dk, kf.grad), rel(dv, vf.grad)]
+    say("PASS" if max(e) < 1.2e-2 else "FAIL", f"flash_cross B={B} H={H} Lq={Lq} Lk={Lk} D={D}",
+        f"o={e[0]:.3e} dq={e[1]:.3e} dk={e[2]:.3e} dv={e[3]:.3e}")
+
+
 def time_attn_bwd(B, H, L, D, iters=10):
     q, k, v = (torch.randn(B, H, L, D, device=dev).to(BF) for _ in range(3))
     dq, dk, dv = (torch.empty_like(q) for _ in range(3))
@@ -288,6 +311,9 @@ def main():
         attn_bwd_case(2, 2, 1017, 128, n_split=576)
         attn_bwd_case(1, 1, 64, 64)
         attn_bwd_case(2, 4, 577, 64, fused_qkv=True)
+        attn_cross_bwd_case(2, 2, 1, 16, 128)
+        attn_cross_bwd_case(3, 16, 1, 729, 128)
+        attn_cross_bwd_case(2, 4, 70, 333, 64)
     if "attnbwd" in which:
         time_attn_bwd(32, 24, 442, 128)
         time_attn_bwd(32, 16, 577, 64)
