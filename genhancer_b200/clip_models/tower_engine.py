@@ -135,23 +135,34 @@ class LinGroup:
 
     # ---- compute ------------------------------------------------------------------------------------------
     def fwd(self, x2d, drop=None, **epi):
-        """-> (y, u).  ``drop`` = the dropped-out copy of x feeding the LoRA branch (lora_dropout > 0), else x."""
+        """-> (y, saved).  ``drop`` = (p, seed, offset) when lora_dropout is active: the LoRA branch then reads the
+        dropped-out copy of x (peft: lora_B(lora_A(dropout(x)))); q/k/v of a fused group share one mask.
+        ``saved`` = (u, xd, drop) is what ``bwd`` needs besides x."""
         if not self.R:
             return K.gemm(x2d, self.w, bias=self.bias, **epi), None
-        u = K.gemm(x2d if drop is None else drop, self.A, alpha=self.s)
-        return K.gemm(x2d, self.w, bias=self.bias, a2=u, b2=self.Bm, **epi), u
+        xd = None
+        if drop is not None:
+            xd = K.dropout_fwd(x2d.contiguous(), *drop)
+        u = K.gemm(x2d if xd is None else xd, self.A, alpha=self.s)
+        return K.gemm(x2d, self.w, bias=self.bias, a2=u, b2=self.Bm, **epi), (u, xd, drop)
 
-    def bwd(self, dy2d, x2d, u, need_dx=True, drop=None, **dx_epi):
+    def bwd(self, dy2d, x2d, saved, need_dx=True, **dx_epi):
         """dx (or None).  Parameter gradients go to the fp32 staging (the engine scatters them once per backward)."""
         dx = None
         if self.R:
+            u, xd, drop = saved
             du = K.gemm(dy2d, self.Bm, b_mn=True, alpha=self.s)
             if need_dx:
                 if drop is None:
                     dx = K.gemm(dy2d, self.w, b_mn=True, a2=du, b2=self.A, **dx_epi)
-                else:
-                    raise NotImplementedError
-            K.gemm(du, x2d if drop is None else drop, a_mn=True, b_mn=True, out=self.gA)
+                else:  # the mask sits between x and A: dx = dy W + mask * (du A) / (1 - p), then the epilogue math
+                    dx = K.gemm(dy2d, self.w, b_mn=True)
+                    K.dropout_bwd_add(K.gemm(du, self.A, b_mn=True), dx, *drop)
+                    if dx_epi.get("act_grad"):
+                        dx = K.act_bwd(dx, dx_epi["aux_in"], dx_epi["act"])
+                    elif dx_epi:
+                        raise NotImplementedError(f"LoRA dropout with dgrad epilogue {sorted(dx_epi)}")
+            K.gemm(du, x2d if xd is None else xd, a_mn=True, b_mn=True, out=self.gA)
             K.gemm(dy2d, u, a_mn=True, b_mn=True, out=self.gB)
         elif need_dx:
             dx = K.gemm(dy2d, self.w, b_mn=True, **dx_epi)
@@ -174,6 +185,9 @@ class TowerEngine:
         self.act = ACT_QUICK_GELU if c.hidden_act == "quick_gelu" else ACT_GELU_TANH
         self.lora_cfg = getattr(model, "lora_config", None)
         self.s = self.lora_cfg.scaling if self.lora_cfg is not None else 1.0
+        self.p_drop = float(getattr(self.lora_cfg, "lora_dropout", 0.0) or 0.0)
+        self._drop_seed = None
+        self._drop_calls = 0
         self._frozen_key = None
         self._train_key = None
         self._grad_key = None
@@ -326,6 +340,17 @@ class TowerEngine:
         if self._head_gbo is not None:
             self._head_gbo.zero_()
 
+    def _drop(self):
+        """(p, seed, offset) of the next LoRA-dropout mask, or None (eval mode / p = 0).  The seed is taken from torch's
+        generator once (``torch.manual_seed`` reproduces a run); the offset is a host-side call counter: no device sync."""
+        training = self.model.training if hasattr(self.model, "training") else self.vm.training
+        if self.p_drop <= 0.0 or not training:
+            return None
+        if self._drop_seed is None:
+            self._drop_seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        self._drop_calls += 1
+        return (self.p_drop, self._drop_seed, self._drop_calls)
+
     # ---- forward ------------------------------------------------------------------------------------------
     def forward(self, pixel_values, _norm=None, save=False):
         """-> (last_hidden_state [B,T,D] bf16, pooler_output [B,D] bf16, ctx or None)."""
@@ -344,18 +369,18 @@ class TowerEngine:
         for li, L in enumerate(self.layers):
             h, m1, r1 = K.layernorm_fwd(x, weight=W["ln1"][li][0], bias=W["ln1"][li][1], eps=eps, save_stats=save)
             h2d = h.view(-1, D)
-            qkv, u_qkv = L.qkv.fwd(h2d)
+            qkv, u_qkv = L.qkv.fwd(h2d, drop=self._drop())
             qkv = qkv.view(B, T, 3, H, dp)
             q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
             attn = torch.empty(B, T, H * dp, dtype=BF16, device=x.device)
             lse = K.flash_attn_fwd(q, k, v, d ** -0.5, attn, want_lse=save)
-            xm, u_o = L.o.fwd(attn.view(-1, H * dp), residual=x.view(-1, D))
+            xm, u_o = L.o.fwd(attn.view(-1, H * dp), drop=self._drop(), residual=x.view(-1, D))
             xm = xm.view(B, T, D)
             g, m2, r2 = K.layernorm_fwd(xm, weight=W["ln2"][li][0], bias=W["ln2"][li][1], eps=eps, save_stats=save)
             g2d = g.view(-1, D)
             pre = torch.empty(B * T, c.intermediate_size, dtype=BF16, device=x.device) if save else None
-            a, u_1 = L.fc1.fwd(g2d, act=act, aux_out=pre)
-            xo, u_2 = L.fc2.fwd(a, residual=xm.view(-1, D))
+            a, u_1 = L.fc1.fwd(g2d, drop=self._drop(), act=act, aux_out=pre)
+            xo, u_2 = L.fc2.fwd(a, drop=self._drop(), residual=xm.view(-1, D))
             if save:
                 S[li] = dict(x=x, m1=m1, r1=r1, h=h2d, u_qkv=u_qkv, qkv=qkv, attn=attn, lse=lse, u_o=u_o, xm=xm, m2=m2,
                              r2=r2, g=g2d, pre=pre, a=a, u_1=u_1, u_2=u_2)
@@ -378,8 +403,8 @@ class TowerEngine:
         a = K.gemm(o.view(B, H * dp), Hd["wo"], bias=Hd["bo"])                              # [B, D]
         y, my, ry = K.layernorm_fwd(a, weight=Hd["ln"][0], bias=Hd["ln"][1], eps=eps, save_stats=save)
         pre = torch.empty(B, c.intermediate_size, dtype=BF16, device=x.device) if save else None
-        y1, u_1 = self.h_fc1.fwd(y, act=act, aux_out=pre)
-        pooled, u_2 = self.h_fc2.fwd(y1, residual=a)
+        y1, u_1 = self.h_fc1.fwd(y, drop=self._drop(), act=act, aux_out=pre)
+        pooled, u_2 = self.h_fc2.fwd(y1, drop=self._drop(), residual=a)
         if save:
             S["x_last"], S["mp"], S["rp"] = x, mp, rp
             S["head"] = dict(q=q, kv=kv, o=o, lse=lse, a=a, my=my, ry=ry, y=y, pre=pre, y1=y1, u_1=u_1, u_2=u_2)
@@ -389,7 +414,7 @@ class TowerEngine:
         """visual_projection (no bias), with its LoRA pair under target_modules='all-linear'."""
         x2 = pooled.to(BF16).contiguous()
         self.prepare()
-        y, u = self.proj.fwd(x2)
+        y, u = self.proj.fwd(x2, drop=self._drop())
         return y, ((x2, u) if save else None)
 
     def project_backward(self, saved, dy):

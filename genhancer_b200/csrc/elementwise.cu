@@ -86,6 +86,41 @@ __global__ void __launch_bounds__(256) batched_copy_kernel(const gh_copy_desc* _
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// LoRA input dropout (peft lora_dropout = 0.1 in every stage-2 YAML; train_SigLIP_stage2_all.py:139).  Counter-based
+// Philox-4x32-10 keyed by (seed, call offset): the backward regenerates the mask instead of storing it.
+// One thread = 4 consecutive elements = one Philox block.  Algorithmic bytes / element: fwd 2 + 2, bwd 2 + 2 + 2.
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+template <bool BWD_ADD>
+__global__ void __launch_bounds__(256) dropout_kernel(const uint2* __restrict__ in, uint2* __restrict__ out, int64_t n4,
+                                                      uint32_t thresh, float inv_keep, uint2 key, uint2 off) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), off.x, off.y), key);
+    const uint2 v = in[i];
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y);
+    float o0 = r.x >= thresh ? a.x * inv_keep : 0.f, o1 = r.y >= thresh ? a.y * inv_keep : 0.f;
+    float o2 = r.z >= thresh ? b.x * inv_keep : 0.f, o3 = r.w >= thresh ? b.y * inv_keep : 0.f;
+    if (BWD_ADD) {
+      const uint2 d = out[i];
+      const float2 c = unpack_bf16x2(d.x), e = unpack_bf16x2(d.y);
+      o0 += c.x; o1 += c.y; o2 += e.x; o3 += e.y;
+    }
+    out[i] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+  }
+}
+
 static inline int ew_grid(int64_t n_items, int block) {
   const int64_t want = (n_items + block - 1) / block;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;  // 8 resident CTAs of 256 threads per SM
@@ -137,4 +172,38 @@ extern "C" int gh_batched_copy(const gh_copy_desc* descs_device, int32_t n_desc,
   batched_copy_kernel<<<dim3(blocks_per_desc, n_desc), 256, 0, static_cast<cudaStream_t>(stream)>>>(descs_device);
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
+}
+
+static int launch_dropout(bool bwd_add, const void* in, void* out, int64_t numel, float p, uint64_t seed, uint64_t offset,
+                          void* stream, const char* who) {
+  using namespace gh;
+  GH_REQUIRE(in && out, GH_ERR_NULL, "%s: NULL pointer", who);
+  GH_REQUIRE(numel >= 0 && numel % 4 == 0, GH_ERR_BAD_SHAPE, "%s: numel=%lld must be a multiple of 4", who, (long long)numel);
+  GH_REQUIRE(p >= 0.f && p < 1.f, GH_ERR_BAD_SHAPE, "%s: p=%f outside [0, 1)", who, p);
+  GH_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0, GH_ERR_ALIGN,
+             "%s: 8-byte alignment", who);
+  if (numel == 0) return GH_OK;
+  const int64_t n4 = numel / 4;
+  const double t = static_cast<double>(p) * 4294967296.0;
+  const uint32_t thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const uint2 off = make_uint2(static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bwd_add)
+    dropout_kernel<true><<<ew_grid(n4, 256), 256, 0, s>>>(static_cast<const uint2*>(in), static_cast<uint2*>(out), n4, thresh,
+                                                          1.f / (1.f - p), key, off);
+  else
+    dropout_kernel<false><<<ew_grid(n4, 256), 256, 0, s>>>(static_cast<const uint2*>(in), static_cast<uint2*>(out), n4, thresh,
+                                                           1.f / (1.f - p), key, off);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+extern "C" int gh_dropout_fwd(const void* x_bf16, void* y_bf16, int64_t numel, float p, uint64_t seed, uint64_t offset,
+                              void* stream) {
+  return launch_dropout(false, x_bf16, y_bf16, numel, p, seed, offset, stream, "gh_dropout_fwd");
+}
+extern "C" int gh_dropout_bwd_add(const void* t_bf16, void* dx_bf16, int64_t numel, float p, uint64_t seed, uint64_t offset,
+                                  void* stream) {
+  return launch_dropout(true, t_bf16, dx_bf16, numel, p, seed, offset, stream, "gh_dropout_bwd_add");
 }

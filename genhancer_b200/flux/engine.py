@@ -47,6 +47,7 @@ class GradSink:
         self.accumulate = accumulate
         self.on_ready = on_ready
         self._flushed: set[str] = set()
+        self._discard = None
         self._small: dict[str, torch.Tensor] = {}
         self._touched: set[str] = set()
         n_small = sum(p.numel() for n, p in params.items() if p.dim() == 1 and p.requires_grad)
@@ -71,7 +72,13 @@ class GradSink:
         return p.grad, (None if first else p.grad)
 
     def small(self, name: str) -> torch.Tensor:
-        return self._small[name]
+        acc = self._small.get(name)
+        if acc is None:  # frozen parameter (stage2_only trains the tower alone): its gradient goes to a discard buffer
+            n = self.params[name].numel()
+            if self._discard is None or self._discard.numel() < n:
+                self._discard = torch.zeros(n, dtype=F32, device=self._scratch.device)
+            acc = self._discard[:n]
+        return acc
 
     def flush(self, prefix: str | None = None) -> None:
         """Write the fp32 accumulators of the 1-D parameters under ``prefix`` (all when None) into ``.grad`` and

@@ -508,6 +508,24 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=N
     _count()
 
 
+def dropout_fwd(x: torch.Tensor, p: float, seed: int, offset: int) -> torch.Tensor:
+    """bf16 inverted dropout with a counter-based mask (seed, offset): see gh_dropout_fwd."""
+    _ensure(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    y = torch.empty_like(x)
+    check(_lib.lib().gh_dropout_fwd(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), int(offset), _stream()))
+    _count()
+    return y
+
+
+def dropout_bwd_add(t: torch.Tensor, dx: torch.Tensor, p: float, seed: int, offset: int) -> None:
+    """dx += mask(seed, offset) * t / (1 - p), in place."""
+    _ensure(t)
+    assert t.dtype == BF16 and dx.dtype == BF16 and t.is_contiguous() and dx.is_contiguous() and t.numel() == dx.numel()
+    check(_lib.lib().gh_dropout_bwd_add(t.data_ptr(), dx.data_ptr(), t.numel(), float(p), int(seed), int(offset), _stream()))
+    _count()
+
+
 class CopyTable:
     """A device-resident table of ``gh_copy_desc`` built once (pointers are stable: parameters and gradients live in
     the flat buffers of ``optim.flatten``); ``run()`` is ONE launch for all of them."""

@@ -119,6 +119,32 @@ def save_checkpoint(out_dir: str, step: int, dit, clip_vis, adapter, opt, video:
     torch.save(opt.state_dict(), os.path.join(out_dir, f"optimizer-state-{step}.bin"))
 
 
+def merged_dir_name(family: str, args, step: int) -> str:
+    """Directory of the LoRA-merged HF model, named as each reference script names it."""
+    size = int(args.clip_config.clip_image_size) if args.clip_config.get("clip_image_size") else 224
+    if family == "SigLIP":                                   # train_SigLIP_stage2_all.py:307
+        return f"siglip-so400m-patch14-{size}-{step}"
+    if family == "MetaCLIP":                                 # train_MetaCLIP_stage2_all.py:306-309
+        return f"metaclip-{'l' if args.clip_config.clip_type == 'large' else 'h'}14-fullcc2.5b-{step}"
+    return f"clip-vit-large-patch14-336-{step}" if size == 336 else f"clip-vit-large-patch14-{step}"  # OpenAI video scripts
+
+
+def save_stage2(out_dir: str, step: int, family: str, args, dit, clip_vis, adapter, opt, video: bool):
+    """Stage-2 outputs: the tower with LoRA merged as an HF directory (pytorch_model.bin, safe_serialization=False;
+    train_SigLIP_stage2_all.py:305-311); the video scripts also write the DiT / project_clip / visual_adapter /
+    optimizer files (train_OpenAICLIP_use2frames_nextpredic_stage2_all.py:469-494).  No deepcopy of the model on the
+    GPU: the merge happens tensor by tensor on the way to the file."""
+    from .clip_models import lora
+    os.makedirs(out_dir, exist_ok=True)
+    lora.save_pretrained(clip_vis.model, os.path.join(out_dir, merged_dir_name(family, args, step)))
+    if video:
+        sd = lambda m: {k: v.detach().clone().cpu() for k, v in m.state_dict().items()}
+        torch.save(sd(dit), os.path.join(out_dir, f"checkpoint-dit-{step}.bin"))
+        torch.save(sd(clip_vis.project_clip), os.path.join(out_dir, f"checkpoint-project-clip-{step}.bin"))
+        torch.save(sd(adapter), os.path.join(out_dir, f"checkpoint-visual-adapter-{step}.bin"))
+        torch.save(opt.state_dict(), os.path.join(out_dir, f"optimizer-state-{step}.bin"))
+
+
 def latest_step(out_dir: str) -> int | None:
     if not os.path.isdir(out_dir):
         return None
@@ -161,8 +187,9 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
     from .video import SuperModel, VideoStep, build_windows_with_mask
 
     args = load_config(parse_args(argv))
-    if stage != "stage1":
-        raise NotImplementedError("stage 2 (LoRA on the tower) is the next row of SURVEY.md section 8 (a19)")
+    if stage not in ("stage1", "stage2_all", "stage2_only"):
+        raise ValueError(f"unknown stage {stage!r}")
+    stage2 = stage != "stage1"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -185,10 +212,23 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
     vae.requires_grad_(False)
     clip_vis.requires_grad_(False)
     train_project_clip = mode != "sliding_windows_nextpredic"   # that script neither trains nor saves it (Q12)
-    for n, p in clip_vis.named_parameters():
-        if ("project_clip" in n and train_project_clip and not video) or ("project_t5" in n and not video):
-            p.requires_grad = True
+    if stage2:
+        # LoRA on the tower (train_SigLIP_stage2_all.py:134-142; OpenAI / MetaCLIP scripts use target_modules="all-linear")
+        from .clip_models import lora
+        lc = args.lora_config
+        targets = lora.SIGLIP_TARGETS if family == "SigLIP" else "all-linear"
+        clip_vis.model = lora.get_peft_model(clip_vis.model, lora.LoraConfig(
+            r=int(lc.r), lora_alpha=int(lc.lora_alpha), target_modules=targets, lora_dropout=float(lc.get("lora_dropout", 0.0)),
+            bias=str(lc.get("bias", "none"))))
+        if is_main:
+            lora.print_trainable_parameters(clip_vis.model)
+        clip_vis.train()
+    if stage != "stage2_only":  # stage2_only: DiT and projectors frozen, only the LoRA'd tower trains (train_SigLIP_stage2_only.py:146-155)
+        for n, p in clip_vis.named_parameters():
+            if ("project_clip" in n and train_project_clip and not video) or ("project_t5" in n and not video):
+                p.requires_grad = True
     dit = dit.to(device).to(torch.bfloat16)
+    dit.requires_grad_(stage != "stage2_only")
     dit.train()
     mean, std = (SIGLIP_MEAN, SIGLIP_STD) if NORMS[family] == "siglip" else (OPENAI_CLIP_MEAN, OPENAI_CLIP_STD)
     trainable = list(dit.named_parameters())
@@ -198,13 +238,24 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
         sm = SuperModel(clip_vis, dit, adapter_in_dim=feat, adapter_out_dim=dit.params.context_in_dim).to(device)
         adapter = sm.visual_adapter.float()
         trainable += [(f"visual_adapter.{n}", p) for n, p in adapter.named_parameters()]
+        if stage2:
+            trainable += [(f"clip_vis.{n}", p) for n, p in clip_vis.named_parameters()]
         times = {"video": ((0, 2), 1), "nextpredic": ((0,), 1), "use2frames_nextpredic": ((0, 1), 2),
                  "sliding_windows_nextpredic": ((0, 1, 2), 3)}[mode]
         step_fn = VideoStep(sm, vae, cond_times=times[0], target_time=times[1], clip_mean=mean, clip_std=std,
-                            scale_factor=float(args.scale_factor))
+                            scale_factor=float(args.scale_factor), tower_grad=stage2)
     else:
         trainable += [(f"clip_vis.{n}", p) for n, p in clip_vis.named_parameters()]
         step_fn = Stage1ImageStep(clip_vis, dit, vae, mean, std, scale_factor=float(args.scale_factor))
+    if stage2 and args.get("load_dir") is not None and args.get("load_step") is not None:
+        # stage 2 starts from the stage-1 DiT / projectors / adapter (train_SigLIP_stage2_all.py:146-156)
+        if os.path.exists(os.path.join(str(args.load_dir), f"checkpoint-dit-{args.load_step}.bin")):
+            load_checkpoint(str(args.load_dir), int(args.load_step), dit, clip_vis, adapter, None, video, strict=True)
+            if is_main:
+                print(f"[genhancer_b200] loaded stage-1 weights from {args.load_dir} step {args.load_step}")
+        elif is_main:
+            print(f"[genhancer_b200] stage-1 checkpoint {args.load_dir}/checkpoint-dit-{args.load_step}.bin not found: "
+                  "starting stage 2 from the current (random) initialisation")
     groups = optim.flatten(trainable)
     broadcast_parameters(groups)
     opt = optim.FusedAdamW(groups, lr=float(args.learning_rate), betas=(float(args.adam_beta1), float(args.adam_beta2)),
@@ -224,7 +275,7 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
                 print(f"[genhancer_b200] resumed from step {last}")
     max_steps = max_steps_override or int(args.max_train_steps)
     loader = make_loader(args, mode, device, rank)
-    ckpt_extra = IMAGE_CKPT_STEPS
+    ckpt_extra = STAGE2_CKPT_STEPS if stage2 else IMAGE_CKPT_STEPS
     losses, micro, t_last = [], 0, time.time()
     train_loss = torch.zeros((), device=device)
     for batch in loader:
@@ -269,8 +320,11 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
         train_loss.zero_()
         if is_main and args.get("output_dir") and (global_step % int(args.checkpointing_steps) == 0
                                                    or global_step in ckpt_extra or global_step >= max_steps):
-            save_checkpoint(args.output_dir, global_step, dit, clip_vis, adapter, opt, video,
-                            save_project_clip=train_project_clip)
+            if stage2:
+                save_stage2(args.output_dir, global_step, family, args, dit, clip_vis, adapter, opt, video)
+            else:
+                save_checkpoint(args.output_dir, global_step, dit, clip_vis, adapter, opt, video,
+                                save_project_clip=train_project_clip)
     if world > 1:
         dist.barrier()
     return SimpleNamespace(global_step=global_step, losses=losses, dit=dit, clip_vis=clip_vis, adapter=adapter, opt=opt)

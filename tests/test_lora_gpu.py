@@ -127,3 +127,69 @@ def test_merge_and_unload_matches_the_wrapped_tower():
         got = plain.vision_model(x).last_hidden_state
     assert cosine(got, ref) >= 0.9999
     assert copy.deepcopy(wrap.model) is not None  # the engine cache does not break deepcopy (reference: deepcopy(...).merge_and_unload())
+
+
+def test_lora_dropout_mask_is_regenerated_and_group_matches_torch():
+    """lora_dropout (0.1 in every stage-2 YAML): the mask is a pure function of (seed, offset, index); the folded
+    forward / backward of one wrapped linear agrees with torch autograd given that mask."""
+    from genhancer_b200 import kernels as K
+    from genhancer_b200.clip_models import lora
+    from genhancer_b200.clip_models.tower_engine import LinGroup
+    torch.manual_seed(0)
+    p, seed, off = 0.1, 1234, 7
+    ones = torch.ones(64, 256, device="cuda", dtype=torch.bfloat16)
+    m1 = K.dropout_fwd(ones, p, seed, off)
+    assert torch.equal(m1, K.dropout_fwd(ones, p, seed, off))            # reproducible
+    assert not torch.equal(m1, K.dropout_fwd(ones, p, seed, off + 1))    # new offset, new mask
+    keep = (m1 != 0).float().mean().item()
+    assert abs(keep - 0.9) < 0.02
+    assert torch.allclose(m1[m1 != 0].float(), torch.tensor(1 / 0.9, device="cuda"), rtol=4e-3)
+    acc = torch.zeros_like(ones)
+    K.dropout_bwd_add(ones, acc, p, seed, off)
+    assert torch.equal(acc, m1)                                            # backward regenerates the same mask
+
+    lin = torch.nn.Linear(256, 384).cuda()
+    lin.bias.requires_grad_(True)
+    lin.weight.requires_grad_(False)
+    pair = lora.LoraPair(256, 384, 16).cuda()
+    with torch.no_grad():
+        pair.B.normal_(0, 0.05)
+    g = LinGroup(["l"], [lin], [pair], 1.0)
+    flat = torch.zeros(g.staging_numel(), device="cuda")
+    g.carve(flat)
+    tab = K.CopyTable("cuda")
+    g.fill_frozen(tab)
+    g.fill_trainable(tab)
+    tab.run()
+    x = torch.randn(64, 256, device="cuda").to(torch.bfloat16)
+    dy = torch.randn(64, 384, device="cuda").to(torch.bfloat16)
+    y, saved = g.fwd(x, drop=(p, seed, off))
+    dx = g.bwd(dy, x, saved)
+    mask = (m1.float() * 0.9).round()
+    xr = x.float().requires_grad_(True)
+    A, Bm = pair.A.detach().clone().requires_grad_(True), pair.B.detach().clone().requires_grad_(True)
+    bias = lin.bias.detach().clone().requires_grad_(True)
+    yr = xr @ lin.weight.float().t() + bias + ((xr * mask / 0.9) @ A.t()) @ Bm.t()
+    yr.backward(dy.float())
+    assert cosine(y, yr) >= 0.9999
+    assert cosine(dx, xr.grad) >= 0.999
+    assert cosine(g.gA, A.grad) >= 0.999 and cosine(g.gB, Bm.grad) >= 0.999 and cosine(g.gb, bias.grad) >= 0.9999
+
+
+def test_lora_dropout_trains_and_eval_mode_is_deterministic():
+    fx = load_golden("tower_lora_clip_small.pt")
+    wrap = _build(fx)
+    wrap.model.lora_config.lora_dropout = 0.1
+    from genhancer_b200.clip_models import tower_engine
+    wrap.model._engine = None
+    x = _norm_input(fx)
+    wrap.train()
+    a = wrap.model.vision_model(x).pooler_output.detach().clone()
+    b = wrap.model.vision_model(x).pooler_output.detach().clone()
+    assert not torch.equal(a, b)                       # fresh masks per call in training mode
+    _run(wrap, x)[-1].backward()
+    assert all(p.A.grad is not None and torch.isfinite(p.A.grad).all() for p in wrap.model.lora.values())
+    wrap.eval()
+    c = wrap.model.vision_model(x).pooler_output
+    assert torch.equal(c, wrap.model.vision_model(x).pooler_output)
+    assert cosine(c, fx["pooler_output"]) >= 0.999     # eval: dropout off -> the golden features

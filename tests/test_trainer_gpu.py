@@ -89,9 +89,69 @@ def test_video_stage1_modes_train(tmp_path, mode):
     assert tuple(ad["proj.0.weight"].shape) == (2048, 1024) and tuple(ad["proj.2.weight"].shape) == (4096, 2048)
 
 
-def test_stage2_entry_points_say_so_loudly(tmp_path):
+LORA = """lora_config:
+  r: 16
+  lora_alpha: 16
+  lora_dropout: 0.1
+  bias: "lora_only"
+load_dir: {load}
+load_step: {load_step}
+"""
+
+
+def _run2(tmp_path, family, mode, stage, steps, dirkey, load="none", load_step=0, extra=""):
     from genhancer_b200 import trainer
-    cfg = tmp_path / "cfg.yaml"
-    cfg.write_text(CFG.format(dirkey="img_dir", out=str(tmp_path / "o"), steps=1, ga=1))
-    with pytest.raises(NotImplementedError):
-        trainer.main("SigLIP", "image", "stage2_all", argv=["--config", str(cfg)])
+    out = str(tmp_path / f"out_{stage}")
+    cfg = tmp_path / f"cfg_{stage}.yaml"
+    cfg.write_text(CFG.format(dirkey=dirkey, out=out, steps=steps, ga=1) + LORA.format(load=load, load_step=load_step) + extra)
+    return trainer.main(family, mode, stage, argv=["--config", str(cfg)]), out
+
+
+def test_image_stage2_all_and_only_train_lora_and_export_merged_tower(tmp_path):
+    """train_SigLIP_stage2_{all,only}.py: LoRA (r16, dropout 0.1, bias lora_only) on the tower; stage 1 -> stage 2
+    hand-over through the flat checkpoint files; output = HF directory with LoRA merged (pytorch_model.bin)."""
+    import warnings
+    warnings.simplefilter("ignore")
+    res1, out1 = _run(tmp_path, "SigLIP", "image", steps=2, ga=1, dirkey="img_dir")
+    del res1
+    torch.cuda.empty_cache()
+    res, out = _run2(tmp_path, "SigLIP", "image", "stage2_all", 2, "img_dir", load=out1, load_step=2)
+    assert res.global_step == 2 and all(math.isfinite(l) for l in res.losses)
+    d = os.path.join(out, "siglip-so400m-patch14-224-2")
+    assert sorted(os.listdir(d)) == ["config.json", "pytorch_model.bin"]
+    sd = torch.load(os.path.join(d, "pytorch_model.bin"), weights_only=True)
+    assert not any("lora" in k for k in sd)
+    k = "vision_model.encoder.layers.3.self_attn.q_proj.weight"
+    base = res.clip_vis.model.state_dict()[k].cpu()
+    assert tuple(sd[k].shape) == (1152, 1152) and not torch.equal(sd[k], base)     # B moved off zero -> merge changed W
+    pair = res.clip_vis.model.lora["vision_model/encoder/layers/3/self_attn/q_proj"]
+    assert pair.B.abs().max().item() > 0 and torch.isfinite(pair.A).all()
+    assert not torch.equal(sd["vision_model.encoder.layers.3.mlp.fc1.bias"],
+                           torch.zeros_like(sd["vision_model.encoder.layers.3.mlp.fc1.bias"]))
+    n_lora = sum(p.numel() for p in res.clip_vis.model.lora.parameters())
+    assert n_lora == 27 * 16 * (8 * 1152 + 2 * (1152 + 4304)) + 16 * 2 * (1152 + 4304)
+    dit_w = res.dit.final_layer.linear.weight.detach().clone()
+    del res
+    torch.cuda.empty_cache()
+    res, out = _run2(tmp_path, "SigLIP", "image", "stage2_only", 2, "img_dir", load=out1, load_step=2)
+    assert res.global_step == 2 and all(math.isfinite(l) for l in res.losses)
+    assert not any(p.requires_grad for p in res.dit.parameters())
+    ref = torch.load(os.path.join(out1, "checkpoint-dit-2.bin"), weights_only=True)["final_layer.linear.weight"]
+    assert torch.equal(res.dit.final_layer.linear.weight.detach().cpu(), ref)       # DiT frozen in stage2_only
+    assert not torch.equal(dit_w.cpu(), ref)                                         # ... and trained in stage2_all
+    assert os.path.isdir(os.path.join(out, "siglip-so400m-patch14-224-2"))
+
+
+def test_video_stage2_all_trains_tower_lora_through_the_adapter(tmp_path):
+    """train_OpenAICLIP_use2frames_nextpredic_stage2_all.py: target_modules='all-linear', gradients reach the LoRA
+    pairs through last_hidden_state -> VisualPromptAdapter -> DiT txt stream and through visual_projection."""
+    import warnings
+    warnings.simplefilter("ignore")
+    res, out = _run2(tmp_path, "OpenAICLIP", "use2frames_nextpredic", "stage2_all", 2, "video_dir")
+    assert res.global_step == 2 and all(math.isfinite(l) for l in res.losses)
+    files = set(os.listdir(out))
+    assert {"checkpoint-dit-2.bin", "checkpoint-visual-adapter-2.bin", "checkpoint-project-clip-2.bin",
+            "optimizer-state-2.bin", "clip-vit-large-patch14-2"} <= files
+    lo = res.clip_vis.model.lora
+    assert "visual_projection" in lo and lo["visual_projection"].B.abs().max().item() > 0
+    assert lo["vision_model/encoder/layers/0/mlp/fc2"].B.abs().max().item() > 0
