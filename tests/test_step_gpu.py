@@ -132,3 +132,43 @@ def test_fused_adamw_matches_torch():
             assert abs(opt.grad_norm().item() - tn.item()) / tn.item() < 1e-3
         for p, r in zip(ps, ref):
             assert rel_err(p, r) < tol
+
+
+def test_stage2_step_small_lora_gradients_match_oracle():
+    """Stage-2 step (train_SigLIP_stage2_all.py:258-290 shape): the velocity-MSE loss reaches the tower's LoRA pairs
+    through the DiT's txt / vec inputs and the projectors.  Checked against autograd over the oracle (pinned piecewise:
+    step_small.pt for the step, tower_lora_*.pt for the LoRA tower) on the same weights, inputs and RNG draws."""
+    from genhancer_b200.clip_models import lora
+    from oracle import genhancer_oracle as O
+    fx = load_golden("step_small.pt")
+    step, wrap, dit = build_step(fx["tower_cfg"], fx["flux_cfg"], fx["ae_cfg"], fx["key_shapes"], fx["seed"],
+                                 fx["clip_dim"], fx["t5_dim"])
+    tc = O.TowerCfg(**fx["tower_cfg"])
+    wrap.model = lora.get_peft_model(wrap.model, lora.LoraConfig(r=16, lora_alpha=16, target_modules="all-linear",
+                                                                 lora_dropout=0.0, bias="lora_only"))
+    lo, flat = O.synth_lora(tc, fx["seed"] + 7, all_linear=True)
+    with torch.no_grad():
+        for key, pair in wrap.model.lora.items():
+            n = key.replace("/", ".")
+            pair.A.copy_(flat[f"{n}.lora_A"])
+            pair.B.copy_(flat[f"{n}.lora_B"])
+    dev = "cuda"
+    loss = step(fx["img"].to(dev), ae_noise=fx["ae_noise"].to(dev), t=fx["t"].to(dev), x_0=fx["x_0"].to(dev))
+    loss.backward()
+    # oracle (CPU fp32), LoRA tensors as autograd leaves
+    ks, seed = fx["key_shapes"], fx["seed"]
+    lo_o = {k: (A.clone().requires_grad_(True), B.clone().requires_grad_(True), s) for k, (A, B, s) in lo.items()}
+    sd_t = O.synth_state_dict(ks["tower"], seed)
+    bkey = "vision_model.encoder.layers.0.mlp.fc2.bias"
+    sd_t[bkey].requires_grad_(True)
+    out = O.stage1_image_step(sd_t, O.synth_state_dict(ks["wrap"], seed + 1), O.synth_state_dict(ks["dit"], seed + 2),
+                              O.synth_state_dict(ks["ae"], seed + 3), fx["img"], tc, O.FluxCfg(**fx["flux_cfg"]),
+                              O.AECfg(**fx["ae_cfg"]), OPENAI_MEAN, OPENAI_STD, fx["ae_noise"], fx["t"], fx["x_0"], lora=lo_o)
+    out.loss.backward()
+    assert abs(loss.item() - out.loss.item()) / out.loss.item() < 1e-2
+    worst = 1.0
+    for wkey, (A, B, _) in lo_o.items():
+        pair = wrap.model.lora[wkey[:-len(".weight")].replace(".", "/")]
+        worst = min(worst, cosine(pair.A.grad, A.grad), cosine(pair.B.grad, B.grad))
+    assert worst >= 0.97, worst
+    assert cosine(dict(wrap.model.named_parameters())[bkey].grad, sd_t[bkey].grad) >= 0.98
