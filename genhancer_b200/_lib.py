@@ -82,6 +82,7 @@ SIGNATURES: dict[str, list] = {
     "gh_version": [],
     "gh_init": [C.c_int],
     "gh_gemm_bf16": [C.POINTER(GemmArgs), _vp],
+    "gh_debug_gemm_prof": [_vp],
     "gh_fm_interp_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "gh_fm_mse_loss_fwdbwd": [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp],
     "gh_layernorm_fwd": [_vp, _rv, _vp, _rv, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp],

@@ -10,6 +10,10 @@ template <int BN, bool A_MN, bool B_MN>
 static int set_attr() {
   auto* k = umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM>;
   GH_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+  if constexpr (BN >= 128) {
+    auto* k2 = umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM, true>;
+    GH_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, true>::SMEM_BYTES));
+  }
   return GH_OK;
 }
 
@@ -36,8 +40,37 @@ static int launch(const CUtensorMap* tm, const GemmParams& p, cudaStream_t strea
   return GH_OK;
 }
 
+// CTA pairs: clusters of 2 CTAs (one TPC), one pair per 256 x BN tile, persistent over the pair-tiles
+template <int BN, bool A_MN, bool B_MN>
+static int launch_pair(const CUtensorMap* tm, const GemmParams& p, cudaStream_t stream) {
+  const int tiles = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  cfg.blockDim = dim3(GemmCfg<BN, true>::THREADS);
+  cfg.dynamicSmemBytes = GemmCfg<BN, true>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  GH_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM, true>, tm[0], tm[1], tm[2], tm[3], p));
+  return GH_OK;
+}
+
 template <int BN>
-static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* tm, const GemmParams& p, cudaStream_t s) {
+static int dispatch_major(bool pair, bool a_mn, bool b_mn, const CUtensorMap* tm, const GemmParams& p, cudaStream_t s) {
+  if constexpr (BN >= 128) {
+    if (pair) {
+      if (!a_mn && !b_mn) return launch_pair<BN, false, false>(tm, p, s);
+      if (!a_mn && b_mn) return launch_pair<BN, false, true>(tm, p, s);
+      if (a_mn && !b_mn) return launch_pair<BN, true, false>(tm, p, s);
+      return launch_pair<BN, true, true>(tm, p, s);
+    }
+  }
   if (!a_mn && !b_mn) return launch<BN, false, false>(tm, p, s);
   if (!a_mn && b_mn) return launch<BN, false, true>(tm, p, s);
   if (a_mn && !b_mn) return launch<BN, true, false>(tm, p, s);
@@ -46,7 +79,7 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* tm, const Gem
 
 // tensor maps of one (A, B) operand pair with reduction length K
 static int make_pair(CUtensorMap* ta, CUtensorMap* tb, const void* a, int64_t lda, bool a_mn, const void* b, int64_t ldb,
-                     bool b_mn, int M, int N, int K, int bn) {
+                     bool b_mn, int M, int N, int K, int bn /* B rows per TMA box */) {
   {
     // A: K-major -> dims (K, M) box (64, 128); MN-major -> dims (M, K) box (64, 64)
     uint64_t dims[2], strides[1] = {static_cast<uint64_t>(lda) * 2};
@@ -65,23 +98,38 @@ static int make_pair(CUtensorMap* ta, CUtensorMap* tb, const void* a, int64_t ld
   return GH_OK;
 }
 
-static int pick_bn(int M, int N) {
-  // Per-tile time ~ BN + c (MMA issue is proportional to BN; c = fixed per-tile cost), and narrow tiles re-read
-  // the A operand from L2 once per BN columns: 128x64 tiles run at about a third of the 128x256 rate
-  // (measured: wgrad M=21504 N=3072 K=14144 at 455 TFLOP/s with BN=64 vs 1350 with BN=256).  So: the widest tile
-  // the problem fills, dropping one notch only when that removes at least a quarter of the waves' work.
+static long long* g_gemm_prof = nullptr;  // gh_debug_gemm_prof
+long long* gemm_prof_ptr() { return g_gemm_prof; }
+
+// Tile shape and CTA mode.  Cost model in MMA-k-step cycles per tile (measured with gh_debug_gemm_prof: the issuer
+// is busy ~92 % of the time, yet a single-CTA 128 x 256 tile needs ~200 cycles per 16-deep MMA instead of 128):
+//   tensor pipe      BN / 2 cycles per k-step (per SM)
+//   shared memory    operand reads + TMA writes at 128 B/clk: single CTA (128 + BN) / 2, CTA pair (128 + BN/2) / 2
+// plus a fixed per-tile cost; waves = tiles per worker (148 CTAs, or 74 pairs each covering 256 rows).
+struct TileChoice { int bn; bool pair; };
+static TileChoice pick_tile(int M, int N) {
   const long mb = (M + 127) / 128;
   const int sms = num_sms();
-  if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  auto cost = [&](int bn) {
-    const long tiles = mb * ((N + bn - 1) / bn);
-    const long waves = (tiles + sms - 1) / sms;
-    return waves * (bn + 32);
-  };
-  const long c256 = cost(256), c128 = cost(128);
-  if (c128 * 4 <= c256 * 3) return 128;
-  return 256;
+  static const int force = [] { const char* e = getenv("GH_GEMM_PAIR"); return e ? atoi(e) : -1; }();
+  TileChoice best{64, false};
+  double best_cost = 1e30;
+  const int bns[3] = {256, 128, 64};
+  for (int pair = 0; pair < 2; ++pair) {
+    if (pair ? (mb < 2 || force == 0) : (force == 1 && mb >= 2)) continue;
+    for (int bn : bns) {
+      if (pair && bn < 128) continue;
+      if (bn > 64 && N <= bn / 2) continue;  // a tile more than twice as wide as the problem
+      const long nb = (N + bn - 1) / bn;
+      const long tiles = (pair ? (mb + 1) / 2 : mb) * nb;
+      const long workers = pair ? sms / 2 : sms;
+      const long waves = (tiles + workers - 1) / workers;
+      const double t = pair ? (bn / 2 > (128 + bn / 2) / 2 ? bn / 2 : (128 + bn / 2) / 2)
+                            : (bn / 2 > (128 + bn) / 2 ? bn / 2 : (128 + bn) / 2);
+      const double cost = waves * (t + 24.0);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{bn, pair != 0}; }
+    }
+  }
+  return best;
 }
 
 }  // namespace gh
@@ -112,7 +160,8 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
                  (!a->gate || a->gate_ld % 4 == 0) && (!a->residual || a->ld_res % 4 == 0),
              GH_ERR_ALIGN, "gh_gemm_bf16: epilogue operand leading dimensions must be multiples of 4");
 
-  const int bn = pick_bn(a->M, a->N);
+  const TileChoice tc = pick_tile(a->M, a->N);
+  const int bn = tc.bn;
   GemmParams p{};
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.num_m_blocks = (a->M + 127) / 128;
@@ -140,12 +189,15 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
               (!a->gate || (a->gate_ld % 8 == 0 && aligned16(a->gate))) &&
               (!a->residual || a->res_dtype == GH_F32 || (a->ld_res % 8 == 0 && aligned16(a->residual)));
   finalize_epilogue(p.ep);
+  p.prof = g_gemm_prof;
+  if (g_gemm_prof) { static const int dbg = [] { const char* e = getenv("GH_GEMM_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }
 
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
   CUtensorMap tm[4];
-  if (int e = make_pair(&tm[0], &tm[1], a->a, a->lda, amn, a->b, a->ldb, bmn, a->M, a->N, a->K, bn)) return e;
+  const int box_n = tc.pair ? bn / 2 : bn;
+  if (int e = make_pair(&tm[0], &tm[1], a->a, a->lda, amn, a->b, a->ldb, bmn, a->M, a->N, a->K, box_n)) return e;
   if (a->K2 > 0) {
-    if (int e = make_pair(&tm[2], &tm[3], a->a2, a->lda2, amn, a->b2, a->ldb2, bmn, a->M, a->N, a->K2, bn)) return e;
+    if (int e = make_pair(&tm[2], &tm[3], a->a2, a->lda2, amn, a->b2, a->ldb2, bmn, a->M, a->N, a->K2, box_n)) return e;
     p.num_k_blocks2 = (a->K2 + 63) / 64;
     const int tail = a->K2 - (p.num_k_blocks2 - 1) * 64;
     p.k2_last_steps = (tail + 15) / 16;
@@ -155,8 +207,13 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 256: return dispatch_major<256>(amn, bmn, tm, p, s);
-    case 128: return dispatch_major<128>(amn, bmn, tm, p, s);
-    default: return dispatch_major<64>(amn, bmn, tm, p, s);
+    case 256: return dispatch_major<256>(tc.pair, amn, bmn, tm, p, s);
+    case 128: return dispatch_major<128>(tc.pair, amn, bmn, tm, p, s);
+    default: return dispatch_major<64>(false, amn, bmn, tm, p, s);
   }
+}
+
+extern "C" int gh_debug_gemm_prof(void* device_buf) {
+  gh::g_gemm_prof = static_cast<long long*>(device_buf);
+  return GH_OK;
 }

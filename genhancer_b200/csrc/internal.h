@@ -40,6 +40,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 
 int num_sms();
+long long* gemm_prof_ptr();  // gh_debug_gemm_prof buffer or NULL
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -69,15 +69,22 @@ struct GemmParams {
   uint32_t mn_lbo, mn_sbo, mn_kstep;  // MN-major descriptor geometry (bytes); see common.cuh
   EpilogueParams ep;
   ConvGeom cv;
+  // bring-up aid (gh_debug_gemm_prof): per-CTA cycle counters of the three pipelines, NULL in production.
+  //   [0] issuer total  [1] issuer waiting for smem data (TMA starvation)  [2] issuer waiting for a free accumulator
+  //   [3] tiles  [4] epilogue warp total  [5] epilogue waiting for an accumulator  [6] producer waiting for a free slot
+  long long* prof;
+  int dbg;  // bring-up: bit 0 = no TMA (MMAs run on whatever is in smem: isolates the tensor-pipe rate)
 };
 
-template <int BN>
+// CTA2 = the kernel runs as CTA pairs (cluster of 2, tcgen05 cta_group::2): one tile is 256 x BN, each CTA stages
+// its own 128 rows of A and BN/2 rows of B (see common.cuh).
+template <int BN, bool CTA2 = false>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;   // per CTA
+  static constexpr int STAGES = CTA2 ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARPS = 8;   // two per TMEM lane quadrant: they take alternate 16-column slices
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
@@ -309,14 +316,20 @@ __device__ __forceinline__ void lean_tile(const EpilogueParams& ep, float* __res
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int MODE>
-__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, int MODE, bool CTA2 = false>
+__global__ void __launch_bounds__(GemmCfg<BN, CTA2>::THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b2,
                  const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTA2>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(!(MODE == MODE_CONV && A_MN), "conv A operand is K-major (NHWC channels)");
+  static_assert(!CTA2 || BN >= 128, "a CTA pair splits the B tile: BN/2 must be a multiple of 64");
+  // CTA pair: rank 0 (leader) issues the MMAs for both; tiles are indexed per PAIR (256 rows)
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int worker = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int m_units = CTA2 ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;   // rows of the tile grid
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment of the (shared-window) address
@@ -334,7 +347,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_tiles = m_units * p.num_n_blocks;
   const int nkb1 = p.num_k_blocks;
   const int nkb = nkb1 + (MODE == MODE_GEMM ? p.num_k_blocks2 : 0);
 
@@ -353,13 +366,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], Cfg::EPI_WARPS);  // one arrive per epilogue warp
-    mbar_init(&tempty_bar[1], Cfg::EPI_WARPS);
+    mbar_init(&tempty_bar[0], Cfg::EPI_WARPS * (CTA2 ? 2 : 1));  // one arrive per epilogue warp (of both CTAs)
+    mbar_init(&tempty_bar[1], Cfg::EPI_WARPS * (CTA2 ? 2 : 1));
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  if (warp == 2) {
+    if (CTA2) tmem_alloc2<Cfg::TMEM_COLS>(tmem_ptr);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -367,10 +384,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = p.a_stage_tx_bytes + Cfg::B_BYTES;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long w_slot = 0;
+    const uint32_t tx_bytes = (p.a_stage_tx_bytes + Cfg::B_BYTES) * (CTA2 ? 2u : 1u);
+    constexpr int BNL = CTA2 ? BN / 2 : BN;            // B rows this CTA loads
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int m_blk, n_blk;
-      decode_tile(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+      decode_tile(tile, m_units, p.num_n_blocks, m_blk, n_blk);
+      if (CTA2) m_blk = m_blk * 2 + static_cast<int>(rank);
+      const int nrow0 = n_blk * BN + static_cast<int>(rank) * BNL;
       int cb = 0, ch0 = 0, cw0 = 0;
       if (MODE == MODE_CONV) {
         const int tiles_per_img = p.cv.tiles_w * p.cv.tiles_h;
@@ -380,50 +401,70 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         cw0 = (r % p.cv.tiles_w) * p.cv.TW;
       }
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        if (lane == 0) {
+        if (p.prof) {
+          const long long t0 = clock64();
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          w_slot += clock64() - t0;
+        } else {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+        }
+        if (elect_one()) {
           uint8_t* sA = stage_base + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          // CTA pair: both CTAs' loads count on the LEADER's full barrier (it expects the bytes of both)
+          const uint32_t fb = CTA2 ? mapa_u32(smem_u32(&full_bar[stage]), 0u) : 0u;
+          if (p.dbg & 1) {
+            if (!CTA2 || rank == 0) mbar_arrive(&full_bar[stage]);
+            goto next_stage;
+          }
+          if (!CTA2 || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          auto ld2 = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+            if (CTA2) tma2_load_2d(dst, m, fb, c0, c1);
+            else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
+          };
           if (MODE == MODE_CONV) {
             const int tap = kb / p.cv.cin_chunks;
             const int cc = kb - tap * p.cv.cin_chunks;
             const int kh = tap / p.cv.KW, kw = tap - kh * p.cv.KW;
-            tma_load_4d(sA, &tmap_a, &full_bar[stage], cc * 64, cw0 * p.cv.stride + kw - p.cv.pad,
-                        ch0 * p.cv.stride + kh - p.cv.pad, cb);
+            if (CTA2)
+              tma2_load_4d(sA, &tmap_a, fb, cc * 64, cw0 * p.cv.stride + kw - p.cv.pad, ch0 * p.cv.stride + kh - p.cv.pad, cb);
+            else
+              tma_load_4d(sA, &tmap_a, &full_bar[stage], cc * 64, cw0 * p.cv.stride + kw - p.cv.pad,
+                          ch0 * p.cv.stride + kh - p.cv.pad, cb);
           } else {
             const bool second = kb >= nkb1;
             const CUtensorMap* ma = second ? &tmap_a2 : &tmap_a;
             const int kc = (second ? kb - nkb1 : kb) * 64;
             if (!A_MN) {
-              tma_load_2d(sA, ma, &full_bar[stage], kc, m_blk * 128);
+              ld2(sA, ma, kc, m_blk * 128);
             } else {
-              tma_load_2d(sA, ma, &full_bar[stage], m_blk * 128, kc);
-              tma_load_2d(sA + 8192, ma, &full_bar[stage], m_blk * 128 + 64, kc);
+              ld2(sA, ma, m_blk * 128, kc);
+              ld2(sA + 8192, ma, m_blk * 128 + 64, kc);
             }
           }
           if (MODE == MODE_CONV) {
-            tma_load_2d(sB, &tmap_b, &full_bar[stage], kb * 64, n_blk * BN);
+            ld2(sB, &tmap_b, kb * 64, nrow0);
           } else {
             const bool second = kb >= nkb1;
             const CUtensorMap* mb = second ? &tmap_b2 : &tmap_b;
             const int kc = (second ? kb - nkb1 : kb) * 64;
             if (!B_MN) {
-              tma_load_2d(sB, mb, &full_bar[stage], kc, n_blk * BN);
+              ld2(sB, mb, kc, nrow0);
             } else {
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i)
-                tma_load_2d(sB + i * 8192, mb, &full_bar[stage], n_blk * BN + i * 64, kc);
+              for (int i = 0; i < BNL / 64; ++i) ld2(sB + i * 8192, mb, nrow0 + i * 64, kc);
             }
           }
         }
+      next_stage:
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, A_MN, B_MN);
+    if (p.prof && lane == 0) p.prof[blockIdx.x * 8 + 6] = w_slot;
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (leader CTA of a pair) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 256 : 128, BN, A_MN, B_MN);
     const uint64_t a_desc_base = A_MN ? umma_desc_base(p.mn_lbo, p.mn_sbo) : umma_desc_base(16u, 1024u);
     const uint64_t b_desc_base = B_MN ? umma_desc_base(p.mn_lbo, p.mn_sbo) : umma_desc_base(16u, 1024u);
     const uint32_t A_KSTEP = A_MN ? p.mn_kstep : 32u;
@@ -432,31 +473,63 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+    long long w_full = 0, w_acc = 0, n_tiles = 0;
+    const long long t_begin = p.prof ? clock64() : 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      if (p.prof) {
+        const long long t0 = clock64();
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        w_acc += clock64() - t0;
+        ++n_tiles;
+      } else {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        if (p.prof) {
+          const long long t0 = clock64();
+          mbar_wait(&full_bar[stage], phase);
+          w_full += clock64() - t0;
+        } else {
+          mbar_wait(&full_bar[stage], phase);
+        }
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sA = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
           const uint32_t sB = sA + Cfg::A_BYTES;
-          const int ksteps = (kb == nkb - 1 && kb >= nkb1) ? p.k2_last_steps : 4;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (k < ksteps)
+          auto mma = [&](int k) {
+            if (CTA2)
+              umma2_ss(d_tmem, umma_desc_at(a_desc_base, sA + k * A_KSTEP), umma_desc_at(b_desc_base, sB + k * B_KSTEP),
+                       idesc, (kb | k) != 0 ? 1u : 0u);
+            else
               umma_ss(d_tmem, umma_desc_at(a_desc_base, sA + k * A_KSTEP), umma_desc_at(b_desc_base, sB + k * B_KSTEP),
                       idesc, (kb | k) != 0 ? 1u : 0u);
+          };
+          if (kb == nkb - 1 && kb >= nkb1) {  // last k block of a folded LoRA pair: only the steps that hold data
+            for (int k = 0; k < p.k2_last_steps; ++k) mma(k);
+          } else {
+            mma(0); mma(1); mma(2); mma(3);
           }
-          umma_commit(&empty_bar[stage]);              // smem slot free once these MMAs retire
-          if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+          if (CTA2) {
+            umma2_commit(&empty_bar[stage]);                   // the slot is free in BOTH CTAs once these MMAs retire
+            if (kb == nkb - 1) umma2_commit(&tfull_bar[acc]);  // accumulator complete (both CTAs' epilogues)
+          } else {
+            umma_commit(&empty_bar[stage]);              // smem slot free once these MMAs retire
+            if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 8 + 0] = clock64() - t_begin;
+      p.prof[blockIdx.x * 8 + 1] = w_full;
+      p.prof[blockIdx.x * 8 + 2] = w_acc;
+      p.prof[blockIdx.x * 8 + 3] = n_tiles;
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -474,9 +547,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const EpilogueParams& ep = p.ep;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long w_tfull = 0, w_lean = 0;
+    const long long e_begin = p.prof ? clock64() : 0;
+    const uint32_t tempty_leader[2] = {CTA2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0u) : 0u,
+                                       CTA2 ? mapa_u32(smem_u32(&tempty_bar[1]), 0u) : 0u};
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int m_blk, n_blk;
-      decode_tile(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+      decode_tile(tile, m_units, p.num_n_blocks, m_blk, n_blk);
+      if (CTA2) m_blk = m_blk * 2 + static_cast<int>(rank);
       // the 2 output rows this lane touches in every slice of the tile (row index == logical GEMM row)
       int rows[2];
       uint32_t rowmask = 0;
@@ -503,18 +581,32 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (ep.fast && n0 + BN <= p.N) {
         // ---------------- lean path: bf16 out = act(alpha*acc + bias) [+ bf16 residual], full-width tile ----------------
         // bias of this warp's columns -> smem (fp32) while the accumulator is still being produced
-        for (int idx = lane; idx < Cfg::EPI_BIAS_FLOATS; idx += 32) {
-          const int col = n0 + (half + 2 * (idx >> 4)) * 16 + (idx & 15);
-          float bv = 0.f;
-          if (ep.bias)
-            bv = ep.bias_f32 ? __ldg(static_cast<const float*>(ep.bias) + col)
-                             : __bfloat162float(static_cast<const __nv_bfloat16*>(ep.bias)[col]);
-          bias_s[idx] = bv;
+        {  // all loads first, then the smem stores (a store between two loads pins their order: 4 L2 round trips)
+          constexpr int NB = Cfg::EPI_BIAS_FLOATS / 32;
+          float bv[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            const int idx = lane + 32 * i;
+            const int col = n0 + (half + 2 * (idx >> 4)) * 16 + (idx & 15);
+            bv[i] = 0.f;
+            if (ep.bias)
+              bv[i] = ep.bias_f32 ? __ldg(static_cast<const float*>(ep.bias) + col)
+                                  : __bfloat162float(static_cast<const __nv_bfloat16*>(ep.bias)[col]);
+          }
+#pragma unroll
+          for (int i = 0; i < NB; ++i) bias_s[lane + 32 * i] = bv[i];
         }
         __syncwarp();
-        mbar_wait(&tfull_bar[acc], acc_phase);
+        if (p.prof) {
+          const long long t0 = clock64();
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          w_tfull += clock64() - t0;
+        } else {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+        }
         tc_fence_after();
 #define GH_LEAN(A, R) lean_tile<BN, A, R>(ep, st, bias_s, t_row, half, lane, sub_row, col8, n0, rows, rowmask)
+        const long long t_lean0 = p.prof ? clock64() : 0;
         if (ep.residual) {
           switch (ep.act) {
             case ACT_GELU_TANH: GH_LEAN(ACT_GELU_TANH, true); break;
@@ -533,6 +625,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
 #undef GH_LEAN
+        if (p.prof) w_lean += clock64() - t_lean0;
       } else {
         // ---------------- general path (every epilogue option, edge tiles) ----------------
         int ns = (p.N - n0 + 15) / 16;   // slices of this tile that hold real columns
@@ -558,7 +651,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
         };
         if (half < ns) issue(half, LA);
-        mbar_wait(&tfull_bar[acc], acc_phase);
+        if (p.prof) {
+          const long long t0 = clock64();
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          w_tfull += clock64() - t0;
+        } else {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+        }
         tc_fence_after();
 #pragma unroll 1
         for (int sl = half; sl < ns; sl += 4) {
@@ -567,15 +666,27 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
       tc_fence_before();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(tempty_leader[acc]);   // the leader's issuer waits for both CTAs' epilogues
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
+    if (p.prof && warp == 4 && lane == 0) {
+      p.prof[blockIdx.x * 8 + 4] = clock64() - e_begin;
+      p.prof[blockIdx.x * 8 + 5] = w_tfull;
+      p.prof[blockIdx.x * 8 + 7] = w_lean;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (CTA2) cluster_sync_all();  // neither CTA leaves while the other may still signal its barriers / use its smem
+  if (warp == 2) {
+    if (CTA2) tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
 }
 
 }  // namespace gh

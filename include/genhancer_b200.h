@@ -100,6 +100,10 @@ typedef struct {
   int32_t K2;
 } gh_gemm_args;
 int gh_gemm_bf16(const gh_gemm_args* args, void* stream);
+/* Bring-up aid: when device_buf (int64 [8 * #SMs]) is non-NULL, every following gh_gemm_bf16 launch writes per-CTA
+ * cycle counters of its TMA / MMA / epilogue pipelines there (see GemmParams::prof in csrc/umma_gemm.cuh).  NULL
+ * switches it off.  Not for production: one process-wide pointer. */
+int gh_debug_gemm_prof(void* device_buf);
 
 /* --------------------------------------------------------------------------
  * Flow-matching interpolation (train_SigLIP_stage1.py:248-250,255):
