@@ -28,7 +28,7 @@ template <int BN>
 static int conv_launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  umma_gemm_kernel<BN, false, false, MODE_CONV><<<grid, GemmCfg<BN>::THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(ta, tb, ta, tb, p);
+  umma_gemm_kernel<BN, false, false, MODE_CONV><<<grid, GemmCfg<BN>::THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(ta, tb, ta, tb, ta, tb, p);
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
 }

@@ -35,7 +35,7 @@ static int launch(const CUtensorMap* tm, const GemmParams& p, cudaStream_t strea
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM>
-      <<<grid, GemmCfg<BN>::THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+      <<<grid, GemmCfg<BN>::THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
 }
@@ -57,7 +57,7 @@ static int launch_pair(const CUtensorMap* tm, const GemmParams& p, cudaStream_t 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  GH_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM, true>, tm[0], tm[1], tm[2], tm[3], p));
+  GH_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM, true>, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p));
   return GH_OK;
 }
 
@@ -193,7 +193,7 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
   if (g_gemm_prof) { static const int dbg = [] { const char* e = getenv("GH_GEMM_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }
 
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
-  CUtensorMap tm[4];
+  CUtensorMap tm[6];
   const int box_n = tc.pair ? bn / 2 : bn;
   if (int e = make_pair(&tm[0], &tm[1], a->a, a->lda, amn, a->b, a->ldb, bmn, a->M, a->N, a->K, box_n)) return e;
   if (a->K2 > 0) {
@@ -204,6 +204,21 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
   } else {
     tm[2] = tm[0];
     tm[3] = tm[1];
+  }
+  // lean epilogue through [32 rows x 64 columns] SWIZZLE_128B tiles: TMA store of D, TMA load of the residual
+  static const int no_tma_epi = [] { const char* e = getenv("GH_GEMM_NO_TMA_EPI"); return e ? atoi(e) : 0; }();
+  p.ep.tma = p.ep.fast && !no_tma_epi && (!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0);
+  tm[4] = tm[0];
+  tm[5] = tm[0];
+  if (p.ep.tma) {
+    uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
+    uint32_t box[2] = {64, 32};
+    uint64_t sd[1] = {static_cast<uint64_t>(a->ldd) * 2};
+    if (int e = make_tmap_bf16(&tm[4], a->d, 2, dims, sd, box, nullptr)) return e;
+    if (a->residual) {
+      uint64_t sr[1] = {static_cast<uint64_t>(a->ld_res) * 2};
+      if (int e = make_tmap_bf16(&tm[5], a->residual, 2, dims, sr, box, nullptr)) return e;
+    }
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (bn) {

@@ -43,6 +43,7 @@ struct EpilogueParams {
   int res_f32;
   int vec8;  // every epilogue operand allows 16-byte bf16 vectors (N % 8 == 0, leading dimensions % 8 == 0)
   int fast;  // bf16 out = act(alpha*acc + bias) [+ bf16 residual], vec8: the lean path (set by finalize_epilogue)
+  int tma;   // lean path through smem tiles + TMA store (tmap_d [, tmap_r] are valid); GEMM mode only
 };
 
 inline void finalize_epilogue(EpilogueParams& ep) {
@@ -84,15 +85,21 @@ struct GemmCfg {
   static constexpr int BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;   // per CTA
-  static constexpr int STAGES = CTA2 ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARPS = 8;   // two per TMEM lane quadrant: they take alternate 16-column slices
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int EPI_LD = 20;     // floats per staged row (16 + 4 pad: conflict-free float4 access)
   static constexpr int EPI_BIAS_FLOATS = BN / 2;  // per epilogue warp: fp32 bias of the columns that warp owns
-  static constexpr int EPI_BYTES = EPI_WARPS * (32 * EPI_LD + EPI_BIAS_FLOATS) * 4;
+  // per epilogue warp: two 4 KB tiles (32 rows x 128 B, SWIZZLE_128B) that the TMA-store epilogue double-buffers;
+  // the register/STG epilogues use the first as fp32 transposition scratch and the second for the staged bias
+  static constexpr int EPI_WARP_BYTES = 8192;
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
   static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_LIMIT = 227 * 1024;
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static_assert(STAGES >= 3, "pipeline too shallow");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + align slack
 };
 
@@ -316,10 +323,106 @@ __device__ __forceinline__ void lean_tile(const EpilogueParams& ep, float* __res
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Lean epilogue through TMA:  bf16 out = act(alpha*acc + bias) [+ bf16 residual].
+// tcgen05.ld hands every lane one ROW of the accumulator (16 consecutive columns per load), so no transposition is
+// needed: the lane converts its 16 values, writes two 16-byte chunks into a [32 rows x 128 B] SWIZZLE_128B tile
+// (conflict-free: chunk index ^ (row & 7)), and one elected lane stores the tile with ONE bulk tensor store --
+// full 128-byte lines, clipped by the hardware at M and N.  The residual tile arrives the same way (TMA load into
+// the same buffer, read-modify-write in place).  Replaces ~32 partial-line STG wavefronts per 16-column slice.
+// Warp (quad, half) owns rows 32*quad.. and the 64-column groups half, half+2, ...
+// ----------------------------------------------------------------------------------------------------------
+template <int BN, int ACT, bool HAS_RES>
+__device__ __forceinline__ void lean_tile_tma(const EpilogueParams& ep, const CUtensorMap* tmap_d, const CUtensorMap* tmap_r,
+                                              uint8_t* stg, uint64_t* res_bar, uint32_t& res_phase, int& buf,
+                                              uint32_t t_row, int half, int lane, int row0, int n0, int N,
+                                              const float4 (&breg)[(BN + 255) / 256]) {
+  constexpr int NG = BN / 64;
+  const float alpha = ep.alpha;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+#pragma unroll 1
+  for (int g = half; g < NG; g += 2) {
+    const int gn = n0 + g * 64;
+    if (gn >= N) break;
+    uint8_t* tile = stg + buf * 4096;
+    uint8_t* rowp = tile + lane * 128;
+    // the bulk store that last read this buffer must be done with it (one other group may still be in flight)
+    if (elect_one()) bulk_wait_group_read<1>();
+    __syncwarp();
+    if (HAS_RES) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(res_bar, 4096u);
+        tma_load_2d(tile, tmap_r, res_bar, gn, row0);
+      }
+    }
+    uint32_t treg[16];
+    tmem_ld_32x16(t_row + g * 64, treg);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      // bias of these 16 columns: held 4 per lane by the lanes (gi % 2) * 16 + 4c .. + 3 of register set gi / 2
+      float b[16];
+      {
+        const int gi = (g - half) >> 1;
+        const float4 src = breg[gi >> 1];
+        const int l0 = (gi & 1) * 16 + c * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          b[4 * q] = __shfl_sync(0xffffffffu, src.x, l0 + q);
+          b[4 * q + 1] = __shfl_sync(0xffffffffu, src.y, l0 + q);
+          b[4 * q + 2] = __shfl_sync(0xffffffffu, src.z, l0 + q);
+          b[4 * q + 3] = __shfl_sync(0xffffffffu, src.w, l0 + q);
+        }
+      }
+      tmem_ld_wait();
+      float v0[8], v1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v0[k] = fmaf(__uint_as_float(treg[k]), alpha, b[k]);
+        v1[k] = fmaf(__uint_as_float(treg[8 + k]), alpha, b[8 + k]);
+      }
+      if (c + 1 < 4) tmem_ld_32x16(t_row + g * 64 + (c + 1) * 16, treg);   // next chunk in flight during the math
+      if (ACT != ACT_NONE) {
+        act_fwd8(ACT, v0);
+        act_fwd8(ACT, v1);
+      }
+      uint4* p0 = reinterpret_cast<uint4*>(rowp + (((2 * c) ^ sw) << 4));
+      uint4* p1 = reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ sw) << 4));
+      if (HAS_RES) {
+        if (c == 0) {
+          mbar_wait(res_bar, res_phase);
+          res_phase ^= 1u;
+        }
+        float r[8];
+        unpack8(*p0, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v0[k] += r[k];
+        unpack8(*p1, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v1[k] += r[k];
+      }
+      uint4 o;
+      o.x = pack_bf16x2(v0[0], v0[1]); o.y = pack_bf16x2(v0[2], v0[3]);
+      o.z = pack_bf16x2(v0[4], v0[5]); o.w = pack_bf16x2(v0[6], v0[7]);
+      *p0 = o;
+      o.x = pack_bf16x2(v1[0], v1[1]); o.y = pack_bf16x2(v1[2], v1[3]);
+      o.z = pack_bf16x2(v1[4], v1[5]); o.w = pack_bf16x2(v1[6], v1[7]);
+      *p1 = o;
+    }
+    fence_proxy_async_smem();   // generic-proxy writes of the tile -> visible to the bulk store
+    __syncwarp();
+    if (elect_one()) {
+      tma_store_2d(tmap_d, tile, gn, row0);
+      bulk_commit_group();
+    }
+    buf ^= 1;
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int MODE, bool CTA2 = false>
 __global__ void __launch_bounds__(GemmCfg<BN, CTA2>::THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b2,
+                 const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
                  const GemmParams p) {
   using Cfg = GemmCfg<BN, CTA2>;
   constexpr int STAGES = Cfg::STAGES;
@@ -343,7 +446,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* res_bars = bars + 2 * STAGES + 4;   // [EPI_WARPS] residual tiles of the TMA epilogue
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + Cfg::EPI_WARPS);
+  static_assert((2 * STAGES + 4 + Cfg::EPI_WARPS) * 8 + 4 <= Cfg::BAR_BYTES, "barrier block too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -368,6 +473,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], Cfg::EPI_WARPS * (CTA2 ? 2 : 1));  // one arrive per epilogue warp (of both CTAs)
     mbar_init(&tempty_bar[1], Cfg::EPI_WARPS * (CTA2 ? 2 : 1));
+    for (int w = 0; w < Cfg::EPI_WARPS; ++w) mbar_init(&res_bars[w], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -540,8 +646,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int ew = warp - 4;
     const int quad = ew & 3;
     const int half = ew >> 2;
-    float* st = epi_buf + ew * (32 * Cfg::EPI_LD);
-    float* bias_s = epi_buf + Cfg::EPI_WARPS * (32 * Cfg::EPI_LD) + ew * Cfg::EPI_BIAS_FLOATS;
+    uint8_t* stg = reinterpret_cast<uint8_t*>(epi_buf) + ew * Cfg::EPI_WARP_BYTES;   // 1024-byte aligned
+    float* st = reinterpret_cast<float*>(stg);
+    float* bias_s = reinterpret_cast<float*>(stg + 4096);
+    uint32_t res_phase = 0;
+    int stg_buf = 0;   // which of the two tiles the next 64-column group uses (alternates across tiles too)
+    const bool tma_epi = MODE == MODE_GEMM && p.ep.tma != 0;
+    if (tma_epi && lane == 0) {
+      tma_prefetch_desc(&tmap_d);
+      if (p.ep.residual) tma_prefetch_desc(&tmap_r);
+    }
     const int sub_row = lane & 15;        // 8 consecutive lanes read 8 consecutive staged rows: conflict-free
     const int col8 = (lane >> 4) * 8;
     const EpilogueParams& ep = p.ep;
@@ -578,7 +692,60 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       const int n0 = n_blk * BN;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      if (ep.fast && n0 + BN <= p.N) {
+      if (tma_epi) {
+        // ---------------- lean path through smem tiles + TMA store (any tile, clipped at M / N by the hardware) ----------
+        // this warp's bias slice, 4 columns per lane, requested while the accumulator is still being produced:
+        // lane l of register set s holds columns n0 + 64 * (half + 2 * (2 s + l / 16)) + 4 * (l % 16) ..
+        float4 breg[(BN + 255) / 256];
+#pragma unroll
+        for (int sidx = 0; sidx < (BN + 255) / 256; ++sidx) {
+          const int col = n0 + 64 * (half + 2 * (2 * sidx + (lane >> 4))) + 4 * (lane & 15);
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias && col < p.N && col < n0 + BN) {
+            if (ep.bias_f32) {
+              bv = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(ep.bias) + col));
+            } else {
+              const uint2 u = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(ep.bias) + col));
+              const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+              bv = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+          }
+          breg[sidx] = bv;
+        }
+        if (p.prof) {
+          const long long t0 = clock64();
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          w_tfull += clock64() - t0;
+        } else {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+        }
+        tc_fence_after();
+        const long long t_lean0 = p.prof ? clock64() : 0;
+        const int row0 = m_blk * 128 + quad * 32;
+#define GH_LEANT(A, R) \
+  lean_tile_tma<BN, A, R>(ep, &tmap_d, &tmap_r, stg, &res_bars[ew], res_phase, stg_buf, t_row, half, lane, row0, n0, p.N, breg)
+        if (row0 < p.M) {
+          if (ep.residual) {
+            switch (ep.act) {
+              case ACT_GELU_TANH: GH_LEANT(ACT_GELU_TANH, true); break;
+              case ACT_QUICK_GELU: GH_LEANT(ACT_QUICK_GELU, true); break;
+              case ACT_SILU: GH_LEANT(ACT_SILU, true); break;
+              case ACT_GELU_ERF: GH_LEANT(ACT_GELU_ERF, true); break;
+              default: GH_LEANT(ACT_NONE, true); break;
+            }
+          } else {
+            switch (ep.act) {
+              case ACT_GELU_TANH: GH_LEANT(ACT_GELU_TANH, false); break;
+              case ACT_QUICK_GELU: GH_LEANT(ACT_QUICK_GELU, false); break;
+              case ACT_SILU: GH_LEANT(ACT_SILU, false); break;
+              case ACT_GELU_ERF: GH_LEANT(ACT_GELU_ERF, false); break;
+              default: GH_LEANT(ACT_NONE, false); break;
+            }
+          }
+        }
+#undef GH_LEANT
+        if (p.prof) w_lean += clock64() - t_lean0;
+      } else if (ep.fast && n0 + BN <= p.N) {
         // ---------------- lean path: bf16 out = act(alpha*acc + bias) [+ bf16 residual], full-width tile ----------------
         // bias of this warp's columns -> smem (fp32) while the accumulator is still being produced
         {  // all loads first, then the smem stores (a store between two loads pins their order: 4 L2 round trips)
@@ -673,6 +840,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (tma_epi) bulk_wait_group_all();   // every bulk store of this thread has left smem AND reached memory
     if (p.prof && warp == 4 && lane == 0) {
       p.prof[blockIdx.x * 8 + 4] = clock64() - e_begin;
       p.prof[blockIdx.x * 8 + 5] = w_tfull;
