@@ -209,13 +209,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for i in range(steps):
             fn(i)
         e1.record()
+        host["enqueue_ms"] = (time.perf_counter() - t0) * 1e3   # host time to ENQUEUE the steps (no sync inside)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -225,21 +229,29 @@ def run_ours(args):
     # ---- device-resident arm -------------------------------------------------------------------------------
     for i in range(args.warmup):
         train_step(dev_batches[i % pool])
-    timer = GemmTimer()
-    K.GEMM_TIMER = timer
+    # forward + backward as ONE CUDA graph (genhancer_b200/graph.py); optimizer + zero_grad stay outside.  With
+    # data parallelism the backward issues NCCL buckets from Python hooks: eager there.
+    graphed = None
+    if world == 1 and not args.no_graph:
+        from genhancer_b200.graph import GraphedMicroStep
+        opt.zero_grad()
+        graphed = GraphedMicroStep(step, dev_batches[0], prepare=opt.zero_grad)
+
+        def train_step(img):  # noqa: F811  (same contract as the eager step above)
+            loss = graphed(img)
+            opt.step(gscale)
+            opt.zero_grad()
+            return loss
+
+        for i in range(args.warmup):
+            train_step(dev_batches[i % pool])
     clocks = ClockSampler(local)
-    n0 = K.LAUNCHES
+    n0, r0 = K.LAUNCHES, (graphed.replays if graphed else 0)
     clocks.start()
     ms_value = timed(lambda i: train_step(dev_batches[i % pool]), args.steps)
+    host_enqueue_ms = host["enqueue_ms"] / args.steps
     clocks.stop()
-    launches = K.LAUNCHES - n0
-    K.GEMM_TIMER = None
-    gemm_flops, gemm_ms, gemm_n = timer.summary()
-    if rank == 0 and args.dump_shapes:
-        os.makedirs(os.path.dirname(os.path.abspath(args.dump_shapes)), exist_ok=True)
-        json.dump({"steps": args.steps, "ms_step": ms_value / args.steps, "rows": timer.by_shape()},
-                  open(args.dump_shapes, "w"), indent=1)
-
+    launches = K.LAUNCHES - n0 + ((graphed.replays - r0) * graphed.launches_per_replay if graphed else 0)
     # ---- end-to-end arm: pinned host batch -> H2D -> step -> loss read back, every step ------------------------
     last = {}
 
@@ -251,10 +263,38 @@ def run_ours(args):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
 
+    # ---- roofline pass: the same step EAGER with CUDA events around every tcgen05 GEMM / conv launch (events cannot
+    # sit inside a graph); its own step time is the denominator of share_of_step ---------------------------------
+    def eager_step(img):
+        loss = step(img)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        opt.step(gscale)
+        opt.zero_grad()
+        return loss
+
+    eager_step(dev_batches[0])
+    timer = GemmTimer()
+    K.GEMM_TIMER = timer
+    n_roof = min(args.steps, 3)
+    ms_roof = timed(lambda i: eager_step(dev_batches[i % pool]), n_roof)
+    K.GEMM_TIMER = None
+    gemm_flops, gemm_ms, gemm_n = timer.summary()
+    if rank == 0 and args.dump_shapes:
+        os.makedirs(os.path.dirname(os.path.abspath(args.dump_shapes)), exist_ok=True)
+        json.dump({"steps": n_roof, "ms_step": ms_roof / n_roof, "rows": timer.by_shape()},
+                  open(args.dump_shapes, "w"), indent=1)
+
     images = B * world * args.steps
     value = images / (ms_value / 1e3)
     e2e = images / (ms_e2e / 1e3)
     peak_sust, peak_burst, prov = peaks()
+    # dram bytes of ONE launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01c_gemm_ncu_full.json")))
+    except (OSError, ValueError):
+        ncu = {}
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_value / args.steps, 3), "higher_is_better": True,
@@ -262,6 +302,7 @@ def run_ours(args):
         "config": {"workload": f"OpenAI CLIP ViT-L/14-{S} stage-1 step (AE encode + tower + projectors + DiT fwd/bwd + "
                                f"velocity-MSE + clip + AdamW), batch {B}/GPU, random-init weights",
                    "global_batch": B * world, "image_size": S, "parallelism": f"dp{world}",
+                   "execution": "forward+backward replayed as one CUDA graph, fused AdamW outside" if graphed else "eager launches",
                    "l2": "per-step working set (weights 3.9 GB + activations) is far larger than the 126 MB L2; "
                          "4 distinct input batches rotate"},
         "mfu": {"flops_per_image": FLOPS_PER_IMAGE,
@@ -275,8 +316,15 @@ def run_ours(args):
                      "achieved": round(gemm_flops / (gemm_ms * 1e-3) / 1e12, 1) if gemm_ms > 0 else None,
                      "peak": peak_sust, "unit": "TFLOP/s",
                      "frac": round(gemm_flops / (gemm_ms * 1e-3) / 1e12 / peak_sust, 4) if gemm_ms > 0 else None,
-                     "traffic": None, "launches_timed": gemm_n, "peak_source": prov,
-                     "share_of_step": round(gemm_ms / ms_value, 4) if ms_value > 0 else None},
+                     "traffic": ncu.get("traffic_bytes_per_launch"),
+                     "traffic_of": {k: ncu.get(k) for k in ("capture", "algorithmic_bytes_per_launch", "duration_us",
+                                                             "tensor_pipe_active_pct", "sm_clock_ghz_during_capture")},
+                     "launches_timed": gemm_n, "peak_source": prov,
+                     "share_of_step": round(gemm_ms / ms_roof, 4) if ms_roof > 0 else None,
+                     "measured_in": f"eager pass of {n_roof} steps, {round(ms_roof / n_roof, 3)} ms/step (CUDA events cannot be "
+                                    "recorded inside the graphed step)" if graphed else "the timed steps"},
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
+        "cuda_graph": bool(graphed),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_step(S, budget_s=args.cpu_budget)
@@ -390,6 +438,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (BASELINE configs[1]: 32)")
     ap.add_argument("--image-size", type=int, default=336)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
     ap.add_argument("--dump-shapes", default="", help="write the per-shape GEMM/conv timing table (JSON) here")
     ap.add_argument("--cpu-budget", type=float, default=45.0)
     ap.add_argument("--ref-budget", type=float, default=240.0)

@@ -5,6 +5,8 @@
 // the TMA unit, so padding (including the FLUX Downsample's asymmetric right/bottom pad,
 // src/flux/modules/autoencoder.py:85-95) costs nothing, and stride-2 convs use the tensor map's element strides.
 // Replaces nn.Conv2d at autoencoder.py:62-67 (ResnetBlock 3x3), :89 (Downsample), :157 (conv_out).
+#include <cstdlib>
+
 #include "internal.h"
 #include "umma_gemm.cuh"
 
@@ -14,6 +16,10 @@ template <int BN>
 static int conv_set_attr() {
   auto* k = umma_gemm_kernel<BN, false, false, MODE_CONV>;
   GH_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+  if constexpr (BN >= 128) {
+    auto* k2 = umma_gemm_kernel<BN, false, false, MODE_CONV, true>;
+    GH_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, true>::SMEM_BYTES));
+  }
   return GH_OK;
 }
 
@@ -30,6 +36,27 @@ static int conv_launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int grid = tiles < num_sms() ? tiles : num_sms();
   umma_gemm_kernel<BN, false, false, MODE_CONV><<<grid, GemmCfg<BN>::THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(ta, tb, ta, tb, ta, tb, p);
   GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+// CTA pairs: two adjacent output patches (256 GEMM rows) share one weight tile, half of it staged per CTA
+template <int BN>
+static int conv_launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+  const int tiles = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  cfg.blockDim = dim3(GemmCfg<BN, true>::THREADS);
+  cfg.dynamicSmemBytes = GemmCfg<BN, true>::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  GH_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, false, false, MODE_CONV, true>, ta, tb, ta, tb, ta, tb, p));
   return GH_OK;
 }
 
@@ -76,6 +103,8 @@ extern "C" int gh_conv2d_nhwc(const gh_conv_args* a, void* stream) {
   // fewer, fatter tiles waste the tail wave: drop to a narrower N tile if that fills the machine better
   while (bn > 64 && static_cast<long>(p.num_m_blocks) * ((a->Cout + bn - 1) / bn) < num_sms()) bn /= 2;
   p.num_n_blocks = (a->Cout + bn - 1) / bn;
+  static const int conv_pair = [] { const char* e = getenv("GH_CONV_PAIR"); return e ? atoi(e) : 1; }();
+  const bool pair = conv_pair && bn >= 128 && p.num_m_blocks >= 2 * num_sms();
   p.num_k_blocks = K / 64;
   p.a_stage_tx_bytes = static_cast<uint32_t>(TW * TH * 128);
   p.mn_lbo = 8192; p.mn_sbo = 1024; p.mn_kstep = 2048;
@@ -101,10 +130,11 @@ extern "C" int gh_conv2d_nhwc(const gh_conv_args* a, void* stream) {
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(a->Cout)};
     const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(pair ? bn / 2 : bn)};
     if (int e = make_tmap_bf16(&tb, a->w, 2, dims, strides, box, nullptr)) return e;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (pair) return bn == 256 ? conv_launch_pair<256>(ta, tb, p, s) : conv_launch_pair<128>(ta, tb, p, s);
   switch (bn) {
     case 256: return conv_launch<256>(ta, tb, p, s);
     case 128: return conv_launch<128>(ta, tb, p, s);

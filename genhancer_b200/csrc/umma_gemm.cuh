@@ -682,7 +682,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int rem = m_blk - cb * tiles_per_img;
           const int oh = (rem / p.cv.tiles_w) * p.cv.TH + tr / p.cv.TW;
           const int ow = (rem % p.cv.tiles_w) * p.cv.TW + tr % p.cv.TW;
-          ok = (tr < p.cv.TW * p.cv.TH) && (oh < p.cv.Ho) && (ow < p.cv.Wo);
+          ok = (tr < p.cv.TW * p.cv.TH) && (oh < p.cv.Ho) && (ow < p.cv.Wo) && (cb < p.cv.B);
           rows[it] = (cb * p.cv.Ho + oh) * p.cv.Wo + ow;
         } else {
           rows[it] = m_blk * 128 + tr;
