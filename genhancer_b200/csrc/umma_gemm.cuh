@@ -506,6 +506,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ch0 = (r / p.cv.tiles_w) * p.cv.TH;
         cw0 = (r % p.cv.tiles_w) * p.cv.TW;
       }
+      int c_cc = 0, c_kw = 0, c_kh = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         if (p.prof) {
           const long long t0 = clock64();
@@ -529,9 +530,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
           };
           if (MODE == MODE_CONV) {
-            const int tap = kb / p.cv.cin_chunks;
-            const int cc = kb - tap * p.cv.cin_chunks;
-            const int kh = tap / p.cv.KW, kw = tap - kh * p.cv.KW;
+            const int cc = c_cc, kh = c_kh, kw = c_kw;   // (tap, 64-channel chunk) of this k block, kept incrementally
             if (CTA2)
               tma2_load_4d(sA, &tmap_a, fb, cc * 64, cw0 * p.cv.stride + kw - p.cv.pad, ch0 * p.cv.stride + kh - p.cv.pad, cb);
             else
@@ -564,6 +563,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       next_stage:
         __syncwarp();
+        if (MODE == MODE_CONV) {
+          if (++c_cc == p.cv.cin_chunks) {
+            c_cc = 0;
+            if (++c_kw == p.cv.KW) { c_kw = 0; ++c_kh; }
+          }
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
