@@ -98,6 +98,7 @@ SIGNATURES: dict[str, list] = {
     "gh_act_fwd": [_vp, _vp, _i64, _i32, _vp],
     "gh_act_bwd": [_vp, _vp, _vp, _i64, _i32, _vp],
     "gh_accum_cast": [_vp, _vp, _i32, _i64, _f32, _i32, _vp],
+    "gh_euler_cfg_step": [_vp, _vp, _vp, _f32, _f32, _i64, _vp],
     "gh_batched_copy": [_vp, _i32, _i32, _vp],
     "gh_dropout_fwd": [_vp, _vp, _i64, _f32, C.c_uint64, C.c_uint64, _vp],
     "gh_dropout_bwd_add": [_vp, _vp, _i64, _f32, C.c_uint64, C.c_uint64, _vp],

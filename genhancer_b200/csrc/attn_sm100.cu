@@ -103,36 +103,47 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const uint32_t tmem = *tmem_ptr;
 
   if (warp == 4) {
-    if (lane == 0) {
-      // ---------------- control thread: TMA + MMA issue ----------------
+    {
+      // ---------------- control warp: TMA + MMA issue ----------------
+      // All 32 lanes run the control flow (waits, loop counters); every async-unit instruction is issued by one
+      // ELECTED lane (elect.sync), so its operands sit in uniform registers -- under `lane == 0` the compiler wraps
+      // each UTCHMMA / UTMALDG / UTCBAR in an ELECT/R2UR/BRA.U.ANY waterfall (~100+ cycles per instruction).
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, ATT_BKV, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
       const uint64_t kdesc = umma_desc_base(16u, 1024u);      // K-major tiles (Q, K, P)
       const uint64_t vdesc = umma_desc_base(8192u, 1024u);    // V as MN-major B operand
       auto load_k = [&](int j) {
-        uint8_t* dst = sK + (j & 1) * Cfg::K_BYTES;
-        mbar_arrive_expect_tx(&bar_k[j & 1], Cfg::K_BYTES);
-#pragma unroll
-        for (int c = 0; c < DC; ++c) tma_load_4d(dst + c * 8192, &tm_k, &bar_k[j & 1], c * 64, j * ATT_BKV, h, b);
+        if (elect_one()) {
+          uint8_t* dst = sK + (j & 1) * Cfg::K_BYTES;
+          mbar_arrive_expect_tx(&bar_k[j & 1], Cfg::K_BYTES);
+  #pragma unroll
+          for (int c = 0; c < DC; ++c) tma_load_4d(dst + c * 8192, &tm_k, &bar_k[j & 1], c * 64, j * ATT_BKV, h, b);
+        }
       };
       auto load_v = [&](int j) {
-        mbar_arrive_expect_tx(bar_v, Cfg::V_BYTES);
-#pragma unroll
-        for (int c = 0; c < DC; ++c) tma_load_4d(sV + c * 8192, &tm_v, bar_v, c * 64, j * ATT_BKV, h, b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_v, Cfg::V_BYTES);
+  #pragma unroll
+          for (int c = 0; c < DC; ++c) tma_load_4d(sV + c * 8192, &tm_v, bar_v, c * 64, j * ATT_BKV, h, b);
+        }
       };
       auto issue_s = [&](int j) {
-        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + (j & 1) * Cfg::K_BYTES);
-#pragma unroll
-        for (int c = 0; c < DC; ++c)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tmem + Cfg::TM_S + (j & 1) * ATT_BKV, umma_desc_at(kdesc, aQ + c * 16384 + k * 32),
-                    umma_desc_at(kdesc, aK + c * 8192 + k * 32), idesc_s, (c | k) != 0 ? 1u : 0u);
-        umma_commit(&bar_s[j & 1]);
+        if (elect_one()) {
+          const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + (j & 1) * Cfg::K_BYTES);
+  #pragma unroll
+          for (int c = 0; c < DC; ++c)
+  #pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss(tmem + Cfg::TM_S + (j & 1) * ATT_BKV, umma_desc_at(kdesc, aQ + c * 16384 + k * 32),
+                      umma_desc_at(kdesc, aK + c * 8192 + k * 32), idesc_s, (c | k) != 0 ? 1u : 0u);
+          umma_commit(&bar_s[j & 1]);
+        }
       };
-      mbar_arrive_expect_tx(bar_q, Cfg::Q_BYTES);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_q, Cfg::Q_BYTES);
 #pragma unroll
-      for (int c = 0; c < DC; ++c) tma_load_4d(sQ + c * 16384, &tm_q, bar_q, c * 64, q0, h, b);
+        for (int c = 0; c < DC; ++c) tma_load_4d(sQ + c * 16384, &tm_q, bar_q, c * 64, q0, h, b);
+      }
       load_k(0);
       load_v(0);
       if (nkv > 1) load_k(1);
@@ -150,7 +161,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_wait(bar_p, j & 1);  // P_j is in smem (and O has been rescaled if needed)
         mbar_wait(bar_v, j & 1);
         tc_fence_after();
-        {
+        if (elect_one()) {
           const uint32_t aP = smem_u32(sP), aV = smem_u32(sV);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -374,44 +385,50 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
   const uint32_t tmem = *tmem_ptr;
 
   if (warp == 4) {
-    if (lane == 0) {
+    {  // control warp: see flash_fwd_kernel (all lanes run the flow, one elected lane issues)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_a = umma_idesc_bf16(128, D, false, true);
       const uint64_t kdesc = umma_desc_base(16u, 1024u);
       const uint64_t mdesc = umma_desc_base(8192u, 1024u);
       auto load_qd = [&](int i) {
-        const int s = i % NQ;
-        mbar_arrive_expect_tx(&bar_qd[s], 2 * Cfg::QD_BYTES);
-#pragma unroll
-        for (int c = 0; c < DC; ++c) {
-          tma_load_4d(sQ + s * Cfg::QD_BYTES + c * 8192, &tm_q, &bar_qd[s], c * 64, i * 64, h, b);
-          tma_load_4d(sDO + s * Cfg::QD_BYTES + c * 8192, &tm_do, &bar_qd[s], c * 64, i * 64, h, b);
+        if (elect_one()) {
+          const int s = i % NQ;
+          mbar_arrive_expect_tx(&bar_qd[s], 2 * Cfg::QD_BYTES);
+  #pragma unroll
+          for (int c = 0; c < DC; ++c) {
+            tma_load_4d(sQ + s * Cfg::QD_BYTES + c * 8192, &tm_q, &bar_qd[s], c * 64, i * 64, h, b);
+            tma_load_4d(sDO + s * Cfg::QD_BYTES + c * 8192, &tm_do, &bar_qd[s], c * 64, i * 64, h, b);
+          }
         }
       };
       auto issue_sd = [&](int i) {
-        const int s = i % NQ;
-        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-        const uint32_t aQ = smem_u32(sQ + s * Cfg::QD_BYTES), aD = smem_u32(sDO + s * Cfg::QD_BYTES);
-        const uint32_t tS = tmem + (i & 1) * 128, tP = tS + 64;
-#pragma unroll
-        for (int c = 0; c < DC; ++c)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tS, umma_desc_at(kdesc, aK + c * 16384 + k * 32), umma_desc_at(kdesc, aQ + c * 8192 + k * 32),
-                    idesc_s, (c | k) != 0 ? 1u : 0u);
-#pragma unroll
-        for (int c = 0; c < DC; ++c)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tP, umma_desc_at(kdesc, aV + c * 16384 + k * 32), umma_desc_at(kdesc, aD + c * 8192 + k * 32),
-                    idesc_s, (c | k) != 0 ? 1u : 0u);
-        umma_commit(&bar_sd[i & 1]);
+        if (elect_one()) {
+          const int s = i % NQ;
+          const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+          const uint32_t aQ = smem_u32(sQ + s * Cfg::QD_BYTES), aD = smem_u32(sDO + s * Cfg::QD_BYTES);
+          const uint32_t tS = tmem + (i & 1) * 128, tP = tS + 64;
+  #pragma unroll
+          for (int c = 0; c < DC; ++c)
+  #pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss(tS, umma_desc_at(kdesc, aK + c * 16384 + k * 32), umma_desc_at(kdesc, aQ + c * 8192 + k * 32),
+                      idesc_s, (c | k) != 0 ? 1u : 0u);
+  #pragma unroll
+          for (int c = 0; c < DC; ++c)
+  #pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss(tP, umma_desc_at(kdesc, aV + c * 16384 + k * 32), umma_desc_at(kdesc, aD + c * 8192 + k * 32),
+                      idesc_s, (c | k) != 0 ? 1u : 0u);
+          umma_commit(&bar_sd[i & 1]);
+        }
       };
-      mbar_arrive_expect_tx(bar_kv, 2 * Cfg::KV_BYTES);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_kv, 2 * Cfg::KV_BYTES);
 #pragma unroll
-      for (int c = 0; c < DC; ++c) {
-        tma_load_4d(sK + c * 16384, &tm_k, bar_kv, c * 64, k0, h, b);
-        tma_load_4d(sV + c * 16384, &tm_v, bar_kv, c * 64, k0, h, b);
+        for (int c = 0; c < DC; ++c) {
+          tma_load_4d(sK + c * 16384, &tm_k, bar_kv, c * 64, k0, h, b);
+          tma_load_4d(sV + c * 16384, &tm_v, bar_kv, c * 64, k0, h, b);
+        }
       }
       load_qd(0);
       if (nq > 1) load_qd(1);
@@ -428,7 +445,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
         mbar_wait(bar_pd, i & 1);  // P^T_i, dS^T_i in smem; implies acc MMAs of i-1 have retired
         tc_fence_after();
         if (i + 2 < nq) load_qd(i + 2);  // ring slot (i+2)%3 == (i-1)%3 is free
-        {
+        if (elect_one()) {
           const int s = i % NQ;
           const uint32_t aPT = smem_u32(sPT), aDST = smem_u32(sDST);
           const uint32_t aQ = smem_u32(sQ + s * Cfg::QD_BYTES), aD = smem_u32(sDO + s * Cfg::QD_BYTES);
@@ -583,44 +600,50 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t tmem = *tmem_ptr;
 
   if (warp == 4) {
-    if (lane == 0) {
+    {  // control warp: see flash_fwd_kernel (all lanes run the flow, one elected lane issues)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_a = umma_idesc_bf16(128, D, false, true);
       const uint64_t kdesc = umma_desc_base(16u, 1024u);
       const uint64_t mdesc = umma_desc_base(8192u, 1024u);
       auto load_kv = [&](int j) {
-        const int s = j % NK;
-        mbar_arrive_expect_tx(&bar_kv[s], 2 * Cfg::KV_BYTES);
-#pragma unroll
-        for (int c = 0; c < DC; ++c) {
-          tma_load_4d(sK + s * Cfg::KV_BYTES + c * 8192, &tm_k, &bar_kv[s], c * 64, j * 64, h, b);
-          tma_load_4d(sV + s * Cfg::KV_BYTES + c * 8192, &tm_v, &bar_kv[s], c * 64, j * 64, h, b);
+        if (elect_one()) {
+          const int s = j % NK;
+          mbar_arrive_expect_tx(&bar_kv[s], 2 * Cfg::KV_BYTES);
+  #pragma unroll
+          for (int c = 0; c < DC; ++c) {
+            tma_load_4d(sK + s * Cfg::KV_BYTES + c * 8192, &tm_k, &bar_kv[s], c * 64, j * 64, h, b);
+            tma_load_4d(sV + s * Cfg::KV_BYTES + c * 8192, &tm_v, &bar_kv[s], c * 64, j * 64, h, b);
+          }
         }
       };
       auto issue_sd = [&](int j) {
-        const int s = j % NK;
-        const uint32_t aQ = smem_u32(sQ), aD = smem_u32(sDO);
-        const uint32_t aK = smem_u32(sK + s * Cfg::KV_BYTES), aV = smem_u32(sV + s * Cfg::KV_BYTES);
-        const uint32_t tS = tmem + (j & 1) * 128, tP = tS + 64;
-#pragma unroll
-        for (int c = 0; c < DC; ++c)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tS, umma_desc_at(kdesc, aQ + c * 16384 + k * 32), umma_desc_at(kdesc, aK + c * 8192 + k * 32),
-                    idesc_s, (c | k) != 0 ? 1u : 0u);
-#pragma unroll
-        for (int c = 0; c < DC; ++c)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tP, umma_desc_at(kdesc, aD + c * 16384 + k * 32), umma_desc_at(kdesc, aV + c * 8192 + k * 32),
-                    idesc_s, (c | k) != 0 ? 1u : 0u);
-        umma_commit(&bar_sd[j & 1]);
+        if (elect_one()) {
+          const int s = j % NK;
+          const uint32_t aQ = smem_u32(sQ), aD = smem_u32(sDO);
+          const uint32_t aK = smem_u32(sK + s * Cfg::KV_BYTES), aV = smem_u32(sV + s * Cfg::KV_BYTES);
+          const uint32_t tS = tmem + (j & 1) * 128, tP = tS + 64;
+  #pragma unroll
+          for (int c = 0; c < DC; ++c)
+  #pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss(tS, umma_desc_at(kdesc, aQ + c * 16384 + k * 32), umma_desc_at(kdesc, aK + c * 8192 + k * 32),
+                      idesc_s, (c | k) != 0 ? 1u : 0u);
+  #pragma unroll
+          for (int c = 0; c < DC; ++c)
+  #pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss(tP, umma_desc_at(kdesc, aD + c * 16384 + k * 32), umma_desc_at(kdesc, aV + c * 8192 + k * 32),
+                      idesc_s, (c | k) != 0 ? 1u : 0u);
+          umma_commit(&bar_sd[j & 1]);
+        }
       };
-      mbar_arrive_expect_tx(bar_q, 2 * Cfg::Q_BYTES);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_q, 2 * Cfg::Q_BYTES);
 #pragma unroll
-      for (int c = 0; c < DC; ++c) {
-        tma_load_4d(sQ + c * 16384, &tm_q, bar_q, c * 64, q0, h, b);
-        tma_load_4d(sDO + c * 16384, &tm_do, bar_q, c * 64, q0, h, b);
+        for (int c = 0; c < DC; ++c) {
+          tma_load_4d(sQ + c * 16384, &tm_q, bar_q, c * 64, q0, h, b);
+          tma_load_4d(sDO + c * 16384, &tm_do, bar_q, c * 64, q0, h, b);
+        }
       }
       load_kv(0);
       if (nkv > 1) load_kv(1);
@@ -637,7 +660,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_wait(bar_pd, j & 1);
         tc_fence_after();
         if (j + 2 < nkv) load_kv(j + 2);
-        {
+        if (elect_one()) {
           const uint32_t aDS = smem_u32(sDS), aK = smem_u32(sK + (j % NK) * Cfg::KV_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)

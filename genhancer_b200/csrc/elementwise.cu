@@ -121,6 +121,29 @@ __global__ void __launch_bounds__(256) dropout_kernel(const uint2* __restrict__ 
   }
 }
 
+// Euler step of the flow sampler with the classifier-free-guidance mix fused (src/flux/sampling.py:143-146):
+//   v = neg ? neg + gs * (pred - neg) : pred ;  x += dt * v      (bf16 in the reference's bf16 arithmetic order:
+//   every intermediate is rounded to bf16 as torch does for bf16 tensors).  4 elements per thread.
+__global__ void __launch_bounds__(256) euler_step_kernel(uint2* __restrict__ x, const uint2* __restrict__ pred,
+                                                         const uint2* __restrict__ neg, float dt, float gs, int64_t n4) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  auto r = [](float v) { return __bfloat162float(__float2bfloat16(v)); };
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint2 xv = x[i], pv = pred[i];
+    float xs[4] = {unpack_bf16x2(xv.x).x, unpack_bf16x2(xv.x).y, unpack_bf16x2(xv.y).x, unpack_bf16x2(xv.y).y};
+    float ps[4] = {unpack_bf16x2(pv.x).x, unpack_bf16x2(pv.x).y, unpack_bf16x2(pv.y).x, unpack_bf16x2(pv.y).y};
+    if (neg) {
+      const uint2 nv = neg[i];
+      const float ns[4] = {unpack_bf16x2(nv.x).x, unpack_bf16x2(nv.x).y, unpack_bf16x2(nv.y).x, unpack_bf16x2(nv.y).y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ps[k] = r(ns[k] + r(gs * r(ps[k] - ns[k])));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xs[k] = r(xs[k] + r(dt * ps[k]));
+    x[i] = make_uint2(pack_bf16x2(xs[0], xs[1]), pack_bf16x2(xs[2], xs[3]));
+  }
+}
+
 static inline int ew_grid(int64_t n_items, int block) {
   const int64_t want = (n_items + block - 1) / block;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;  // 8 resident CTAs of 256 threads per SM
@@ -206,4 +229,19 @@ extern "C" int gh_dropout_fwd(const void* x_bf16, void* y_bf16, int64_t numel, f
 extern "C" int gh_dropout_bwd_add(const void* t_bf16, void* dx_bf16, int64_t numel, float p, uint64_t seed, uint64_t offset,
                                   void* stream) {
   return launch_dropout(true, t_bf16, dx_bf16, numel, p, seed, offset, stream, "gh_dropout_bwd_add");
+}
+
+extern "C" int gh_euler_cfg_step(void* x_bf16, const void* pred_bf16, const void* neg_pred_bf16, float dt, float true_gs,
+                                 int64_t numel, void* stream) {
+  using namespace gh;
+  GH_REQUIRE(x_bf16 && pred_bf16, GH_ERR_NULL, "gh_euler_cfg_step: NULL pointer");
+  GH_REQUIRE(numel >= 0 && numel % 4 == 0, GH_ERR_BAD_SHAPE, "gh_euler_cfg_step: numel=%lld must be a multiple of 4",
+             (long long)numel);
+  if (numel == 0) return GH_OK;
+  const int64_t n4 = numel / 4;
+  euler_step_kernel<<<ew_grid(n4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint2*>(x_bf16), static_cast<const uint2*>(pred_bf16), static_cast<const uint2*>(neg_pred_bf16), dt,
+      true_gs, n4);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
 }

@@ -29,27 +29,45 @@ struct RowMap {  // row r = b * rpb + l  ->  element offset b * batch_stride + l
   }
 };
 
+// Sum over the WPR warps that share one row (WPR = 1: plain warp reduction).  Wide rows (C > 2048) are split
+// over two warps so that the row cache stays at 8 x 16 B per lane: with one warp per 3072-wide row the kernels
+// needed 144 / 180 registers -> ONE 256-thread block per SM -> 2.1-2.4 TB/s.  The pair meets at its own named
+// barrier (64 threads), so blocks whose last pair is past the end need no block-wide sync.
+template <int WPR>
+__device__ __forceinline__ float row_sum(float v, int warp, int lane, float* red) {
+  v = warp_sum(v);
+  if (WPR == 1) return v;
+  const int bar = 1 + (warp >> 1);
+  if (lane == 0) red[warp] = v;
+  asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
+  const float t = red[warp] + red[warp ^ 1];
+  asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");  // red[] may be rewritten by the next reduction
+  return t;
+}
+
 // ============================================================================
-// LayerNorm forward: one warp per row, row cached in registers.
+// LayerNorm forward: one warp (or a pair of warps) per row, row cached in registers.
 //   y = n * w + b                      (affine, fp32 params)            or
 //   y = (1 + scale[b]) * n + shift[b]  (AdaLN, bf16 per-sample vectors) or  y = n
 // algorithmic bytes / element: 2 (read) + 2 (write)
 // ============================================================================
-template <int VMAX>
+template <int VMAX, int WPR>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, RowMap xm, bf16* __restrict__ y,
                                                      RowMap ym, int rows, int C, const float* __restrict__ w,
                                                      const float* __restrict__ bias, const bf16* __restrict__ shift,
                                                      const bf16* __restrict__ scale, int64_t mod_ld, float eps,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  __shared__ float red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + warp;
+  const int r = blockIdx.x * (8 / WPR) + warp / WPR;
   if (r >= rows) return;
+  const int lane_g = (warp % WPR) * 32 + lane;   // position among the 32 * WPR lanes of this row
   const bf16* xr = x + xm.off(r);
   uint4 v[VMAX];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < VMAX; ++i) {
-    const int c = (i * 32 + lane) * 8;
+    const int c = (i * 32 * WPR + lane_g) * 8;
     if (c < C) {
       v[i] = *reinterpret_cast<const uint4*>(xr + c);
       float f[8];
@@ -58,11 +76,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
       for (int j = 0; j < 8; ++j) s += f[j];
     }
   }
-  const float mean = warp_sum(s) / C;
+  const float mean = row_sum<WPR>(s, warp, lane, red) / C;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < VMAX; ++i) {
-    const int c = (i * 32 + lane) * 8;
+    const int c = (i * 32 * WPR + lane_g) * 8;
     if (c < C) {
       float f[8];
       unpack8(v[i], f);
@@ -70,8 +88,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
       for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; q += d * d; }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / C + eps);
-  if (lane == 0) {
+  const float rstd = rsqrtf(row_sum<WPR>(q, warp, lane, red) / C + eps);
+  if (lane_g == 0) {
     if (mean_out) mean_out[r] = mean;
     if (rstd_out) rstd_out[r] = rstd;
   }
@@ -79,7 +97,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
   bf16* yr = y + ym.off(r);
 #pragma unroll
   for (int i = 0; i < VMAX; ++i) {
-    const int c = (i * 32 + lane) * 8;
+    const int c = (i * 32 * WPR + lane_g) * 8;
     if (c < C) {
       float f[8], o[8];
       unpack8(v[i], f);
@@ -109,16 +127,18 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 // LayerNorm backward w.r.t. x (one warp per row):
 //   dn = dy * g,  g = w | (1 + scale[b]) | 1 ;  dx = rstd * (dn - mean(dn) - n * mean(dn * n)) [+ dres]
 // ============================================================================
-template <int VMAX>
+template <int VMAX, int WPR>
 __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__ dy, RowMap dym,
                                                         const bf16* __restrict__ x, RowMap xm, int rows, int C,
                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                                         const float* __restrict__ w, const bf16* __restrict__ scale,
                                                         int64_t mod_ld, const bf16* __restrict__ dres, RowMap drm,
                                                         bf16* __restrict__ dx, RowMap dxm) {
+  __shared__ float red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + warp;
+  const int r = blockIdx.x * (8 / WPR) + warp / WPR;
   if (r >= rows) return;
+  const int lane_g = (warp % WPR) * 32 + lane;
   const bf16* xr = x + xm.off(r);
   const bf16* dyr = dy + dym.off(r);
   const int b = r / xm.rpb;
@@ -127,7 +147,7 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VMAX; ++i) {
-    const int c = (i * 32 + lane) * 8;
+    const int c = (i * 32 * WPR + lane_g) * 8;
     if (c < C) {
       vn[i] = *reinterpret_cast<const uint4*>(xr + c);
       vd[i] = *reinterpret_cast<const uint4*>(dyr + c);
@@ -155,12 +175,12 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__
       // keep dn in fp32 precision would need 2x registers; re-derive from dy*g below instead
     }
   }
-  const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
+  const float m1 = row_sum<WPR>(s1, warp, lane, red) / C, m2 = row_sum<WPR>(s2, warp, lane, red) / C;
   bf16* dxr = dx + dxm.off(r);
   const bf16* drr = dres ? dres + drm.off(r) : nullptr;
 #pragma unroll
   for (int i = 0; i < VMAX; ++i) {
-    const int c = (i * 32 + lane) * 8;
+    const int c = (i * 32 * WPR + lane_g) * 8;
     if (c < C) {
       float fx[8], fd[8], g[8], o[8];
       unpack8(vn[i], fx);
@@ -206,35 +226,84 @@ __global__ void __launch_bounds__(512) col_reduce_kernel(const bf16* __restrict_
                                                          const bf16* __restrict__ gate, int64_t gate_ld,
                                                          bf16* __restrict__ du, RowMap dum, float* __restrict__ acc0,
                                                          float* __restrict__ acc1, int64_t acc_ld, int rows_per_cta) {
+  // blockDim = (C / 8 column groups, ny row lanes): thread (tx, ty) owns 8 columns and the rows l0 + ty + k * ny of
+  // its CTA's chunk; the ny partial sums meet in shared memory, so one CTA issues ONE atomic per column however
+  // many rows it covers (same-address atomics serialise in L2: fewer, fatter CTAs beat many small ones).
+  extern __shared__ float cr_smem[];
+  const int ny = blockDim.y, ty = threadIdx.y;
   const int c = (blockIdx.z * blockDim.x + threadIdx.x) * 8;
-  if (c >= C) return;
+  const bool live = c < C;
   const int b = blockIdx.y;
   const int l0 = blockIdx.x * rows_per_cta;
   const int l1 = min(l0 + rows_per_cta, dym.rpb);
   float a0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  float g[8];
-  if (MODE == 1) unpack8(*reinterpret_cast<const uint4*>(gate + static_cast<int64_t>(b) * gate_ld + c), g);
-  for (int l = l0; l < l1; ++l) {
-    const int r = b * dym.rpb + l;
-    float fd[8];
-    unpack8(*reinterpret_cast<const uint4*>(dy + dym.off(r) + c), fd);
-    if (MODE == 0) {
-      float fx[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + xm.off(r) + c), fx);
-      const float mu = mean[r], rs = rstd[r];
+  if (live && l0 + ty < l1) {
+    float g[8];
+    if (MODE == 1) unpack8(*reinterpret_cast<const uint4*>(gate + static_cast<int64_t>(b) * gate_ld + c), g);
+    // the chunk lies inside ONE sample: resolve the row maps once, then walk by the row strides, four rows per trip
+    // with all loads issued before the math (a per-row `off()` division serialised the address stream)
+    const int r0 = b * dym.rpb + l0 + ty;
+    const int64_t sd = dym.row_stride * ny, sx = xm.row_stride * ny, su = dum.row_stride * ny;
+    const bf16* pd = dy + dym.off(r0) + c;
+    const bf16* px = (MODE != 2) ? x + xm.off(r0) + c : nullptr;
+    bf16* pu = (MODE == 1) ? du + dum.off(r0) + c : nullptr;
+    auto one = [&](const uint4& vd, const uint4& vx, int r, bf16* out) {
+      float fd[8];
+      unpack8(vd, fd);
+      if (MODE == 0) {
+        float fx[8];
+        unpack8(vx, fx);
+        const float mu = mean[r], rs = rstd[r];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a0[j] += fd[j]; a1[j] += fd[j] * ((fx[j] - mu) * rs); }
-    } else if (MODE == 1) {
-      float fu[8], o[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + xm.off(r) + c), fu);
+        for (int j = 0; j < 8; ++j) { a0[j] += fd[j]; a1[j] += fd[j] * ((fx[j] - mu) * rs); }
+      } else if (MODE == 1) {
+        float fu[8], o[8];
+        unpack8(vx, fu);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a0[j] += fd[j] * fu[j]; o[j] = g[j] * fd[j]; }
-      *reinterpret_cast<uint4*>(du + dum.off(r) + c) = pack8(o);
-    } else {
+        for (int j = 0; j < 8; ++j) { a0[j] += fd[j] * fu[j]; o[j] = g[j] * fd[j]; }
+        *reinterpret_cast<uint4*>(out) = pack8(o);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a0[j] += fd[j];
+        for (int j = 0; j < 8; ++j) a0[j] += fd[j];
+      }
+    };
+    int l = l0 + ty, r = r0;
+    for (; l + 3 * ny < l1; l += 4 * ny, r += 4 * ny) {
+      uint4 vd[4], vx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vd[u] = *reinterpret_cast<const uint4*>(pd + u * sd);
+        if (MODE != 2) vx[u] = *reinterpret_cast<const uint4*>(px + u * sx);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) one(vd[u], vx[u], r + u * ny, MODE == 1 ? pu + u * su : nullptr);
+      pd += 4 * sd;
+      if (MODE != 2) px += 4 * sx;
+      if (MODE == 1) pu += 4 * su;
+    }
+    for (; l < l1; l += ny, r += ny) {
+      const uint4 vd = *reinterpret_cast<const uint4*>(pd);
+      uint4 vx = make_uint4(0, 0, 0, 0);
+      if (MODE != 2) vx = *reinterpret_cast<const uint4*>(px);
+      one(vd, vx, r, pu);
+      pd += sd;
+      if (MODE != 2) px += sx;
+      if (MODE == 1) pu += su;
     }
   }
+  if (ny > 1) {  // fold the row lanes: [ny][blockDim.x][16] floats
+    float* mine = cr_smem + (static_cast<size_t>(ty) * blockDim.x + threadIdx.x) * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mine[j] = a0[j]; mine[8 + j] = a1[j]; }
+    __syncthreads();
+    if (ty != 0) return;
+    for (int y = 1; y < ny; ++y) {
+      const float* o = cr_smem + (static_cast<size_t>(y) * blockDim.x + threadIdx.x) * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a0[j] += o[j]; a1[j] += o[8 + j]; }
+    }
+  }
+  if (!live) return;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     atomicAdd(acc0 + static_cast<int64_t>(b) * acc_ld + c + j, a0[j]);
@@ -472,15 +541,14 @@ extern "C" int gh_layernorm_fwd(const void* x, const gh_rows_view* xv, void* y, 
   GH_REQUIRE(!scale || mod_ld % 8 == 0, GH_ERR_ALIGN, "gh_layernorm_fwd: mod_ld must be a multiple of 8");
   const RowMap xm = mk(xv->rows_per_batch, xv->batch_stride, xv->row_stride);
   const RowMap ym = mk(yv->rows_per_batch, yv->batch_stride, yv->row_stride);
-  const int grid = (rows + 7) / 8;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define GH_LN(V)                                                                                                   \
-  ln_fwd_kernel<V><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), xm, static_cast<bf16*>(y), ym, rows, C, weight, \
-                                        bias, static_cast<const bf16*>(shift), static_cast<const bf16*>(scale),     \
-                                        mod_ld, eps, mean_out, rstd_out)
-  if (C <= 1024) GH_LN(4);
-  else if (C <= 2048) GH_LN(8);
-  else GH_LN(16);
+#define GH_LN(V, W)                                                                                                  \
+  ln_fwd_kernel<V, W><<<(rows + 8 / W - 1) / (8 / W), 256, 0, s>>>(                                                   \
+      static_cast<const bf16*>(x), xm, static_cast<bf16*>(y), ym, rows, C, weight, bias,                            \
+      static_cast<const bf16*>(shift), static_cast<const bf16*>(scale), mod_ld, eps, mean_out, rstd_out)
+  if (C <= 1024) GH_LN(4, 1);
+  else if (C <= 2048) GH_LN(8, 1);
+  else GH_LN(8, 2);   // wide rows: a pair of warps per row (see row_sum)
 #undef GH_LN
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
@@ -499,15 +567,14 @@ extern "C" int gh_layernorm_bwd_dx(const void* dy, const gh_rows_view* dyv, cons
   const RowMap xm = mk(xv->rows_per_batch, xv->batch_stride, xv->row_stride);
   const RowMap dxm = mk(dxv->rows_per_batch, dxv->batch_stride, dxv->row_stride);
   const RowMap drm = dres ? mk(drv->rows_per_batch, drv->batch_stride, drv->row_stride) : dxm;
-  const int grid = (rows + 7) / 8;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define GH_LNB(V)                                                                                                \
-  ln_bwd_dx_kernel<V><<<grid, 256, 0, s>>>(static_cast<const bf16*>(dy), dym, static_cast<const bf16*>(x), xm, rows, \
-                                           C, mean, rstd, weight, static_cast<const bf16*>(scale), mod_ld,         \
-                                           static_cast<const bf16*>(dres), drm, static_cast<bf16*>(dx), dxm)
-  if (C <= 1024) GH_LNB(4);
-  else if (C <= 2048) GH_LNB(8);
-  else GH_LNB(16);
+#define GH_LNB(V, W)                                                                                               \
+  ln_bwd_dx_kernel<V, W><<<(rows + 8 / W - 1) / (8 / W), 256, 0, s>>>(                                              \
+      static_cast<const bf16*>(dy), dym, static_cast<const bf16*>(x), xm, rows, C, mean, rstd, weight,             \
+      static_cast<const bf16*>(scale), mod_ld, static_cast<const bf16*>(dres), drm, static_cast<bf16*>(dx), dxm)
+  if (C <= 1024) GH_LNB(4, 1);
+  else if (C <= 2048) GH_LNB(8, 1);
+  else GH_LNB(8, 2);
 #undef GH_LNB
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
@@ -527,15 +594,19 @@ static int launch_col_reduce(int mode, const void* dy, const gh_rows_view* dyv, 
   const RowMap dum = du ? mk(duv->rows_per_batch, duv->batch_stride, duv->row_stride) : dym;
   const int threads = (C / 8) < 512 ? ((C / 8 + 31) / 32 * 32) : 512;
   const int gz = (C / 8 + threads - 1) / threads;
-  // enough row-chunks to fill the machine, but >= 16 rows per CTA to amortise the atomics
-  int rows_per_cta = 16;
-  while (static_cast<int64_t>((dym.rpb + rows_per_cta - 1) / rows_per_cta) * batches * gz > 4L * num_sms() &&
-         rows_per_cta < 256)
+  int ny = 512 / threads;                 // row lanes per CTA (narrow rows: several rows side by side)
+  if (ny < 1) ny = 1;
+  // about two 512-thread CTAs per SM, each walking >= 16 rows per lane: one atomic per column and CTA at the end
+  const int64_t want_ctas = 2L * num_sms();
+  int rows_per_cta = 16 * ny;
+  while (static_cast<int64_t>((dym.rpb + rows_per_cta - 1) / rows_per_cta) * batches * gz > want_ctas && rows_per_cta < 8192)
     rows_per_cta *= 2;
   dim3 grid((dym.rpb + rows_per_cta - 1) / rows_per_cta, batches, gz);
+  dim3 block(threads, ny);
+  const size_t smem = ny > 1 ? static_cast<size_t>(ny) * threads * 16 * sizeof(float) : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define GH_CR(M)                                                                                                   \
-  col_reduce_kernel<M><<<grid, threads, 0, s>>>(static_cast<const bf16*>(dy), dym, static_cast<const bf16*>(x), xm, C, \
+  col_reduce_kernel<M><<<grid, block, smem, s>>>(static_cast<const bf16*>(dy), dym, static_cast<const bf16*>(x), xm, C, \
                                                 mean, rstd, static_cast<const bf16*>(gate), gate_ld,                  \
                                                 static_cast<bf16*>(du), dum, acc0, acc1, acc_ld, rows_per_cta)
   if (mode == 0) GH_CR(0);

@@ -510,6 +510,17 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=N
     _count()
 
 
+def euler_cfg_step(x: torch.Tensor, pred: torch.Tensor, neg_pred: torch.Tensor | None, dt: float, true_gs: float) -> None:
+    """x += dt * (neg + true_gs * (pred - neg) | pred), bf16, in place (one Euler step of the flow sampler)."""
+    _ensure(x)
+    assert x.dtype == BF16 and pred.dtype == BF16 and x.is_contiguous() and pred.is_contiguous() and x.numel() == pred.numel()
+    if neg_pred is not None:
+        assert neg_pred.dtype == BF16 and neg_pred.is_contiguous() and neg_pred.numel() == x.numel()
+    check(_lib.lib().gh_euler_cfg_step(x.data_ptr(), pred.data_ptr(), _p(neg_pred), float(dt), float(true_gs), x.numel(),
+                                       _stream()))
+    _count()
+
+
 def dropout_fwd(x: torch.Tensor, p: float, seed: int, offset: int) -> torch.Tensor:
     """bf16 inverted dropout with a counter-based mask (seed, offset): see gh_dropout_fwd."""
     _ensure(x)

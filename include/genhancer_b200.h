@@ -193,6 +193,12 @@ int gh_act_bwd(const void* dy, const void* x, void* dx, int64_t numel, int32_t a
 int gh_accum_cast(const float* src, void* dst, int32_t dst_dtype, int64_t numel, float scale, int32_t accumulate,
                   void* stream);
 
+/* One Euler step of the flow sampler, classifier-free-guidance mix fused (src/flux/sampling.py:129-146):
+ *   v = neg_pred ? neg_pred + true_gs * (pred - neg_pred) : pred ;  x += dt * v     (dt = t_prev - t_curr)
+ * bf16, in place on x; neg_pred may be NULL.  numel % 4 == 0. */
+int gh_euler_cfg_step(void* x_bf16, const void* pred_bf16, const void* neg_pred_bf16, float dt, float true_gs,
+                      int64_t numel, void* stream);
+
 /* Batched strided cast-copy: dst = scale * src (+ dst) for a DEVICE-resident table of small matrices, one launch.
  * Logical row (column) i of a matrix lives at storage row (column) (i / group) * pitch + i % group when group > 0
  * (heads of 72 / 80 features stored in 128-wide slots for the attention kernels), else at i.  Used to refresh the bf16 operand

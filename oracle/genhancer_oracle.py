@@ -726,3 +726,41 @@ def stage1_video_step(sd_tower, sd_adapter, sd_dit, sd_ae, cond_frames, target, 
 def lora_merge(w: torch.Tensor, A: torch.Tensor, Bm: torch.Tensor, scaling: float) -> torch.Tensor:
     """peft merge_and_unload: W += scaling * B @ A (R/train_SigLIP_stage2_all.py:307-311)."""
     return w + scaling * (Bm @ A)
+
+
+# --------------------------------------------------------------------------------------
+# flow sampler (R/src/flux/sampling.py)
+# --------------------------------------------------------------------------------------
+
+
+def get_schedule(num_steps: int, image_seq_len: int, base_shift: float = 0.5, max_shift: float = 1.15, shift: bool = True):
+    """R/src/flux/sampling.py:66-94: linspace(1, 0, n+1), shifted by mu(image_seq_len) through
+    t -> e^mu / (e^mu + (1/t - 1))."""
+    ts = torch.linspace(1, 0, num_steps + 1)
+    if shift:
+        m = (max_shift - base_shift) / (4096 - 256)
+        mu = m * image_seq_len + (base_shift - m * 256)
+        ts = math.exp(mu) / (math.exp(mu) + (1 / ts - 1) ** 1.0)
+    return ts.tolist()
+
+
+def denoise(sd: dict, c: FluxCfg, img, img_ids, txt, txt_ids, vec, neg_txt, neg_txt_ids, neg_vec, timesteps, guidance=4.0,
+            true_gs=1.0, timestep_to_start_cfg=0):
+    """R/src/flux/sampling.py:97-150: Euler steps x += (t_prev - t_curr) * v with the true-CFG mix
+    v = neg + true_gs * (pred - neg) from step `timestep_to_start_cfg` on."""
+    g = torch.full((img.shape[0],), guidance, dtype=img.dtype)
+    for i, (tc, tp) in enumerate(zip(timesteps[:-1], timesteps[1:])):
+        tv = torch.full((img.shape[0],), tc, dtype=img.dtype)
+        pred = flux_forward(sd, c, img, img_ids, txt, txt_ids, tv, vec, g)
+        if i >= timestep_to_start_cfg:
+            neg = flux_forward(sd, c, img, img_ids, neg_txt, neg_txt_ids, tv, neg_vec, g)
+            pred = neg + true_gs * (pred - neg)
+        img = img + (tp - tc) * pred
+    return img
+
+
+def unpack(x: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """R/src/flux/sampling.py:234-242: b (h w) (c ph pw) -> b c (h ph) (w pw)."""
+    h, w = math.ceil(height / 16), math.ceil(width / 16)
+    b, _, d = x.shape
+    return x.view(b, h, w, d // 4, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(b, d // 4, 2 * h, 2 * w)

@@ -316,6 +316,43 @@ def golden_flux(name: str, n_txt: int, seed=31, video_ids=False):
                os.path.join(GOLD, f"flux_{name}.pt"))
 
 
+def golden_sampler(seed=71):
+    """The reference's own sampler (src/flux/sampling.py) driving the reference's Flux: schedule, 4 Euler steps with the
+    true-CFG branch switched on from step 1, unpack."""
+    import src.flux.sampling as RS  # noqa: E402  (reference)
+    print("[sampler]")
+    fc = O.FluxCfg(vec_in_dim=32, context_in_dim=48, hidden_size=256, num_heads=2, depth=1, depth_single_blocks=2)
+    dit = ref_flux(fc)
+    ks = O.flux_key_shapes(fc)
+    sd = O.synth_state_dict(ks, seed)
+    dit.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed)
+    B, height, width = 2, 64, 96
+    noise = RS.get_noise(B, height, width, torch.device("cpu"), torch.float32, seed)
+    h2, w2 = noise.shape[2] // 2, noise.shape[3] // 2
+    img = rearrange(noise, "b c (h ph) (w pw) -> b (h w) (c ph pw)", ph=2, pw=2)
+    n_txt = 3
+    txt, neg_txt = torch.randn(B, n_txt, 48, generator=g), torch.randn(B, n_txt, 48, generator=g)
+    vec, neg_vec = torch.randn(B, 32, generator=g), torch.randn(B, 32, generator=g)
+    img_ids, txt_ids = O.make_img_ids(B, h2, w2), torch.zeros(B, n_txt, 3)
+    sched = RS.get_schedule(4, img.shape[1], shift=True)
+    sched_plain = RS.get_schedule(7, 1024, shift=False)
+    sched_big = RS.get_schedule(25, 4096)
+    with torch.no_grad():
+        out = RS.denoise(dit, img, img_ids, txt, txt_ids, vec, neg_txt, txt_ids, neg_vec, sched, guidance=4.0, true_gs=2.5,
+                         timestep_to_start_cfg=1)
+        oout = O.denoise(sd, fc, img, img_ids, txt, txt_ids, vec, neg_txt, txt_ids, neg_vec, sched, 4.0, 2.5, 1)
+    close(oout, out, 5e-5, "denoised latent")
+    assert O.get_schedule(4, img.shape[1]) == sched and O.get_schedule(7, 1024, shift=False) == sched_plain
+    assert O.get_schedule(25, 4096) == sched_big
+    un = RS.unpack(out, height, width)
+    assert torch.equal(O.unpack(out, height, width), un)
+    torch.save(dict(kind="sampler", cfg=fc.__dict__, seed=seed, key_shapes=ks, height=height, width=width, noise=noise,
+                    img=img, txt=txt, neg_txt=neg_txt, vec=vec, neg_vec=neg_vec, img_ids=img_ids, txt_ids=txt_ids,
+                    schedule=sched, schedule_plain=sched_plain, schedule_big=sched_big, true_gs=2.5, start_cfg=1,
+                    denoised=out, unpacked=un), os.path.join(GOLD, "sampler_small.pt"))
+
+
 def golden_step_small(seed=41):
     """A whole image-mode stage-1 micro-step with every component at reduced size, through the reference's
     own prepare_clip / Flux / AutoEncoder / OpenAICLIP code, vs oracle.stage1_image_step."""
@@ -543,7 +580,7 @@ def golden_cfg1_full(seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="", help="comma-separated subset: tower,lora,ae,flux,step,video")
+    ap.add_argument("--only", default="", help="comma-separated subset: tower,lora,ae,flux,sampler,step,video")
     ap.add_argument("--full", action="store_true", help="also run BASELINE config 1 at full size (~1-2 min, ~12 GB)")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -561,6 +598,8 @@ def main():
     if want("flux"):
         golden_flux("img", n_txt=1)
         golden_flux("video", n_txt=8, video_ids=True)
+    if want("sampler"):
+        golden_sampler()
     if want("step"):
         golden_step_small()
     if want("video"):

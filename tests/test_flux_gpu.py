@@ -77,3 +77,37 @@ def test_flux_grad_accumulation_doubles():
     run()
     for k, p in dit.named_parameters():
         assert rel_err(p.grad.float(), 2 * g1[k]) < 2e-2, k
+
+
+def test_sampler_denoise_matches_reference():
+    """src/flux/sampling.py::denoise (Euler steps + true-CFG mix) on the fused engine vs the reference's sampler driving
+    the reference's Flux (fp32 on CPU); bf16 over 4 steps x 2 DiT evaluations."""
+    from genhancer_b200.flux import sampling as S
+    from genhancer_b200.flux.model import Flux, FluxParams
+    from oracle import genhancer_oracle as O
+    fx = load_golden("sampler_small.pt")
+    fc = dict(fx["cfg"])
+    fc["axes_dim"] = list(fc["axes_dim"])
+    dit = Flux(FluxParams(**fc))
+    dit.load_state_dict(O.synth_state_dict(fx["key_shapes"], fx["seed"]), strict=True)
+    dit = dit.to("cuda").to(torch.bfloat16)
+    c = lambda k: fx[k].to("cuda")
+    out = S.denoise(dit, c("img"), c("img_ids"), c("txt").to(torch.bfloat16), c("txt_ids"), c("vec").to(torch.bfloat16),
+                    c("neg_txt").to(torch.bfloat16), c("txt_ids"), c("neg_vec").to(torch.bfloat16), fx["schedule"],
+                    guidance=4.0, true_gs=fx["true_gs"], timestep_to_start_cfg=fx["start_cfg"])
+    assert out.dtype == torch.float32 and out.shape == fx["denoised"].shape
+    assert cosine(out, fx["denoised"]) >= 0.999
+    assert rel_err(out, fx["denoised"]) < 4e-2
+    img = S.unpack(out, fx["height"], fx["width"])
+    assert img.shape == fx["unpacked"].shape
+    # Euler / CFG kernel against torch on the same bf16 operands
+    from genhancer_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x, p, n = (torch.randn(2, 24, 64, device="cuda", generator=g).to(torch.bfloat16) for _ in range(3))
+    ref = x + (-0.25) * (n + 2.5 * (p - n))
+    y = x.clone()
+    K.euler_cfg_step(y, p, n, -0.25, 2.5)
+    assert torch.equal(y, ref)
+    y = x.clone()
+    K.euler_cfg_step(y, p, None, -0.25, 1.0)
+    assert torch.equal(y, x + (-0.25) * p)

@@ -1,6 +1,7 @@
 """CPU: the oracle (oracle/genhancer_oracle.py) against the golden fixtures, which hold outputs of the REFERENCE
 itself (minted by oracle/make_golden.py from /root/reference in the build container).  This is what pins the
 oracle; the GPU tests then compare the CUDA path with the same fixtures."""
+import pytest
 import torch
 import torch.nn.functional as F
 
@@ -159,3 +160,27 @@ def test_oracle_video_step_and_window_builder():
     random.seed(3)
     starts = sorted(random.sample(list(range(0, 11)), k=4))
     assert a[3][:, 0, 0, 0].tolist() == [float(s + 3) for s in starts] and a[5] == 4
+
+
+def test_sampler_schedule_unpack_and_oracle_denoise_match_reference():
+    """Fixture: the reference's src/flux/sampling.py driving the reference's Flux (make_golden.py::golden_sampler)."""
+    from genhancer_b200.flux import sampling as S
+    fx = load_golden("sampler_small.pt")
+    n_img = fx["img"].shape[1]
+    # host-side pieces of the drop-in module: exact
+    assert S.get_schedule(4, n_img, shift=True) == fx["schedule"]
+    assert S.get_schedule(7, 1024, shift=False) == fx["schedule_plain"]
+    assert S.get_schedule(25, 4096) == fx["schedule_big"]
+    assert fx["schedule"][0] == 1.0 and fx["schedule"][-1] == 0.0
+    assert torch.equal(S.get_noise(2, fx["height"], fx["width"], torch.device("cpu"), torch.float32, fx["seed"]), fx["noise"])
+    assert torch.equal(S.unpack(fx["denoised"], fx["height"], fx["width"]), fx["unpacked"])
+    with pytest.raises(NotImplementedError):
+        S.prepare(None, None, fx["img"], "a prompt")
+    # the oracle restatement
+    assert O.get_schedule(4, n_img) == fx["schedule"]
+    assert torch.equal(O.unpack(fx["denoised"], fx["height"], fx["width"]), fx["unpacked"])
+    sd = O.synth_state_dict(fx["key_shapes"], fx["seed"])
+    with torch.no_grad():
+        out = O.denoise(sd, O.FluxCfg(**fx["cfg"]), fx["img"], fx["img_ids"], fx["txt"], fx["txt_ids"], fx["vec"], fx["neg_txt"],
+                        fx["txt_ids"], fx["neg_vec"], fx["schedule"], 4.0, fx["true_gs"], fx["start_cfg"])
+    assert (out - fx["denoised"]).abs().max().item() <= 5e-5 * fx["denoised"].abs().max().item()

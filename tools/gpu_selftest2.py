@@ -282,6 +282,34 @@ def time_attn(B, H, L, D, iters=10):
     say(f"TIME flash_fwd B={B} H={H} L={L} D={D}: {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s | torch SDPA {ms2:.3f} ms {fl / ms2 / 1e9:.0f} TFLOP/s")
 
 
+def time_hbm_kernels():
+    """HBM-bound kernels at the step's sizes: achieved GB/s of algorithmic bytes (inputs rotate over > L2)."""
+    def run(name, fn, nbytes, iters=20):
+        for _ in range(3):
+            fn(0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        say(f"TIME {name}: {ms * 1e3:.1f} us  {nbytes / ms / 1e6:.0f} GB/s")
+    for (B, L, C) in [(32, 442, 3072), (32, 577, 1024)]:
+        xs = [torch.randn(B, L, C, device=dev).to(BF) for _ in range(4)]
+        dys = [torch.randn(B, L, C, device=dev).to(BF) for _ in range(4)]
+        mod = torch.randn(B, 2 * C, device=dev).to(BF)
+        out = torch.empty(B, L, C, device=dev, dtype=BF)
+        n = B * L * C * 2
+        _, mean, rstd = K.layernorm_fwd(xs[0], shift=mod[:, :C], scale=mod[:, C:])
+        run(f"ln_fwd adaln {B}x{L}x{C}", lambda i: K.layernorm_fwd(xs[i % 4], shift=mod[:, :C], scale=mod[:, C:], out=out), 2 * n)
+        run(f"ln_bwd_dx(+dres) {B}x{L}x{C}", lambda i: K.layernorm_bwd_dx(dys[i % 4], xs[i % 4], mean, rstd, scale=mod[:, C:],
+                                                                        dres=dys[(i + 1) % 4], out=out), 4 * n)
+        acc = torch.zeros(C, device=dev)
+        run(f"colsum {B * L}x{C}", lambda i: K.colsum(dys[i % 4].view(-1, C), acc), n)
+
+
 def main():
     say("== selftest2", torch.cuda.get_device_name(0))
     which = sys.argv[1:] or ["ln", "gate", "rope", "misc", "attn", "time"]
@@ -317,6 +345,8 @@ def main():
     if "attnbwd" in which:
         time_attn_bwd(32, 24, 442, 128)
         time_attn_bwd(32, 16, 577, 64)
+    if "hbm" in which:
+        time_hbm_kernels()
     if "time" in which:
         time_attn(32, 24, 442, 128)
         time_attn(32, 16, 577, 64)
