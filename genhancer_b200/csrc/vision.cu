@@ -333,6 +333,40 @@ extern "C" int gh_groupnorm_swish_nhwc(const void* x, void* y, int32_t B, int64_
   return GH_OK;
 }
 
+namespace gh {
+// nearest-neighbour 2x upsample on NHWC bf16 (FLUX decoder Upsample, autoencoder.py:98-106): one thread = 8 channels
+// of one OUTPUT pixel; reads hit L1/L2 (each input vector is read by 4 outputs).  algorithmic bytes / output elem: 0.5 + 2
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H,
+                                                         int W, int C8) {
+  const int64_t n = static_cast<int64_t>(B) * 2 * H * 2 * W * C8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = static_cast<int>(i % C8);
+    int64_t t = i / C8;
+    const int ow = static_cast<int>(t % (2 * W));
+    t /= 2 * W;
+    const int oh = static_cast<int>(t % (2 * H));
+    const int b = static_cast<int>(t / (2 * H));
+    y[i] = __ldg(x + ((static_cast<int64_t>(b) * H + (oh >> 1)) * W + (ow >> 1)) * C8 + c);
+  }
+}
+}  // namespace gh
+
+extern "C" int gh_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  using namespace gh;
+  GH_REQUIRE(x_bf16 && y_bf16, GH_ERR_NULL, "gh_upsample2x_nhwc: NULL pointer");
+  GH_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, GH_ERR_BAD_SHAPE, "gh_upsample2x_nhwc: bad shape (C %% 8 == 0)");
+  GH_REQUIRE(aligned16(x_bf16) && aligned16(y_bf16), GH_ERR_ALIGN, "gh_upsample2x_nhwc: 16B alignment");
+  if (B == 0) return GH_OK;
+  const int64_t n = static_cast<int64_t>(B) * 4 * H * W * (C / 8);
+  const int64_t want = (n + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  upsample2x_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x_bf16), static_cast<uint4*>(y_bf16), B, H, W, C / 8);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
 extern "C" int gh_softmax_rows(const float* s, int64_t ld_in, void* p_bf16, int64_t ld_out, int32_t rows, int32_t n,
                                float scale, void* stream) {
   GH_REQUIRE(s && p_bf16, GH_ERR_NULL, "gh_softmax_rows: NULL pointer");

@@ -70,42 +70,9 @@ class Downsample(nn.Module):  # autoencoder.py:85-95
         self.conv = nn.Conv2d(in_channels, in_channels, 3, 2, 0)
 
 
-class Encoder(nn.Module):
-    """Encoder.forward of autoencoder.py:159-180; returns the [B, 2z, H/8, W/8] moments (fp32, NCHW view)."""
-
-    def __init__(self, resolution: int, in_channels: int, ch: int, ch_mult: list[int], num_res_blocks: int,
-                 z_channels: int):
-        super().__init__()
-        if in_channels != 3:
-            raise NotImplementedError("the sm_100a conv_in gather is written for 3-channel images")
-        self.ch, self.num_resolutions, self.num_res_blocks = ch, len(ch_mult), num_res_blocks
-        self.resolution, self.in_channels, self.z_channels = resolution, in_channels, z_channels
-        self.conv_in = nn.Conv2d(in_channels, ch, 3, 1, 1)
-        in_ch_mult = (1,) + tuple(ch_mult)
-        self.in_ch_mult = in_ch_mult
-        self.down = nn.ModuleList()
-        block_in = ch
-        for lvl in range(self.num_resolutions):
-            block = nn.ModuleList()
-            block_in = ch * in_ch_mult[lvl]
-            block_out = ch * ch_mult[lvl]
-            for _ in range(num_res_blocks):
-                block.append(ResnetBlock(block_in, block_out))
-                block_in = block_out
-            down = nn.Module()
-            down.block = block
-            down.attn = nn.ModuleList()
-            if lvl != self.num_resolutions - 1:
-                down.downsample = Downsample(block_in)
-            self.down.append(down)
-        self.mid = nn.Module()
-        self.mid.block_1 = ResnetBlock(block_in, block_in)
-        self.mid.attn_1 = AttnBlock(block_in)
-        self.mid.block_2 = ResnetBlock(block_in, block_in)
-        self.norm_out = _gn(block_in)
-        self.conv_out = nn.Conv2d(block_in, 2 * z_channels, 3, 1, 1)
-        self._cache = None
-        self._cache_key = None
+class _ConvStack(nn.Module):
+    """What Encoder and Decoder share on the B200 path: cached bf16 conv operands and the ResnetBlock / AttnBlock
+    schedules over the implicit-GEMM conv, GroupNorm and GEMM kernels (NHWC bf16 activations)."""
 
     # ---- cached kernel operands: conv weights as bf16 [Cout, (kh,kw,ci)], fp32 biases / norm affines ----------
     def _prepared(self) -> dict:
@@ -117,9 +84,19 @@ class Encoder(nn.Module):
             if isinstance(m, nn.Conv2d):
                 w = m.weight.detach()
                 o, i, kh, kw = w.shape
-                if name == "conv_in":  # k = (kh*3+kw)*3 + c, padded 27 -> 32 (gh_im2col3x3_c3 layout)
+                if name == "conv_in" and i == 3:  # k = (kh*3+kw)*3 + c, padded 27 -> 32 (gh_im2col3x3_c3 layout)
                     wk = torch.zeros(o, 32, dtype=BF16, device=w.device)
                     wk[:, :27] = w.permute(0, 2, 3, 1).reshape(o, 27).to(BF16)
+                elif name == "conv_in":  # decoder: z channels, F.unfold column order (ci, kh, kw)
+                    wk = w.reshape(o, i * kh * kw).to(BF16).contiguous()
+                elif o % 8 != 0:  # conv_out of the decoder (3 channels): zero rows up to a multiple of 8
+                    o8 = (o + 7) // 8 * 8
+                    wk = torch.zeros(o8, kh * kw * i, dtype=BF16, device=w.device)
+                    wk[:o] = w.permute(0, 2, 3, 1).reshape(o, kh * kw * i).to(BF16)
+                    bb = torch.zeros(o8, dtype=torch.float32, device=w.device)
+                    bb[:o] = m.bias.detach().float()
+                    W[name] = (wk, bb)
+                    continue
                 else:
                     wk = w.permute(0, 2, 3, 1).reshape(o, kh * kw * i).to(BF16).contiguous()
                 W[name] = (wk, m.bias.detach().float().contiguous())
@@ -159,6 +136,51 @@ class Encoder(nn.Module):
                      residual=h.view(-1, C))
         return out.view(B, H, Wd, C)
 
+
+
+class Upsample(nn.Module):  # autoencoder.py:98-106
+    def __init__(self, in_channels: int):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, in_channels, 3, 1, 1)
+
+
+class Encoder(_ConvStack):
+    """Encoder.forward of autoencoder.py:159-180; returns the [B, 2z, H/8, W/8] moments (fp32, NCHW view)."""
+
+    def __init__(self, resolution: int, in_channels: int, ch: int, ch_mult: list[int], num_res_blocks: int,
+                 z_channels: int):
+        super().__init__()
+        if in_channels != 3:
+            raise NotImplementedError("the sm_100a conv_in gather is written for 3-channel images")
+        self.ch, self.num_resolutions, self.num_res_blocks = ch, len(ch_mult), num_res_blocks
+        self.resolution, self.in_channels, self.z_channels = resolution, in_channels, z_channels
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, 1, 1)
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.in_ch_mult = in_ch_mult
+        self.down = nn.ModuleList()
+        block_in = ch
+        for lvl in range(self.num_resolutions):
+            block = nn.ModuleList()
+            block_in = ch * in_ch_mult[lvl]
+            block_out = ch * ch_mult[lvl]
+            for _ in range(num_res_blocks):
+                block.append(ResnetBlock(block_in, block_out))
+                block_in = block_out
+            down = nn.Module()
+            down.block = block
+            down.attn = nn.ModuleList()
+            if lvl != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in)
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(block_in, block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(block_in, block_in)
+        self.norm_out = _gn(block_in)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels, 3, 1, 1)
+        self._cache = None
+        self._cache_key = None
+
     def moments_nhwc(self, img: Tensor, mean: float = 0.0, std: float = 1.0) -> Tensor:
         """img fp32 NCHW; (img - mean) / std is folded into the conv_in gather. -> fp32 [B, H/8, W/8, 2z]."""
         if img.dim() != 4 or img.shape[1] != 3:
@@ -186,6 +208,66 @@ class Encoder(nn.Module):
         return self.moments_nhwc(x).permute(0, 3, 1, 2)
 
 
+class Decoder(_ConvStack):
+    """Decoder.forward of autoencoder.py:236-259 on the sm_100a kernels: z [B, z, h, w] -> image [B, out_ch, 8h, 8w]
+    (fp32, NCHW).  Not on the training path (the reference only uses it for reconstruction demos); SURVEY.md 8f-1."""
+
+    def __init__(self, ch: int, out_ch: int, ch_mult: list[int], num_res_blocks: int, in_channels: int, resolution: int,
+                 z_channels: int):
+        super().__init__()
+        self.ch, self.num_resolutions, self.num_res_blocks = ch, len(ch_mult), num_res_blocks
+        self.resolution, self.in_channels, self.out_ch = resolution, in_channels, out_ch
+        self.ffactor = 2 ** (self.num_resolutions - 1)
+        block_in = ch * ch_mult[self.num_resolutions - 1]
+        curr_res = resolution // 2 ** (self.num_resolutions - 1)
+        self.z_shape = (1, z_channels, curr_res, curr_res)
+        self.conv_in = nn.Conv2d(z_channels, block_in, 3, 1, 1)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(block_in, block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(block_in, block_in)
+        self.up = nn.ModuleList()
+        for lvl in reversed(range(self.num_resolutions)):
+            block = nn.ModuleList()
+            block_out = ch * ch_mult[lvl]
+            for _ in range(num_res_blocks + 1):
+                block.append(ResnetBlock(block_in, block_out))
+                block_in = block_out
+            up = nn.Module()
+            up.block = block
+            up.attn = nn.ModuleList()
+            if lvl != 0:
+                up.upsample = Upsample(block_in)
+            self.up.insert(0, up)  # prepend to get consistent order
+        self.norm_out = _gn(block_in)
+        self.conv_out = nn.Conv2d(block_in, out_ch, 3, 1, 1)
+        self._cache = None
+        self._cache_key = None
+
+    @torch.no_grad()
+    def forward(self, z: Tensor) -> Tensor:
+        if z.dim() != 4 or z.shape[1] != self.conv_in.in_channels:
+            raise ValueError(f"Decoder expects [B,{self.conv_in.in_channels},h,w] latents, got {tuple(z.shape)}")
+        W = self._prepared()
+        B, zc, h0, w0 = z.shape
+        # conv_in has z_channels (16) inputs: below the 64-channel granularity of the implicit-GEMM conv, so its 3x3
+        # patches are unfolded (16*9 = 144 columns of a [B h w, 144] bf16 matrix: 40 KB per image) and fed to the GEMM
+        a = torch.nn.functional.unfold(z.float(), 3, padding=1).transpose(1, 2).reshape(B * h0 * w0, zc * 9).to(BF16).contiguous()
+        h = K.gemm(a, W["conv_in"][0], bias=W["conv_in"][1]).view(B, h0, w0, -1)
+        h = self._res(W, "mid.block_1", self.mid.block_1, h)
+        h = self._attn(W, h)
+        h = self._res(W, "mid.block_2", self.mid.block_2, h)
+        for lvl in reversed(range(self.num_resolutions)):
+            for j, blk in enumerate(self.up[lvl].block):
+                h = self._res(W, f"up.{lvl}.block.{j}", blk, h)
+            if lvl != 0:
+                n = f"up.{lvl}.upsample.conv"
+                h = K.conv2d_nhwc(K.upsample2x_nhwc(h), W[n][0], 3, 3, 1, 1, bias=W[n][1])
+        h = K.groupnorm_swish_nhwc(h, *W["norm_out"])
+        y = K.conv2d_nhwc(h, W["conv_out"][0], 3, 3, 1, 1, bias=W["conv_out"][1], act=ACT_NONE, out_dtype=F32)
+        return y[..., :self.out_ch].permute(0, 3, 1, 2).contiguous()
+
+
 class DiagonalGaussian(nn.Module):  # autoencoder.py:262-274
     def __init__(self, sample: bool = True, chunk_dim: int = 1):
         super().__init__()
@@ -205,14 +287,19 @@ class AutoEncoder(nn.Module):
         self.encoder = Encoder(resolution=params.resolution, in_channels=params.in_channels, ch=params.ch,
                                ch_mult=params.ch_mult, num_res_blocks=params.num_res_blocks,
                                z_channels=params.z_channels)
+        self.decoder = Decoder(resolution=params.resolution, in_channels=params.in_channels, ch=params.ch,
+                               out_ch=params.out_ch, ch_mult=params.ch_mult, num_res_blocks=params.num_res_blocks,
+                               z_channels=params.z_channels)
         self.reg = DiagonalGaussian()
         self.scale_factor = params.scale_factor
         self.shift_factor = params.shift_factor
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        # the decoder is not on the training path: its tensors in FLUX's ae.safetensors are dropped
-        sd = {k: v for k, v in state_dict.items() if not k.startswith("decoder.")}
-        return super().load_state_dict(sd, strict=strict, assign=assign)
+        # the decoder is not on the training path: a checkpoint without `decoder.*` tensors (encoder-only export) loads
+        # under strict=True as well
+        if strict and not any(k.startswith("decoder.") for k in state_dict):
+            state_dict = {**state_dict, **{f"decoder.{k}": v for k, v in self.decoder.state_dict().items()}}
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
 
     @torch.no_grad()
     def encode_patchified(self, img: Tensor, mean: float = 0.0, std: float = 1.0, noise: Tensor | None = None) -> Tensor:
@@ -240,8 +327,10 @@ class AutoEncoder(nn.Module):
         h2, w2 = H // 16, Wd // 16
         return x1.view(B, h2, w2, z, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, z, h2 * 2, w2 * 2)
 
+    @torch.no_grad()
     def decode(self, z: Tensor) -> Tensor:
-        raise NotImplementedError("the FLUX decoder is not on GenHancer's training path (SURVEY.md 2.1 #7)")
+        """z [B, z, h, w] -> image [B, out_ch, 8h, 8w] (autoencoder.py:307-309): z / scale_factor + shift_factor."""
+        return self.decoder(z.float() / self.scale_factor + self.shift_factor)
 
     def forward(self, x: Tensor) -> Tensor:
         return self.decode(self.encode(x))

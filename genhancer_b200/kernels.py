@@ -440,6 +440,16 @@ def groupnorm_swish_nhwc(x, weight, bias, eps=1e-6, swish=True):
     return y
 
 
+def upsample2x_nhwc(x: torch.Tensor) -> torch.Tensor:
+    _ensure(x)
+    assert x.dtype == BF16 and x.is_contiguous() and x.dim() == 4
+    B, H, W, Cc = x.shape
+    y = torch.empty(B, 2 * H, 2 * W, Cc, dtype=BF16, device=x.device)
+    check(_lib.lib().gh_upsample2x_nhwc(x.data_ptr(), y.data_ptr(), B, H, W, Cc, _stream()))
+    _count()
+    return y
+
+
 def softmax_rows(s, n, scale, ld_out):
     _ensure(s)
     assert s.dtype == F32 and s.dim() == 2 and s.stride(1) == 1

@@ -300,6 +300,9 @@ int gh_embed_assemble(const void* patch_bf16, const float* cls, const float* pos
 int64_t gh_groupnorm_ws_bytes(int32_t B, int64_t HW);
 int gh_groupnorm_swish_nhwc(const void* x, void* y, int32_t B, int64_t HW, int32_t C, const float* weight,
                             const float* bias, float eps, int32_t swish, void* ws, void* stream);
+/* nearest-neighbour 2x upsample, NHWC bf16 [B,H,W,C] -> [B,2H,2W,C] (FLUX decoder Upsample, autoencoder.py:98-106;
+ * the 3x3 conv that follows is gh_conv2d_nhwc).  C % 8 == 0. */
+int gh_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 /* p[r,:n] = softmax(scale * s[r,:n]) fp32 -> bf16, pad columns zeroed (AE mid AttnBlock, autoencoder.py:37-52). */
 int gh_softmax_rows(const float* s, int64_t ld_in, void* p_bf16, int64_t ld_out, int32_t rows, int32_t n, float scale,
                     void* stream);

@@ -476,6 +476,80 @@ def ae_encode(sd: dict, x: torch.Tensor, c: AECfg, noise: torch.Tensor) -> torch
     return c.scale_factor * (z - c.shift_factor)
 
 
+def _mid_attn(sd, h):  # AttnBlock (autoencoder.py:37-55)
+    y = _gn_swish(h, sd["mid.attn_1.norm.weight"], sd["mid.attn_1.norm.bias"], swish=False)
+    q = F.conv2d(y, sd["mid.attn_1.q.weight"], sd["mid.attn_1.q.bias"])
+    k = F.conv2d(y, sd["mid.attn_1.k.weight"], sd["mid.attn_1.k.bias"])
+    v = F.conv2d(y, sd["mid.attn_1.v.weight"], sd["mid.attn_1.v.bias"])
+    B, C, Hh, Ww = q.shape
+    qf, kf, vf = (t.flatten(2).transpose(1, 2) for t in (q, k, v))
+    a = torch.softmax((qf @ kf.transpose(1, 2)) * (C ** -0.5), dim=-1) @ vf
+    a = a.transpose(1, 2).reshape(B, C, Hh, Ww)
+    return h + F.conv2d(a, sd["mid.attn_1.proj_out.weight"], sd["mid.attn_1.proj_out.bias"])
+
+
+def ae_decoder_key_shapes(c: AECfg, out_ch: int = 3) -> dict:
+    """Names/shapes of AutoEncoder.decoder.state_dict() (R/src/flux/modules/autoencoder.py:183-234)."""
+    ks: dict = {}
+
+    def conv(name, o, i, k):
+        ks[f"{name}.weight"] = (o, i, k, k)
+        ks[f"{name}.bias"] = (o,)
+
+    def gn(name, ch):
+        ks[f"{name}.weight"] = (ch,)
+        ks[f"{name}.bias"] = (ch,)
+
+    def res(name, i, o):
+        gn(f"{name}.norm1", i)
+        conv(f"{name}.conv1", o, i, 3)
+        gn(f"{name}.norm2", o)
+        conv(f"{name}.conv2", o, o, 3)
+        if i != o:
+            conv(f"{name}.nin_shortcut", o, i, 1)
+
+    n_lvl = len(c.ch_mult)
+    block_in = c.ch * c.ch_mult[n_lvl - 1]
+    conv("conv_in", block_in, c.z_channels, 3)
+    res("mid.block_1", block_in, block_in)
+    gn("mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"mid.attn_1.{n}", block_in, block_in, 1)
+    res("mid.block_2", block_in, block_in)
+    for lvl in reversed(range(n_lvl)):
+        block_out = c.ch * c.ch_mult[lvl]
+        for j in range(c.num_res_blocks + 1):
+            res(f"up.{lvl}.block.{j}", block_in, block_out)
+            block_in = block_out
+        if lvl != 0:
+            conv(f"up.{lvl}.upsample.conv", block_in, block_in, 3)
+    gn("norm_out", block_in)
+    conv("conv_out", out_ch, block_in, 3)
+    return ks
+
+
+def ae_decoder_forward(sd: dict, z: torch.Tensor, c: AECfg) -> torch.Tensor:
+    """Decoder.forward (autoencoder.py:236-259): conv_in -> mid -> up levels (num_res_blocks + 1 ResnetBlocks, then
+    nearest 2x Upsample + 3x3 conv, :98-106) -> GroupNorm + swish -> conv_out."""
+    h = F.conv2d(z, sd["conv_in.weight"], sd["conv_in.bias"], padding=1)
+    h = _resnet(sd, "mid.block_1", h)
+    h = _mid_attn(sd, h)
+    h = _resnet(sd, "mid.block_2", h)
+    for lvl in reversed(range(len(c.ch_mult))):
+        for j in range(c.num_res_blocks + 1):
+            h = _resnet(sd, f"up.{lvl}.block.{j}", h)
+        if lvl != 0:
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
+            h = F.conv2d(h, sd[f"up.{lvl}.upsample.conv.weight"], sd[f"up.{lvl}.upsample.conv.bias"], padding=1)
+    h = _gn_swish(h, sd["norm_out.weight"], sd["norm_out.bias"])
+    return F.conv2d(h, sd["conv_out.weight"], sd["conv_out.bias"], padding=1)
+
+
+def ae_decode(sd: dict, z: torch.Tensor, c: AECfg) -> torch.Tensor:
+    """AutoEncoder.decode (autoencoder.py:307-309): z / scale_factor + shift_factor -> decoder."""
+    return ae_decoder_forward(sd, z / c.scale_factor + c.shift_factor, c)
+
+
 # --------------------------------------------------------------------------------------
 # conditioning packer / ids
 # --------------------------------------------------------------------------------------

@@ -237,6 +237,27 @@ def golden_ae(seed=21):
                os.path.join(GOLD, "ae_small.pt"))
 
 
+def golden_ae_decoder(seed=23):
+    """The reference's Decoder (autoencoder.py:183-259) and AutoEncoder.decode on synthetic weights."""
+    print("[ae decoder]")
+    ac = O.AECfg(ch=64)
+    ae = AutoEncoder(AutoEncoderParams(resolution=256, in_channels=3, ch=ac.ch, out_ch=3, ch_mult=list(ac.ch_mult),
+                                       num_res_blocks=2, z_channels=16, scale_factor=ac.scale_factor,
+                                       shift_factor=ac.shift_factor))
+    ks = O.ae_decoder_key_shapes(ac)
+    assert {k: tuple(v.shape) for k, v in ae.decoder.state_dict().items()} == {k: tuple(v) for k, v in ks.items()}
+    sd = O.synth_state_dict(ks, seed)
+    ae.decoder.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(2, 16, 6, 10, generator=g)
+    with torch.no_grad():
+        img = ae.decode(z)
+        oimg = O.ae_decode(sd, z, ac)
+    close(oimg, img, 2e-5, "decoded image")
+    torch.save(dict(kind="ae_decoder", cfg=ac.__dict__, seed=seed, key_shapes=ks, z=z, image=img),
+               os.path.join(GOLD, "ae_decoder_small.pt"))
+
+
 def ref_flux(fc: O.FluxCfg):
     return Flux(FluxParams(in_channels=fc.in_channels, vec_in_dim=fc.vec_in_dim, context_in_dim=fc.context_in_dim,
                            hidden_size=fc.hidden_size, mlp_ratio=fc.mlp_ratio, num_heads=fc.num_heads, depth=fc.depth,
@@ -580,7 +601,7 @@ def golden_cfg1_full(seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="", help="comma-separated subset: tower,lora,ae,flux,sampler,step,video")
+    ap.add_argument("--only", default="", help="comma-separated subset: tower,lora,ae,decoder,flux,sampler,step,video")
     ap.add_argument("--full", action="store_true", help="also run BASELINE config 1 at full size (~1-2 min, ~12 GB)")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -595,6 +616,8 @@ def main():
         golden_tower_lora("siglip_small", O.TowerCfg("siglip", 144, 2, 2, 304, 56, 14, 144, 1e-6, "gelu_tanh"), all_linear=False)
     if want("ae"):
         golden_ae()
+    if want("decoder"):
+        golden_ae_decoder()
     if want("flux"):
         golden_flux("img", n_txt=1)
         golden_flux("video", n_txt=8, video_ids=True)

@@ -184,3 +184,14 @@ def test_sampler_schedule_unpack_and_oracle_denoise_match_reference():
         out = O.denoise(sd, O.FluxCfg(**fx["cfg"]), fx["img"], fx["img_ids"], fx["txt"], fx["txt_ids"], fx["vec"], fx["neg_txt"],
                         fx["txt_ids"], fx["neg_vec"], fx["schedule"], 4.0, fx["true_gs"], fx["start_cfg"])
     assert (out - fx["denoised"]).abs().max().item() <= 5e-5 * fx["denoised"].abs().max().item()
+
+
+def test_oracle_ae_decoder():
+    fx = load_golden("ae_decoder_small.pt")
+    ac = O.AECfg(**fx["cfg"])
+    assert {k: tuple(v) for k, v in O.ae_decoder_key_shapes(ac).items()} == {k: tuple(v) for k, v in fx["key_shapes"].items()}
+    sd = O.synth_state_dict(fx["key_shapes"], fx["seed"])
+    with torch.no_grad():
+        img = O.ae_decode(sd, fx["z"], ac)
+    assert img.shape == fx["image"].shape == (2, 3, 48, 80)
+    assert (img - fx["image"]).abs().max().item() <= 2e-5 * fx["image"].abs().max().item()

@@ -128,3 +128,32 @@ def test_ae_noise_draw_matches_reference_rng_order():
     after_ref = torch.randn(3, device="cuda")
     z2 = ae.encode(x, noise=noise)
     assert torch.equal(z1, z2) and torch.equal(after, after_ref)
+
+
+def test_ae_decoder_matches_reference_and_round_trip_shapes():
+    """Decoder (autoencoder.py:183-259) + AutoEncoder.decode: unfolded conv_in, mid attention, three nearest-2x
+    upsample + conv stages, 3-channel conv_out (zero-padded to 8 output channels for the kernel)."""
+    from genhancer_b200.flux.modules.autoencoder import AutoEncoder, AutoEncoderParams
+    from oracle import genhancer_oracle as O
+    fx = load_golden("ae_decoder_small.pt")
+    ac = dict(fx["cfg"])
+    ae = AutoEncoder(AutoEncoderParams(resolution=256, in_channels=3, ch=ac["ch"], out_ch=3, ch_mult=list(ac["ch_mult"]),
+                                       num_res_blocks=ac["num_res_blocks"], z_channels=ac["z_channels"],
+                                       scale_factor=ac["scale_factor"], shift_factor=ac["shift_factor"]))
+    ae.decoder.load_state_dict(O.synth_state_dict(fx["key_shapes"], fx["seed"]), strict=True)
+    assert sorted(ae.decoder.state_dict()) == sorted(fx["key_shapes"])          # the reference's key names
+    ae = ae.to("cuda")
+    img = ae.decode(fx["z"].to("cuda"))
+    assert img.shape == fx["image"].shape and img.dtype == torch.float32
+    assert cosine(img, fx["image"]) >= 0.999
+    assert rel_err(img, fx["image"]) < 3e-2
+    # upsample kernel: exact
+    from genhancer_b200 import kernels as K
+    x = torch.randn(2, 5, 7, 64, device="cuda").to(torch.bfloat16)
+    ref = x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    assert torch.equal(K.upsample2x_nhwc(x), ref)
+    # encode -> decode keeps the image geometry (random weights: only shapes / finiteness are meaningful)
+    rec = ae.decode(ae.encode(torch.rand(1, 3, 64, 96, device="cuda") * 2 - 1))
+    assert rec.shape == (1, 3, 64, 96) and torch.isfinite(rec).all()
+    with pytest.raises(ValueError):
+        ae.decoder(torch.zeros(1, 8, 4, 4, device="cuda"))
