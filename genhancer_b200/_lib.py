@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("gate", C.c_void_p), ("gate_ld", C.c_int64), ("rows_per_batch", C.c_int32),
         ("residual", C.c_void_p), ("ld_res", C.c_int64), ("res_dtype", C.c_int32),
         ("a2", C.c_void_p), ("lda2", C.c_int64), ("b2", C.c_void_p), ("ldb2", C.c_int64), ("K2", C.c_int32),
+        ("k_splits", C.c_int32),
     ]
 
 

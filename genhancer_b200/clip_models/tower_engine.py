@@ -162,8 +162,10 @@ class LinGroup:
                         dx = K.act_bwd(dx, dx_epi["aux_in"], dx_epi["act"])
                     elif dx_epi:
                         raise NotImplementedError(f"LoRA dropout with dgrad epilogue {sorted(dx_epi)}")
-            K.gemm(du, x2d if xd is None else xd, a_mn=True, b_mn=True, out=self.gA)
-            K.gemm(dy2d, u, a_mn=True, b_mn=True, out=self.gB)
+            # skinny outputs reduced over every token of the batch: split-K, partial products added into the staging
+            # (which is all-zero between backward calls, see TowerEngine._scatter_grads)
+            K.gemm(du, x2d if xd is None else xd, a_mn=True, b_mn=True, out=self.gA, k_splits=-1)
+            K.gemm(dy2d, u, a_mn=True, b_mn=True, out=self.gB, k_splits=-1)
         elif need_dx:
             dx = K.gemm(dy2d, self.w, b_mn=True, **dx_epi)
         if self.gb is not None:

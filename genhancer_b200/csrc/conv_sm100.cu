@@ -93,6 +93,7 @@ extern "C" int gh_conv2d_nhwc(const gh_conv_args* a, void* stream) {
   const int K = a->KH * a->KW * a->Cin;
   int bn = a->Cout >= 256 ? 256 : (a->Cout > 64 ? 128 : 64);
   GemmParams p{};
+  p.k_splits = 1;
   p.prof = gemm_prof_ptr();
   p.cv.B = a->B; p.cv.Ho = a->Ho; p.cv.Wo = a->Wo; p.cv.TW = TW; p.cv.TH = TH;
   p.cv.tiles_w = (a->Wo + TW - 1) / TW;

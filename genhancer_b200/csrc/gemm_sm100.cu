@@ -32,7 +32,7 @@ int gemm_init() {
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap* tm, const GemmParams& p, cudaStream_t stream) {
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int tiles = p.num_m_blocks * p.num_n_blocks * p.k_splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM>
       <<<grid, GemmCfg<BN>::THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
@@ -43,7 +43,7 @@ static int launch(const CUtensorMap* tm, const GemmParams& p, cudaStream_t strea
 // CTA pairs: clusters of 2 CTAs (one TPC), one pair per 256 x BN tile, persistent over the pair-tiles
 template <int BN, bool A_MN, bool B_MN>
 static int launch_pair(const CUtensorMap* tm, const GemmParams& p, cudaStream_t stream) {
-  const int tiles = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
+  const int tiles = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks * p.k_splits;
   const int pairs = num_sms() / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
@@ -188,6 +188,20 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
               (!a->aux_out || (a->ld_aux_out % 8 == 0 && aligned16(a->aux_out))) &&
               (!a->gate || (a->gate_ld % 8 == 0 && aligned16(a->gate))) &&
               (!a->residual || a->res_dtype == GH_F32 || (a->ld_res % 8 == 0 && aligned16(a->residual)));
+  // split-K: skinny fp32 outputs reduced over a long K (LoRA wgrads)
+  p.k_splits = 1;
+  if (a->k_splits != 0) {
+    GH_REQUIRE(a->d_dtype == GH_F32 && a->K2 == 0 && !a->bias && a->act == 0 && !a->act_grad && !a->gate && !a->residual &&
+                   !a->aux_out,
+               GH_ERR_UNSUPPORTED, "gh_gemm_bf16: split-K adds bare partial products into an fp32 D (no epilogue options)");
+    const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+    int s = a->k_splits > 0 ? a->k_splits : num_sms() / (tiles_mn > 0 ? tiles_mn : 1);   // < 0: fill the machine
+    if (s > p.num_k_blocks / 4) s = p.num_k_blocks / 4;                                 // >= 4 k blocks per slice
+    if (s > 64) s = 64;
+    if (s < 1) s = 1;
+    p.k_splits = s;
+    p.ep.atomic = 1;   // also for s == 1: the contract is "D += A B^T"
+  }
   finalize_epilogue(p.ep);
   p.prof = g_gemm_prof;
   if (g_gemm_prof) { static const int dbg = [] { const char* e = getenv("GH_GEMM_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }

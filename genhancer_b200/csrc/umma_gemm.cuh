@@ -42,6 +42,7 @@ struct EpilogueParams {
   int64_t ld_res;
   int res_f32;
   int vec8;  // every epilogue operand allows 16-byte bf16 vectors (N % 8 == 0, leading dimensions % 8 == 0)
+  int atomic;  // fp32 D accumulated with red.global.add (split-K)
   int fast;  // bf16 out = act(alpha*acc + bias) [+ bf16 residual], vec8: the lean path (set by finalize_epilogue)
   int tma;   // lean path through smem tiles + TMA store (tmap_d [, tmap_r] are valid); GEMM mode only
 };
@@ -66,6 +67,10 @@ struct GemmParams {
   // num_k_blocks2 more 64-wide steps that pull from (tmap_a2, tmap_b2); the last of them issues only
   // k2_last_steps of the four 16-deep MMAs (rank 16 -> one MMA, the rest of the box is TMA zero fill).
   int num_k_blocks2, k2_last_steps;
+  // Split-K for skinny outputs (LoRA wgrads: 16..48 x K outputs reduced over all tokens): the tile grid gets a third
+  // axis of k_splits slices of the K loop; every slice ADDS its partial result into the fp32 output with red.add
+  // (the caller zeroes D).  k_splits = 1: off.  Not combined with the second operand pair.
+  int k_splits;
   uint32_t a_stage_tx_bytes;  // bytes TMA deposits for the A tile of one stage
   uint32_t mn_lbo, mn_sbo, mn_kstep;  // MN-major descriptor geometry (bytes); see common.cuh
   EpilogueParams ep;
@@ -230,7 +235,12 @@ __device__ __forceinline__ void slice_finish(const EpilogueParams& ep, const flo
         for (int k = 0; k < 8; ++k) v[k] += r[k];
       }
     }
-    if (ep.d_f32) {
+    if (ep.d_f32 && ep.atomic) {
+      float* dp = static_cast<float*>(ep.d) + row * ep.ldd + gn;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < 4 || hi) atomicAdd(dp + k, v[k]);
+    } else if (ep.d_f32) {
       float* dp = static_cast<float*>(ep.d) + row * ep.ldd + gn;
       *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
       if (hi) *reinterpret_cast<float4*>(dp + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -452,7 +462,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = m_units * p.num_n_blocks;
+  const int tiles_mn = m_units * p.num_n_blocks;
+  const int num_tiles = tiles_mn * p.k_splits;   // tile index = split * tiles_mn + (m, n) index
   const int nkb1 = p.num_k_blocks;
   const int nkb = nkb1 + (MODE == MODE_GEMM ? p.num_k_blocks2 : 0);
 
@@ -495,7 +506,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr int BNL = CTA2 ? BN / 2 : BN;            // B rows this CTA loads
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int m_blk, n_blk;
-      decode_tile(tile, m_units, p.num_n_blocks, m_blk, n_blk);
+      const int split = tile / tiles_mn;
+      decode_tile(tile - split * tiles_mn, m_units, p.num_n_blocks, m_blk, n_blk);
+      const int kb0 = (split * nkb) / p.k_splits, kb1 = ((split + 1) * nkb) / p.k_splits;
       if (CTA2) m_blk = m_blk * 2 + static_cast<int>(rank);
       const int nrow0 = n_blk * BN + static_cast<int>(rank) * BNL;
       int cb = 0, ch0 = 0, cw0 = 0;
@@ -507,7 +520,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         cw0 = (r % p.cv.tiles_w) * p.cv.TW;
       }
       int c_cc = 0, c_kw = 0, c_kh = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         if (p.prof) {
           const long long t0 = clock64();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -597,7 +610,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-      for (int kb = 0; kb < nkb; ++kb) {
+      const int split = tile / tiles_mn;
+      const int kb0 = (split * nkb) / p.k_splits, kb1 = ((split + 1) * nkb) / p.k_splits;
+      for (int kb = kb0; kb < kb1; ++kb) {
         if (p.prof) {
           const long long t0 = clock64();
           mbar_wait(&full_bar[stage], phase);
@@ -612,10 +627,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           auto mma = [&](int k) {
             if (CTA2)
               umma2_ss(d_tmem, umma_desc_at(a_desc_base, sA + k * A_KSTEP), umma_desc_at(b_desc_base, sB + k * B_KSTEP),
-                       idesc, (kb | k) != 0 ? 1u : 0u);
+                       idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
             else
               umma_ss(d_tmem, umma_desc_at(a_desc_base, sA + k * A_KSTEP), umma_desc_at(b_desc_base, sB + k * B_KSTEP),
-                      idesc, (kb | k) != 0 ? 1u : 0u);
+                      idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           };
           if (kb == nkb - 1 && kb >= nkb1) {  // last k block of a folded LoRA pair: only the steps that hold data
             for (int k = 0; k < p.k2_last_steps; ++k) mma(k);
@@ -624,10 +639,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           if (CTA2) {
             umma2_commit(&empty_bar[stage]);                   // the slot is free in BOTH CTAs once these MMAs retire
-            if (kb == nkb - 1) umma2_commit(&tfull_bar[acc]);  // accumulator complete (both CTAs' epilogues)
+            if (kb == kb1 - 1) umma2_commit(&tfull_bar[acc]);  // accumulator complete (both CTAs' epilogues)
           } else {
             umma_commit(&empty_bar[stage]);              // smem slot free once these MMAs retire
-            if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
           }
         }
         __syncwarp();
@@ -672,7 +687,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                        CTA2 ? mapa_u32(smem_u32(&tempty_bar[1]), 0u) : 0u};
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int m_blk, n_blk;
-      decode_tile(tile, m_units, p.num_n_blocks, m_blk, n_blk);
+      decode_tile(tile % tiles_mn, m_units, p.num_n_blocks, m_blk, n_blk);
       if (CTA2) m_blk = m_blk * 2 + static_cast<int>(rank);
       // the 2 output rows this lane touches in every slice of the tile (row index == logical GEMM row)
       int rows[2];

@@ -55,7 +55,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          aux_in: torch.Tensor | None = None, aux_out: torch.Tensor | None = None,
          gate: torch.Tensor | None = None, rows_per_batch: int = 0,
          residual: torch.Tensor | None = None, a2: torch.Tensor | None = None,
-         b2: torch.Tensor | None = None) -> torch.Tensor:
+         b2: torch.Tensor | None = None, k_splits: int = 0) -> torch.Tensor:
     """D[M,N] = epilogue(alpha * (A @ B^T + A2 @ B2^T)).
 
     ``a2`` / ``b2`` (same majors as ``a`` / ``b``, reduction length K2 = the LoRA rank) fold a low-rank branch into
@@ -99,6 +99,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if residual is not None:
         _rowmajor2d(residual, "gemm residual")
         g.residual, g.ld_res, g.res_dtype = residual.data_ptr(), residual.stride(0), _dt(residual)
+    g.k_splits = k_splits   # != 0: out (fp32, zeroed or to be accumulated into by the caller) += A @ B^T, split over K
     K2 = 0
     if a2 is not None:
         _rowmajor2d(a2, "gemm a2")

@@ -98,6 +98,11 @@ typedef struct {
   const void* b2;
   int64_t ldb2;
   int32_t K2;
+  /* Split-K for skinny outputs reduced over a long K (LoRA wgrads dA = du^T x, dB = dy^T u: 16..48 rows or columns,
+   * K = all tokens of the batch): != 0 makes the call D += A B^T on an fp32 D the CALLER HAS ZEROED (or wants
+   * accumulated into), computed by k_splits slices of the K loop that add their partial products with red.add;
+   * < 0 picks the slice count that fills the machine.  No epilogue options, no second operand pair. */
+  int32_t k_splits;
 } gh_gemm_args;
 int gh_gemm_bf16(const gh_gemm_args* args, void* stream);
 /* Bring-up aid: when device_buf (int64 [8 * #SMs]) is non-NULL, every following gh_gemm_bf16 launch writes per-CTA

@@ -245,6 +245,18 @@ def main():
         gemm_case(432, 16, 392, a_mn=True, b_mn=True, f32=True)
         gemm_case(392, 16, 1152)
         gemm_case(392, 48, 432, b_mn=True)
+        # split-K: D (fp32, pre-filled) += A^T B over k slices (LoRA wgrads)
+        for (M, N, Kd) in [(16, 1152, 23328), (48, 1152, 5000), (4304, 16, 23328), (6144, 48, 3000), (304, 520, 777)]:
+            g = torch.Generator(device="cuda").manual_seed(4)
+            A = torch.randn(Kd, M, device="cuda", generator=g).to(torch.bfloat16)
+            B = torch.randn(Kd, N, device="cuda", generator=g).to(torch.bfloat16)
+            base = torch.randn(M, N, device="cuda", generator=g)
+            out = base.clone()
+            K.gemm(A, B, a_mn=True, b_mn=True, out=out, k_splits=-1)
+            torch.cuda.synchronize()
+            ref = base + A.float().t() @ B.float()
+            e = relerr(out, ref)
+            say("PASS" if e < 2e-3 else "FAIL", f"split-K wgrad M={M} N={N} K={Kd}", f"relerr={e:.3e}")
         copy_table_cases()
     if "time" in which:
         time_gemm(4096, 4096, 4096)
