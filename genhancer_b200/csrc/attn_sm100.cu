@@ -341,7 +341,7 @@ struct AttnBwdKVCfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(288, 1)
 flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                      const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                      const AttnBwdParams p) {
@@ -370,11 +370,13 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
   const int h = blockIdx.y, b = blockIdx.z;
   const int nq = (p.Lq + 63) / 64;
 
-  if (warp == 4 && lane == 0) {
+  // warps 0..7: compute (warp w and w + 4 share TMEM lane quadrant w % 4; each thread owns HALF of its row's 64
+  // columns -- two warps per scheduler instead of one: the element-wise part was latency-bound); warp 8: control
+  if (warp == 8 && lane == 0) {
     mbar_init(bar_kv, 1);
     for (int i = 0; i < NQ; ++i) mbar_init(&bar_qd[i], 1);
     mbar_init(&bar_sd[0], 1); mbar_init(&bar_sd[1], 1);
-    mbar_init(bar_pd, 4);
+    mbar_init(bar_pd, 8);
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
@@ -384,7 +386,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     {  // control warp: see flash_fwd_kernel (all lanes run the flow, one elected lane issues)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_a = umma_idesc_bf16(128, D, false, true);
@@ -463,25 +465,25 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
     }
     __syncwarp();
   } else {
-    const int row = threadIdx.x;  // key row within the block == TMEM lane
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const int row = threadIdx.x & 127;  // key row within the block == TMEM lane
+    const int half = threadIdx.x >> 7;  // which 32 of the 64 query columns this thread owns
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int64_t stat_base = (static_cast<int64_t>(b) * p.H + h) * p.Lq;
     for (int i = 0; i < nq; ++i) {
       // stage lse / delta of this query block (threads 0-63 -> lse, 64-127 -> delta)
       float* st = sStat + (i & 1) * 128;
-      {
+      if (threadIdx.x < 128) {
         const int c = row & 63;
         const int ql = i * 64 + c;
         const float v = ql < p.Lq ? (row < 64 ? p.lse2[stat_base + ql] : p.delta[stat_base + ql]) : 0.f;
         st[row] = v;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&bar_sd[i & 1], (i >> 1) & 1);
       tc_fence_after();
       const int q_left = p.Lq - i * 64;
-      uint32_t pt[32], dst[32];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      uint32_t pt[16], dst[16];
+      {
         uint32_t s[32], dp[32];
         tmem_ld_32x32(t_lane + (i & 1) * 128 + half * 32, s);
         tmem_ld_32x32(t_lane + (i & 1) * 128 + 64 + half * 32, dp);
@@ -495,15 +497,15 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
           if (cc + 1 >= q_left) p1 = 0.f;
           const float d0 = p0 * (__uint_as_float(dp[c]) - st[64 + cc]) * p.scale;
           const float d1 = p1 * (__uint_as_float(dp[c + 1]) - st[64 + cc + 1]) * p.scale;
-          pt[cc >> 1] = pack_bf16x2(p0, p1);
-          dst[cc >> 1] = pack_bf16x2(d0, d1);
+          pt[c >> 1] = pack_bf16x2(p0, p1);
+          dst[c >> 1] = pack_bf16x2(d0, d1);
         }
       }
       if (i > 0) mbar_wait(bar_acc, (i - 1) & 1);  // previous dV/dK MMAs no longer read sPT/sDST
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        st_sw128(sPT, row, c, make_uint4(pt[4 * c], pt[4 * c + 1], pt[4 * c + 2], pt[4 * c + 3]));
-        st_sw128(sDST, row, c, make_uint4(dst[4 * c], dst[4 * c + 1], dst[4 * c + 2], dst[4 * c + 3]));
+      for (int c = 0; c < 4; ++c) {
+        st_sw128(sPT, row, half * 4 + c, make_uint4(pt[4 * c], pt[4 * c + 1], pt[4 * c + 2], pt[4 * c + 3]));
+        st_sw128(sDST, row, half * 4 + c, make_uint4(dst[4 * c], dst[4 * c + 1], dst[4 * c + 2], dst[4 * c + 3]));
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -518,7 +520,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
       bf16* dstp = which ? p.dk + b * p.dk_bs + h * p.dk_hs + static_cast<int64_t>(kl) * p.dk_rs
                          : p.dv + b * p.dv_bs + h * p.dv_hs + static_cast<int64_t>(kl) * p.dv_rs;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = half; c < D / 32; c += 2) {   // the two threads of a row take alternate 32-column chunks
         uint32_t o[32];
         tmem_ld_32x32(t_lane + (which ? Cfg::TM_DK : Cfg::TM_DV) + c * 32, o);
         tmem_ld_wait();
@@ -558,7 +560,7 @@ struct AttnBwdQCfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(288, 1)
 flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                     const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                     const AttnBwdParams p) {
@@ -585,11 +587,13 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int h = blockIdx.y, b = blockIdx.z;
   const int nkv = (p.Lk + 63) / 64;
 
-  if (warp == 4 && lane == 0) {
+  // warps 0..7: compute (warp w and w + 4 share TMEM lane quadrant w % 4; each thread owns HALF of its row's 64
+  // columns -- two warps per scheduler instead of one: the element-wise part was latency-bound); warp 8: control
+  if (warp == 8 && lane == 0) {
     mbar_init(bar_q, 1);
     for (int i = 0; i < NK; ++i) mbar_init(&bar_kv[i], 1);
     mbar_init(&bar_sd[0], 1); mbar_init(&bar_sd[1], 1);
-    mbar_init(bar_pd, 4);
+    mbar_init(bar_pd, 8);
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
@@ -599,7 +603,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     {  // control warp: see flash_fwd_kernel (all lanes run the flow, one elected lane issues)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_a = umma_idesc_bf16(128, D, false, true);
@@ -672,8 +676,9 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
     __syncwarp();
   } else {
-    const int row = threadIdx.x;
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const int row = threadIdx.x & 127;
+    const int half = threadIdx.x >> 7;  // which 32 of the 64 key columns this thread owns
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int ql = q0 + row;
     const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + ql;
     const float lse = ql < p.Lq ? p.lse2[stat] : 0.f;
@@ -682,9 +687,8 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_wait(&bar_sd[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const int kv_left = p.Lk - j * 64;
-      uint32_t ds[32];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      uint32_t ds[16];
+      {
         uint32_t s[32], dp[32];
         tmem_ld_32x32(t_lane + (j & 1) * 128 + half * 32, s);
         tmem_ld_32x32(t_lane + (j & 1) * 128 + 64 + half * 32, dp);
@@ -696,14 +700,14 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           float p1 = exp2f(__uint_as_float(s[c + 1]) * p.scale_log2 - lse);
           if (cc >= kv_left) p0 = 0.f;
           if (cc + 1 >= kv_left) p1 = 0.f;
-          ds[cc >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dl) * p.scale,
-                                    p1 * (__uint_as_float(dp[c + 1]) - dl) * p.scale);
+          ds[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dl) * p.scale,
+                                   p1 * (__uint_as_float(dp[c + 1]) - dl) * p.scale);
         }
       }
       if (j > 0) mbar_wait(bar_acc, (j - 1) & 1);
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        st_sw128(sDS, row, c, make_uint4(ds[4 * c], ds[4 * c + 1], ds[4 * c + 2], ds[4 * c + 3]));
+      for (int c = 0; c < 4; ++c)
+        st_sw128(sDS, row, half * 4 + c, make_uint4(ds[4 * c], ds[4 * c + 1], ds[4 * c + 2], ds[4 * c + 3]));
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -713,7 +717,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tc_fence_after();
     bf16* dstp = p.dq + b * p.dq_bs + h * p.dq_hs + static_cast<int64_t>(ql) * p.dq_rs;
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = half; c < D / 32; c += 2) {
       uint32_t o[32];
       tmem_ld_32x32(t_lane + Cfg::TM_DQ + c * 32, o);
       tmem_ld_wait();
@@ -859,9 +863,9 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
     if (int e = make_qkv_map(&mdo, &dot, B, H, Lq, D, 64)) return e;
     dim3 grid((Lk + 127) / 128, H, B);
     if (D == 64)
-      flash_bwd_dkv_kernel<64><<<grid, 160, AttnBwdKVCfg<64>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, p);
+      flash_bwd_dkv_kernel<64><<<grid, 288, AttnBwdKVCfg<64>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, p);
     else
-      flash_bwd_dkv_kernel<128><<<grid, 160, AttnBwdKVCfg<128>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, p);
+      flash_bwd_dkv_kernel<128><<<grid, 288, AttnBwdKVCfg<128>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, p);
     GH_CHECK_CUDA(cudaGetLastError());
   }
   {
@@ -872,9 +876,9 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
     if (int e = make_qkv_map(&mdo, &dot, B, H, Lq, D, 128)) return e;
     dim3 grid((Lq + 127) / 128, H, B);
     if (D == 64)
-      flash_bwd_dq_kernel<64><<<grid, 160, AttnBwdQCfg<64>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, p);
+      flash_bwd_dq_kernel<64><<<grid, 288, AttnBwdQCfg<64>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, p);
     else
-      flash_bwd_dq_kernel<128><<<grid, 160, AttnBwdQCfg<128>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, p);
+      flash_bwd_dq_kernel<128><<<grid, 288, AttnBwdQCfg<128>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, p);
     GH_CHECK_CUDA(cudaGetLastError());
   }
   return GH_OK;
