@@ -185,13 +185,29 @@ def run_ours(args):
     reducer = GradReducer(groups, engine_modules=[dit]) if world > 1 else None
     gscale = reducer.grad_scale if reducer else 1.0
 
+    # Data parallel: the exchange + update of step n run inside step n+1, right before its first trainable kernel
+    # (train_step.Stage1ImageStep.__call__: before_trainable) -- the all-reduce tail hides under the frozen AE / tower
+    # forward.  Per timed step: one forward, one backward, one complete exchange, one optimizer update.
+    pending = {"n": 0}
+
+    def flush():
+        if pending["n"]:
+            reducer.wait()
+            opt.step(gscale)
+            opt.zero_grad()
+            pending["n"] = 0
+
     def train_step(img):
-        loss = step(img)
+        if reducer is None:
+            loss = step(img)
+            loss.backward()
+            opt.step(gscale)
+            opt.zero_grad()
+            return loss
+        loss = step(img, before_trainable=flush)
         loss.backward()
-        if reducer is not None:
-            reducer.finish()
-        opt.step(gscale)
-        opt.zero_grad()
+        reducer.issue_rest()        # the fp32 projector group: issued now, waited for in the next step's flush()
+        pending["n"] = 1
         return loss
 
     # synthetic data: per-step seeded batches (SURVEY.md 8d cfg 2), a pool resident in HBM / pinned host memory
@@ -229,13 +245,16 @@ def run_ours(args):
     # ---- device-resident arm -------------------------------------------------------------------------------
     for i in range(args.warmup):
         train_step(dev_batches[i % pool])
-    # forward + backward as ONE CUDA graph (genhancer_b200/graph.py); optimizer + zero_grad stay outside.  With
-    # data parallelism the backward issues NCCL buckets from Python hooks: eager there.
+    # forward + backward (+ the overlapped gradient exchange) as ONE CUDA graph (genhancer_b200/graph.py); optimizer
+    # + zero_grad stay outside.  Data parallel: the NCCL all-reduces the backward schedule issues per finished block
+    # are captured as a forked branch of the graph, joined by reducer.finish() at its end.
     graphed = None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         from genhancer_b200.graph import GraphedMicroStep
+        flush()
         opt.zero_grad()
-        graphed = GraphedMicroStep(step, dev_batches[0], prepare=opt.zero_grad)
+        graphed = GraphedMicroStep(step, dev_batches[0], prepare=opt.zero_grad,
+                                   after_backward=reducer.finish if reducer is not None else None)
 
         def train_step(img):  # noqa: F811  (same contract as the eager step above)
             loss = graphed(img)
@@ -265,6 +284,8 @@ def run_ours(args):
 
     # ---- roofline pass: the same step EAGER with CUDA events around every tcgen05 GEMM / conv launch (events cannot
     # sit inside a graph); its own step time is the denominator of share_of_step ---------------------------------
+    flush()   # (data parallel: the last timed step's deferred exchange + update)
+
     def eager_step(img):
         loss = step(img)
         loss.backward()
@@ -302,7 +323,8 @@ def run_ours(args):
         "config": {"workload": f"OpenAI CLIP ViT-L/14-{S} stage-1 step (AE encode + tower + projectors + DiT fwd/bwd + "
                                f"velocity-MSE + clip + AdamW), batch {B}/GPU, random-init weights",
                    "global_batch": B * world, "image_size": S, "parallelism": f"dp{world}",
-                   "execution": "forward+backward replayed as one CUDA graph, fused AdamW outside" if graphed else "eager launches",
+                   "execution": ("forward+backward" + ("+overlapped NCCL gradient all-reduce" if world > 1 else "")
+                                 + " replayed as one CUDA graph, fused AdamW outside") if graphed else "eager launches",
                    "l2": "per-step working set (weights 3.9 GB + activations) is far larger than the 126 MB L2; "
                          "4 distinct input batches rotate"},
         "mfu": {"flops_per_image": FLOPS_PER_IMAGE,
@@ -331,7 +353,16 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
+        # NCCL will not tear a communicator down while a captured graph still holds its kernels: drop the graph
+        # first; a watchdog ends the process (exit 0, the line is printed) if the teardown stalls anyway.
+        sys.stdout.flush()
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        if graphed is not None:
+            graphed.graph.reset()
+            graphed = None
+        barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------------------

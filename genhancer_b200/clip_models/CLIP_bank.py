@@ -54,10 +54,13 @@ class _Wrapper(nn.Module):
             return vt.project(self.model, out.pooler_output)
         return out.pooler_output
 
+    def project(self, class_token):
+        """-> (projection_clip, projection_t5[:, None, :]): the two trainable MLP projectors (CLIP_bank.py:36-39)."""
+        return run_projector(self.project_clip, class_token), run_projector(self.project_t5, class_token[:, None, :])
+
     def forward(self, images, _norm=None):
         class_token = self.class_token(images, _norm)
-        projection_clip = run_projector(self.project_clip, class_token)
-        projection_t5 = run_projector(self.project_t5, class_token[:, None, :])
+        projection_clip, projection_t5 = self.project(class_token)
         return class_token, projection_clip, projection_t5
 
 

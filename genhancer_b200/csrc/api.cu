@@ -1,4 +1,5 @@
 // genhancer_b200 -- C-ABI plumbing: error reporting, init, TMA descriptor encoding.
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -33,6 +34,8 @@ PFN_encodeTiled get_encode_tiled() {
   return g_encode;
 }
 
+static int g_sm_budget = 0;   // gh_set_sm_budget: SMs the persistent grids may fill (0 = all)
+
 int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0, n = 0;
@@ -41,7 +44,12 @@ int num_sms() {
       g_num_sms = n;
     else
       g_num_sms = 148;
+    if (const char* e = getenv("GH_SM_BUDGET")) {
+      const int b = atoi(e);
+      if (b > 0) g_sm_budget = b;
+    }
   }
+  if (g_sm_budget > 0 && g_sm_budget < g_num_sms) return g_sm_budget & ~1;   // even: CTA pairs need whole TPCs
   return g_num_sms;
 }
 
@@ -73,6 +81,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 extern "C" const char* gh_last_error(void) { return gh::g_last_error.c_str(); }
 extern "C" int gh_version(void) { return 100; }
+
+extern "C" int gh_set_sm_budget(int sms) {
+  gh::g_sm_budget = sms > 0 ? sms : 0;
+  return GH_OK;
+}
 
 extern "C" int gh_init(int device) {
   using namespace gh;

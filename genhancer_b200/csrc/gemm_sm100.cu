@@ -32,8 +32,8 @@ int gemm_init() {
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap* tm, const GemmParams& p, cudaStream_t stream) {
-  const int tiles = p.num_m_blocks * p.num_n_blocks * p.k_splits;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const long tiles = static_cast<long>(p.num_m_blocks) * p.num_n_blocks * p.k_splits * p.batch;
+  const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
   umma_gemm_kernel<BN, A_MN, B_MN, MODE_GEMM>
       <<<grid, GemmCfg<BN>::THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   GH_CHECK_CUDA(cudaGetLastError());
@@ -43,10 +43,10 @@ static int launch(const CUtensorMap* tm, const GemmParams& p, cudaStream_t strea
 // CTA pairs: clusters of 2 CTAs (one TPC), one pair per 256 x BN tile, persistent over the pair-tiles
 template <int BN, bool A_MN, bool B_MN>
 static int launch_pair(const CUtensorMap* tm, const GemmParams& p, cudaStream_t stream) {
-  const int tiles = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks * p.k_splits;
+  const long tiles = static_cast<long>((p.num_m_blocks + 1) / 2) * p.num_n_blocks * p.k_splits * p.batch;
   const int pairs = num_sms() / 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  cfg.gridDim = dim3(2 * (tiles < pairs ? static_cast<int>(tiles) : pairs));
   cfg.blockDim = dim3(GemmCfg<BN, true>::THREADS);
   cfg.dynamicSmemBytes = GemmCfg<BN, true>::SMEM_BYTES;
   cfg.stream = stream;
@@ -78,21 +78,23 @@ static int dispatch_major(bool pair, bool a_mn, bool b_mn, const CUtensorMap* tm
 }
 
 // tensor maps of one (A, B) operand pair with reduction length K
+// (batched: a_extra / b_extra = (batch - 1) * batch offset, the rows the flat tensor holds beyond one problem)
 static int make_pair(CUtensorMap* ta, CUtensorMap* tb, const void* a, int64_t lda, bool a_mn, const void* b, int64_t ldb,
-                     bool b_mn, int M, int N, int K, int bn /* B rows per TMA box */) {
+                     bool b_mn, int M, int N, int K, int bn /* B rows per TMA box */, int64_t a_extra = 0,
+                     int64_t b_extra = 0) {
   {
     // A: K-major -> dims (K, M) box (64, 128); MN-major -> dims (M, K) box (64, 64)
     uint64_t dims[2], strides[1] = {static_cast<uint64_t>(lda) * 2};
     uint32_t box[2];
-    if (!a_mn) { dims[0] = K; dims[1] = M; box[0] = 64; box[1] = 128; }
-    else       { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = 64; }
+    if (!a_mn) { dims[0] = K; dims[1] = M + a_extra; box[0] = 64; box[1] = 128; }
+    else       { dims[0] = M; dims[1] = K + a_extra; box[0] = 64; box[1] = 64; }
     if (int e = make_tmap_bf16(ta, a, 2, dims, strides, box, nullptr)) return e;
   }
   {
     uint64_t dims[2], strides[1] = {static_cast<uint64_t>(ldb) * 2};
     uint32_t box[2];
-    if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = static_cast<uint32_t>(bn); }
-    else       { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64; }
+    if (!b_mn) { dims[0] = K; dims[1] = N + b_extra; box[0] = 64; box[1] = static_cast<uint32_t>(bn); }
+    else       { dims[0] = N; dims[1] = K + b_extra; box[0] = 64; box[1] = 64; }
     if (int e = make_tmap_bf16(tb, b, 2, dims, strides, box, nullptr)) return e;
   }
   return GH_OK;
@@ -107,7 +109,7 @@ long long* gemm_prof_ptr() { return g_gemm_prof; }
 //   shared memory    operand reads + TMA writes at 128 B/clk: single CTA (128 + BN) / 2, CTA pair (128 + BN/2) / 2
 // plus a fixed per-tile cost; waves = tiles per worker (148 CTAs, or 74 pairs each covering 256 rows).
 struct TileChoice { int bn; bool pair; };
-static TileChoice pick_tile(int M, int N) {
+static TileChoice pick_tile(int M, int N, int batch = 1) {
   const long mb = (M + 127) / 128;
   const int sms = num_sms();
   static const int force = [] { const char* e = getenv("GH_GEMM_PAIR"); return e ? atoi(e) : -1; }();
@@ -120,7 +122,7 @@ static TileChoice pick_tile(int M, int N) {
       if (pair && bn < 128) continue;
       if (bn > 64 && N <= bn / 2) continue;  // a tile more than twice as wide as the problem
       const long nb = (N + bn - 1) / bn;
-      const long tiles = (pair ? (mb + 1) / 2 : mb) * nb;
+      const long tiles = (pair ? (mb + 1) / 2 : mb) * nb * batch;
       const long workers = pair ? sms / 2 : sms;
       const long waves = (tiles + workers - 1) / workers;
       const double t = pair ? (bn / 2 > (128 + bn / 2) / 2 ? bn / 2 : (128 + bn / 2) / 2)
@@ -160,13 +162,21 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
                  (!a->gate || a->gate_ld % 4 == 0) && (!a->residual || a->ld_res % 4 == 0),
              GH_ERR_ALIGN, "gh_gemm_bf16: epilogue operand leading dimensions must be multiples of 4");
 
-  const TileChoice tc = pick_tile(a->M, a->N);
+  const int batch = a->batch > 1 ? a->batch : 1;
+  GH_REQUIRE(batch == 1 || (a->K2 == 0 && a->k_splits == 0 && !a->gate && a->a_batch_rows >= 0 && a->b_batch_rows >= 0 &&
+                            a->d_batch_rows >= a->M),
+             GH_ERR_UNSUPPORTED, "gh_gemm_bf16: batched mode takes no second operand pair, split-K or gate, and needs "
+                                 "d_batch_rows >= M");
+  const TileChoice tc = pick_tile(a->M, a->N, batch);
   const int bn = tc.bn;
   GemmParams p{};
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.num_m_blocks = (a->M + 127) / 128;
   p.num_n_blocks = (a->N + bn - 1) / bn;
   p.num_k_blocks = (a->K + 63) / 64;
+  p.batch = batch;
+  p.a_boff = static_cast<int>(a->a_batch_rows); p.b_boff = static_cast<int>(a->b_batch_rows);
+  p.d_brows = static_cast<int>(a->d_batch_rows);
   p.a_stage_tx_bytes = 128 * 64 * 2;
   p.mn_lbo = 8192; p.mn_sbo = 1024; p.mn_kstep = 2048;
   if (const char* dbg = getenv("GH_DEBUG_MN_DESC")) {  // bring-up aid: "lbo,sbo,kstep" in bytes
@@ -209,7 +219,9 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
   CUtensorMap tm[6];
   const int box_n = tc.pair ? bn / 2 : bn;
-  if (int e = make_pair(&tm[0], &tm[1], a->a, a->lda, amn, a->b, a->ldb, bmn, a->M, a->N, a->K, box_n)) return e;
+  if (int e = make_pair(&tm[0], &tm[1], a->a, a->lda, amn, a->b, a->ldb, bmn, a->M, a->N, a->K, box_n,
+                        (batch - 1) * a->a_batch_rows, (batch - 1) * a->b_batch_rows))
+    return e;
   if (a->K2 > 0) {
     if (int e = make_pair(&tm[2], &tm[3], a->a2, a->lda2, amn, a->b2, a->ldb2, bmn, a->M, a->N, a->K2, box_n)) return e;
     p.num_k_blocks2 = (a->K2 + 63) / 64;
@@ -221,7 +233,7 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
   }
   // lean epilogue through [32 rows x 64 columns] SWIZZLE_128B tiles: TMA store of D, TMA load of the residual
   static const int no_tma_epi = [] { const char* e = getenv("GH_GEMM_NO_TMA_EPI"); return e ? atoi(e) : 0; }();
-  p.ep.tma = p.ep.fast && !no_tma_epi && (!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0);
+  p.ep.tma = p.ep.fast && !no_tma_epi && batch == 1 && (!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0);
   tm[4] = tm[0];
   tm[5] = tm[0];
   if (p.ep.tma) {

@@ -71,6 +71,12 @@ struct GemmParams {
   // axis of k_splits slices of the K loop; every slice ADDS its partial result into the fp32 output with red.add
   // (the caller zeroes D).  k_splits = 1: off.  Not combined with the second operand pair.
   int k_splits;
+  // Batched GEMM over FLAT 2-D operands (the AE mid-block attention: 32 per-image Q K^T / P V products in one
+  // launch): problem b reads A at row (or, MN-major, k) offset b * a_boff of the same tensor map, B at b * b_boff,
+  // and writes D rows b * d_brows + m.  Tiles that overrun a problem's M / N read the neighbour's rows (or TMA
+  // zero fill at the end of the tensor) and are masked by the epilogue; an overrun along K of a K-major operand is
+  // zero-filled because the tensor map's K extent is the per-problem K.  batch = 1: plain GEMM.
+  int batch, a_boff, b_boff, d_brows;
   uint32_t a_stage_tx_bytes;  // bytes TMA deposits for the A tile of one stage
   uint32_t mn_lbo, mn_sbo, mn_kstep;  // MN-major descriptor geometry (bytes); see common.cuh
   EpilogueParams ep;
@@ -463,7 +469,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_mn = m_units * p.num_n_blocks;
-  const int num_tiles = tiles_mn * p.k_splits;   // tile index = split * tiles_mn + (m, n) index
+  const int tiles_pb = tiles_mn * p.k_splits;    // tiles of one problem: index = split * tiles_mn + (m, n) index
+  const int num_tiles = tiles_pb * (MODE == MODE_GEMM ? p.batch : 1);   // batch-major
   const int nkb1 = p.num_k_blocks;
   const int nkb = nkb1 + (MODE == MODE_GEMM ? p.num_k_blocks2 : 0);
 
@@ -506,11 +513,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr int BNL = CTA2 ? BN / 2 : BN;            // B rows this CTA loads
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int m_blk, n_blk;
-      const int split = tile / tiles_mn;
-      decode_tile(tile - split * tiles_mn, m_units, p.num_n_blocks, m_blk, n_blk);
+      const int bi = (MODE == MODE_GEMM && p.batch > 1) ? tile / tiles_pb : 0;
+      const int ptile = tile - bi * tiles_pb;
+      const int split = ptile / tiles_mn;
+      decode_tile(ptile - split * tiles_mn, m_units, p.num_n_blocks, m_blk, n_blk);
       const int kb0 = (split * nkb) / p.k_splits, kb1 = ((split + 1) * nkb) / p.k_splits;
       if (CTA2) m_blk = m_blk * 2 + static_cast<int>(rank);
       const int nrow0 = n_blk * BN + static_cast<int>(rank) * BNL;
+      const int a_off = bi * p.a_boff, b_off = bi * p.b_boff;
       int cb = 0, ch0 = 0, cw0 = 0;
       if (MODE == MODE_CONV) {
         const int tiles_per_img = p.cv.tiles_w * p.cv.tiles_h;
@@ -554,10 +564,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const CUtensorMap* ma = second ? &tmap_a2 : &tmap_a;
             const int kc = (second ? kb - nkb1 : kb) * 64;
             if (!A_MN) {
-              ld2(sA, ma, kc, m_blk * 128);
+              ld2(sA, ma, kc, m_blk * 128 + a_off);
             } else {
-              ld2(sA, ma, m_blk * 128, kc);
-              ld2(sA + 8192, ma, m_blk * 128 + 64, kc);
+              ld2(sA, ma, m_blk * 128, kc + a_off);
+              ld2(sA + 8192, ma, m_blk * 128 + 64, kc + a_off);
             }
           }
           if (MODE == MODE_CONV) {
@@ -567,10 +577,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const CUtensorMap* mb = second ? &tmap_b2 : &tmap_b;
             const int kc = (second ? kb - nkb1 : kb) * 64;
             if (!B_MN) {
-              ld2(sB, mb, kc, nrow0);
+              ld2(sB, mb, kc, nrow0 + b_off);
             } else {
 #pragma unroll
-              for (int i = 0; i < BNL / 64; ++i) ld2(sB + i * 8192, mb, nrow0 + i * 64, kc);
+              for (int i = 0; i < BNL / 64; ++i) ld2(sB + i * 8192, mb, nrow0 + i * 64, kc + b_off);
             }
           }
         }
@@ -610,7 +620,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-      const int split = tile / tiles_mn;
+      const int split = (tile % tiles_pb) / tiles_mn;
       const int kb0 = (split * nkb) / p.k_splits, kb1 = ((split + 1) * nkb) / p.k_splits;
       for (int kb = kb0; kb < kb1; ++kb) {
         if (p.prof) {
@@ -689,6 +699,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int m_blk, n_blk;
       decode_tile(tile % tiles_mn, m_units, p.num_n_blocks, m_blk, n_blk);
       if (CTA2) m_blk = m_blk * 2 + static_cast<int>(rank);
+      const int d_row_off = (MODE == MODE_GEMM && p.batch > 1) ? (tile / tiles_pb) * p.d_brows : 0;
       // the 2 output rows this lane touches in every slice of the tile (row index == logical GEMM row)
       int rows[2];
       uint32_t rowmask = 0;
@@ -705,8 +716,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ok = (tr < p.cv.TW * p.cv.TH) && (oh < p.cv.Ho) && (ow < p.cv.Wo) && (cb < p.cv.B);
           rows[it] = (cb * p.cv.Ho + oh) * p.cv.Wo + ow;
         } else {
-          rows[it] = m_blk * 128 + tr;
-          ok = rows[it] < p.M;
+          ok = m_blk * 128 + tr < p.M;
+          rows[it] = m_blk * 128 + tr + d_row_off;   // row of the flat output (batched: problem b starts at b * d_brows)
         }
         rowmask |= static_cast<uint32_t>(ok) << it;
       }

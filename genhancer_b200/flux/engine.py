@@ -259,7 +259,9 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
         """dmod_acc fp32 [B, n] -> param grads of the modulation linear, dsvec += dmod @ W."""
         dmod = torch.empty(dmod_acc.shape, dtype=BF16, device=dev)
         K.accum_cast(dmod_acc, dmod)
-        K.gemm(dmod, P[w_name], b_mn=True, out=dsvec, residual=dsvec)
+        # [B, n] x [n, C] with B = 32 rows: one M tile and 12-48 N tiles would leave most SMs idle while each CTA
+        # streams the whole K = n (up to 18432) alone -> split-K over the machine, partials red.add-ed into dsvec
+        K.gemm(dmod, P[w_name], b_mn=True, out=dsvec, k_splits=-1)
         if sink.wants(w_name):
             gw, res = sink.big(w_name)
             K.gemm(dmod, svec, a_mn=True, b_mn=True, out=gw, residual=res)

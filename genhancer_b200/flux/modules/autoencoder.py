@@ -125,13 +125,13 @@ class _ConvStack(nn.Module):
         L = H * Wd
         y = K.groupnorm_swish_nhwc(h, *W["mid.attn_1.norm"], swish=False)
         qkv = K.gemm(y.view(-1, C), W["mid.attn_1.qkv"][0], bias=W["mid.attn_1.qkv"][1]).view(B, L, 3 * C)
-        o = torch.empty(B, L, C, dtype=BF16, device=h.device)
+        # all B per-image products in ONE batched launch each (flat [B*L, .] operands, gh_gemm_bf16 batch mode):
+        # 32 x (Q K^T, softmax, P V) was 96 launch-bound kernels
         ldp = (L + 7) // 8 * 8
-        for b in range(B):
-            q, k, v = qkv[b, :, :C], qkv[b, :, C:2 * C], qkv[b, :, 2 * C:]
-            s = K.gemm(q, k, out_dtype=F32)                                   # [L, L] fp32 scores
-            p = K.softmax_rows(s, L, C ** -0.5, ldp)                          # bf16, pad columns zero
-            K.gemm(p[:, :L], v, b_mn=True, out=o[b])                          # P @ V (V is [K=L, N=C])
+        flat = qkv.view(B * L, 3 * C)
+        s = K.gemm(flat[:, :C], flat[:, C:2 * C], out_dtype=F32, batch=B)            # [B*L, L] fp32 scores
+        p = K.softmax_rows(s, L, C ** -0.5, ldp)                                     # bf16, pad columns zero
+        o = K.gemm(p[:, :L], flat[:, 2 * C:], b_mn=True, batch=B)                    # P @ V (V is [K=L, N=C] per image)
         out = K.gemm(o.view(-1, C), W["mid.attn_1.proj_out"][0], bias=W["mid.attn_1.proj_out"][1],
                      residual=h.view(-1, C))
         return out.view(B, H, Wd, C)

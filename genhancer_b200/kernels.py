@@ -55,8 +55,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          aux_in: torch.Tensor | None = None, aux_out: torch.Tensor | None = None,
          gate: torch.Tensor | None = None, rows_per_batch: int = 0,
          residual: torch.Tensor | None = None, a2: torch.Tensor | None = None,
-         b2: torch.Tensor | None = None, k_splits: int = 0) -> torch.Tensor:
+         b2: torch.Tensor | None = None, k_splits: int = 0, batch: int = 1) -> torch.Tensor:
     """D[M,N] = epilogue(alpha * (A @ B^T + A2 @ B2^T)).
+
+    ``batch`` > 1: ``a``, ``b`` and ``out`` are ``batch`` equal problems stacked along their FIRST dimension
+    ([batch*M, K] / [batch*N, K] -> [batch*M, N], or the ``*_mn`` forms stacked along K); one launch computes them all.
 
     ``a2`` / ``b2`` (same majors as ``a`` / ``b``, reduction length K2 = the LoRA rank) fold a low-rank branch into
     the base GEMM: one extra 16-deep MMA per tile instead of a second GEMM and a second pass over the output.
@@ -69,15 +72,18 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     _rowmajor2d(b, "gemm b")
     if a.dtype != BF16 or b.dtype != BF16:
         raise _lib.GhError("gemm operands must be bf16")
-    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
-    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if batch < 1 or a.shape[0] % batch or b.shape[0] % batch:
+        raise _lib.GhError(f"gemm: batch={batch} does not divide the stacked operands {tuple(a.shape)} / {tuple(b.shape)}")
+    a_rows, b_rows = a.shape[0] // batch, b.shape[0] // batch
+    M, K = (a.shape[1], a_rows) if a_mn else (a_rows, a.shape[1])
+    N, Kb = (b.shape[1], b_rows) if b_mn else (b_rows, b.shape[1])
     if K != Kb:
         raise _lib.GhError(f"gemm: reduction mismatch {K} vs {Kb}")
     if out is None:
-        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+        out = torch.empty((batch * M, N), dtype=out_dtype, device=a.device)
     _rowmajor2d(out, "gemm out")
-    if tuple(out.shape) != (M, N):
-        raise _lib.GhError(f"gemm: out has shape {tuple(out.shape)}, expected {(M, N)}")
+    if tuple(out.shape) != (batch * M, N):
+        raise _lib.GhError(f"gemm: out has shape {tuple(out.shape)}, expected {(batch * M, N)}")
     g = GemmArgs()
     g.a, g.lda, g.a_mn_major = a.data_ptr(), a.stride(0), int(a_mn)
     g.b, g.ldb, g.b_mn_major = b.data_ptr(), b.stride(0), int(b_mn)
@@ -99,6 +105,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if residual is not None:
         _rowmajor2d(residual, "gemm residual")
         g.residual, g.ld_res, g.res_dtype = residual.data_ptr(), residual.stride(0), _dt(residual)
+    if batch > 1:
+        g.batch, g.a_batch_rows, g.b_batch_rows, g.d_batch_rows = batch, a_rows, b_rows, M
     g.k_splits = k_splits   # != 0: out (fp32, zeroed or to be accumulated into by the caller) += A @ B^T, split over K
     K2 = 0
     if a2 is not None:
@@ -113,7 +121,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         g.a2, g.lda2, g.b2, g.ldb2, g.K2 = a2.data_ptr(), a2.stride(0), b2.data_ptr(), b2.stride(0), K2
     tm = GEMM_TIMER
     if tm is not None:
-        ev0, ev1 = tm(2.0 * M * N * (K + K2), f"gemm M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} d={'f32' if out.dtype == F32 else 'bf16'}")
+        ev0, ev1 = tm(2.0 * batch * M * N * (K + K2), f"gemm M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} d={'f32' if out.dtype == F32 else 'bf16'}"
+                      + (f" batch={batch}" if batch > 1 else ""))
         ev0.record()
     check(_lib.lib().gh_gemm_bf16(C.byref(g), _stream()))
     if tm is not None:

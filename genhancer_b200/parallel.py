@@ -75,16 +75,26 @@ class GradReducer:
             self._issue(gi, g, lo, hi, prefix or "<rest>")
 
     # ---- called by the trainer after loss.backward() ---------------------------------------------------
-    def finish(self) -> None:
-        """Reduce whatever the backward schedule did not announce (autograd-managed groups such as the fp32
-        projectors / adapter), then make the current stream wait for every bucket."""
+    def issue_rest(self) -> None:
+        """Issue (without waiting) the all-reduce of whatever the backward schedule did not announce: the
+        autograd-managed groups such as the fp32 projectors / adapter.  Call right after ``loss.backward()``."""
         if self.enabled and self.world > 1:
             for gi, g in enumerate(self.groups):
                 self._reduce_rest(gi, g)
-            for w in self._works:
-                w.wait()
+
+    def wait(self) -> None:
+        """Make the current stream wait for every bucket issued so far."""
+        for w in self._works:
+            w.wait()
         self._works.clear()
         self._done.clear()
+
+    def finish(self) -> None:
+        """``issue_rest()`` + ``wait()``.  The data-parallel loops call the two halves separately: the rest is issued
+        right after backward, the wait is deferred into the next step (``before_trainable``), so the tail of the
+        exchange hides under the frozen AE / tower forward."""
+        self.issue_rest()
+        self.wait()
 
     @property
     def grad_scale(self) -> float:

@@ -80,12 +80,24 @@ class Stage1ImageStep:
         return self._ids[key]
 
     def __call__(self, img: Tensor, ae_noise: Tensor | None = None, t: Tensor | None = None,
-                 x_0: Tensor | None = None, return_parts: bool = False):
-        """img: [B,3,S,S] fp32 in [0,1] on the device.  Returns the scalar loss (autograd-connected)."""
+                 x_0: Tensor | None = None, return_parts: bool = False, before_trainable=None):
+        """img: [B,3,S,S] fp32 in [0,1] on the device.  Returns the scalar loss (autograd-connected).
+
+        ``before_trainable()`` is called once, after everything that reads NO trainable parameter (the frozen AE
+        encoder, and in stage 1 the frozen tower) and before the first kernel that does.  The data-parallel loop
+        puts the PREVIOUS step's ``reducer.finish(); opt.step(); opt.zero_grad()`` there, so the tail of the
+        gradient all-reduce hides under ~30 ms of frozen forward instead of being exposed after backward; the
+        arithmetic is that of the sequential loop (weights are updated before they are next read)."""
         B = img.shape[0]
         dev = img.device
         x_1 = self.vae.encode_patchified(img, 0.5, 0.5, noise=ae_noise)                 # [B, L, 64] fp32
-        _, vec, txt = self.clip_vis(img, _norm=(self.clip_mean, self.clip_std))
+        tower_trains = any(p.requires_grad for p in self.clip_vis.model.parameters())
+        if before_trainable is not None and tower_trains:
+            before_trainable()
+        cls = self.clip_vis.class_token(img, _norm=(self.clip_mean, self.clip_std))
+        if before_trainable is not None and not tower_trains:
+            before_trainable()
+        vec, txt = self.clip_vis.project(cls)
         h2 = w2 = int(round(x_1.shape[1] ** 0.5))
         img_ids, txt_ids, guidance = self._static(B, h2, w2, txt.shape[1], dev)
         t, x_0 = sample_t_x0(x_1, self.scale_factor, t, x_0)

@@ -276,55 +276,75 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
     max_steps = max_steps_override or int(args.max_train_steps)
     loader = make_loader(args, mode, device, rank)
     ckpt_extra = STAGE2_CKPT_STEPS if stage2 else IMAGE_CKPT_STEPS
-    losses, micro, t_last = [], 0, time.time()
+    losses, micro = [], 0
+    st = SimpleNamespace(step=global_step, pending=False, t_last=time.time())
     train_loss = torch.zeros((), device=device)
+    pending_loss = torch.zeros((), device=device)
+
+    def finish_step():
+        """Gradient exchange (wait) + clip + AdamW + bookkeeping of the optimizer step whose backward has been issued.
+        With data parallelism it runs INSIDE the next micro-step, right before the first kernel that reads a trainable
+        parameter (``before_trainable``), so the all-reduce tail hides under the frozen AE / tower forward."""
+        if not st.pending:
+            return
+        st.pending = False
+        if reducer is not None:
+            reducer.wait()
+        opt.step(reducer.grad_scale if reducer else 1.0)
+        opt.zero_grad()
+        st.step += 1
+        if st.step % 10 == 0 or st.step == max_steps:
+            lv = float(pending_loss)        # one host sync per logged step (the reference syncs every micro-step)
+            losses.append(lv)
+            if is_main:
+                dt = time.time() - st.t_last
+                print(f"[genhancer_b200] step {st.step} loss {lv:.4f} grad-norm {float(opt.grad_norm()):.3f} "
+                      f"({dt:.2f} s since last log)", flush=True)
+            st.t_last = time.time()
+        if is_main and args.get("output_dir") and (st.step % int(args.checkpointing_steps) == 0
+                                                   or st.step in ckpt_extra or st.step >= max_steps):
+            if stage2:
+                save_stage2(args.output_dir, st.step, family, args, dit, clip_vis, adapter, opt, video)
+            else:
+                save_checkpoint(args.output_dir, st.step, dit, clip_vis, adapter, opt, video,
+                                save_project_clip=train_project_clip)
+
     for batch in loader:
-        if global_step >= max_steps:
+        if st.step + int(st.pending) >= max_steps:
             break
         sync = (micro + 1) % ga == 0
         if reducer is not None:
             reducer.enabled = sync
         if mode == "image":
-            loss = step_fn(batch["image"].to(device, non_blocking=True).float())
+            loss = step_fn(batch["image"].to(device, non_blocking=True).float(), before_trainable=finish_step)
         elif mode == "sliding_windows_nextpredic":
             w = build_windows_with_mask(batch["full_frames"].to(device), batch["frame_mask"].to(device),
                                         int(args.get("window_cond", 3)), int(args.get("window_stride", 1)),
                                         args.get("max_windows_per_video", 8))
             if w is None:
                 continue
-            loss = step_fn(list(w[:3]), w[3])
+            loss = step_fn(list(w[:3]), w[3], before_trainable=finish_step)
         else:
             f = {k: batch[k].to(device, non_blocking=True).float() for k in ("start_frame", "middle_frame", "end_frame")}
             cond, tgt = {"video": (("start_frame", "end_frame"), "middle_frame"),
                          "nextpredic": (("start_frame",), "middle_frame"),
                          "use2frames_nextpredic": (("start_frame", "middle_frame"), "end_frame")}[mode]
-            loss = step_fn([f[k] for k in cond], f[tgt])
+            loss = step_fn([f[k] for k in cond], f[tgt], before_trainable=finish_step)
+        finish_step()                   # (no-op if the step object already called it)
         (loss / ga).backward()          # accelerator.backward divides by gradient_accumulation_steps
         train_loss += loss.detach() / ga
         micro += 1
         if not sync:
             continue
         if reducer is not None:
-            reducer.finish()
-        opt.step(reducer.grad_scale if reducer else 1.0)
-        opt.zero_grad()
-        global_step += 1
-        if global_step % 10 == 0 or global_step == max_steps:
-            lv = float(train_loss)          # one host sync per logged step (the reference syncs every micro-step)
-            losses.append(lv)
-            if is_main:
-                dt = time.time() - t_last
-                print(f"[genhancer_b200] step {global_step} loss {lv:.4f} grad-norm {float(opt.grad_norm()):.3f} "
-                      f"({dt:.2f} s since last log)", flush=True)
-            t_last = time.time()
+            reducer.issue_rest()        # projector / adapter groups: issued now, waited for in finish_step()
+        pending_loss.copy_(train_loss)
         train_loss.zero_()
-        if is_main and args.get("output_dir") and (global_step % int(args.checkpointing_steps) == 0
-                                                   or global_step in ckpt_extra or global_step >= max_steps):
-            if stage2:
-                save_stage2(args.output_dir, global_step, family, args, dit, clip_vis, adapter, opt, video)
-            else:
-                save_checkpoint(args.output_dir, global_step, dit, clip_vis, adapter, opt, video,
-                                save_project_clip=train_project_clip)
+        st.pending = True
+        if reducer is None:
+            finish_step()               # single GPU: nothing to hide
+    finish_step()
+    global_step = st.step
     if world > 1:
         dist.barrier()
     return SimpleNamespace(global_step=global_step, losses=losses, dit=dit, clip_vis=clip_vis, adapter=adapter, opt=opt)

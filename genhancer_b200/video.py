@@ -127,14 +127,18 @@ class VideoStep:
                               torch.full((B,), self.guidance, device=dev, dtype=BF16))
         return self._ids[key]
 
-    def __call__(self, cond_frames, target: Tensor, ae_noise=None, t=None, x_0=None, return_parts: bool = False):
-        """cond_frames: sequence of [B,3,S,S] fp32 frames (as the dataset yields them); target [B,3,S,S]."""
+    def __call__(self, cond_frames, target: Tensor, ae_noise=None, t=None, x_0=None, return_parts: bool = False,
+                 before_trainable=None):
+        """cond_frames: sequence of [B,3,S,S] fp32 frames (as the dataset yields them); target [B,3,S,S].
+        ``before_trainable``: see Stage1ImageStep.__call__ (the deferred exchange + update of the previous step)."""
         if len(cond_frames) != len(self.cond_times):
             raise ValueError(f"expected {len(self.cond_times)} conditioning frames, got {len(cond_frames)}")
         B, dev = target.shape[0], target.device
         n = len(cond_frames)
         x_1 = self.vae.encode_patchified(target, 0.5, 0.5, noise=ae_noise)
         model = self.m.clip_vis.model
+        if before_trainable is not None and self.tower_grad:
+            before_trainable()
         frames = torch.cat(list(cond_frames), dim=0) if n > 1 else cond_frames[0]       # one tower pass for all frames
         ctx = torch.enable_grad() if self.tower_grad else torch.no_grad()
         with ctx:
@@ -146,6 +150,8 @@ class VideoStep:
         g = int(round(P ** 0.5))
         if g * g != P:
             raise AssertionError(f"patch tokens must form a square grid, got P={P}")
+        if before_trainable is not None and not self.tower_grad:
+            before_trainable()
         txt = self.m.visual_adapter(visual_context)
         h2 = w2 = int(round(x_1.shape[1] ** 0.5))
         img_ids, txt_ids, guidance = self._static(B, h2, w2, g, dev)

@@ -40,6 +40,10 @@ const char* gh_last_error(void);
 int gh_version(void);
 /* Resolve the driver entry points, raise the kernels' dynamic-smem limits on `device`. */
 int gh_init(int device);
+/* How many SMs the persistent kernels (one CTA or CTA pair per SM) may fill; 0 = all.  Data-parallel training leaves a
+ * few SMs to the concurrent NCCL all-reduce kernels: a persistent grid that finds some SMs taken runs its last CTAs as
+ * a second wave (accelerate / DeepSpeed have no analogue: their GEMMs are not persistent). */
+int gh_set_sm_budget(int sms);
 
 /* --------------------------------------------------------------------------
  * gh_gemm_bf16 -- tcgen05/TMEM GEMM fed by TMA, fused epilogue.
@@ -103,6 +107,15 @@ typedef struct {
    * accumulated into), computed by k_splits slices of the K loop that add their partial products with red.add;
    * < 0 picks the slice count that fills the machine.  No epilogue options, no second operand pair. */
   int32_t k_splits;
+  /* Batched mode (batch > 1): `batch` independent M x N x K problems in ONE launch over FLAT 2-D operands.  Problem i
+   * reads A at row offset i * a_batch_rows (K-major A: rows of the [.,K] matrix; MN-major A: rows of the [K,.] matrix,
+   * i.e. the k index), B at i * b_batch_rows likewise, and writes D (and reads residual / aux_in, writes aux_out) at
+   * row i * d_batch_rows + m.  Used for the AE mid-block attention (autoencoder.py:37-52: one 1764 x 1764 x 512
+   * Q K^T and one P V per image) which is otherwise 64 launch-bound GEMMs.  Rows that a tile reads beyond its own
+   * problem belong to the next one (finite values; their products are masked or multiply TMA-zero-filled columns).
+   * No second operand pair, split-K or gate.  batch <= 1: plain GEMM. */
+  int32_t batch;
+  int64_t a_batch_rows, b_batch_rows, d_batch_rows;
 } gh_gemm_args;
 int gh_gemm_bf16(const gh_gemm_args* args, void* stream);
 /* Bring-up aid: when device_buf (int64 [8 * #SMs]) is non-NULL, every following gh_gemm_bf16 launch writes per-CTA

@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Data-parallel overlap sweep (run under torchrun, N >= 2): one model build, then for each
+(NCCL max CTAs, SM budget of our persistent grids, deferred exchange yes/no) a few timed steps of bench.py's step.
+
+NCCL's all-reduce kernels need whole SMs (their shared memory does not fit beside a 227 KB GEMM CTA); a persistent
+GEMM grid of 148 CTAs that finds n SMs taken runs n CTAs as a second wave.  The sweep finds the (few CTAs for NCCL,
+148 - n SMs for us) point at which the exchange hides for free.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_sweep.py
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    from genhancer_b200 import _lib, optim
+    from genhancer_b200.parallel import GradReducer, broadcast_parameters
+
+    world, rank, local = (int(os.environ[k]) for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    B, S = 32, 336
+    step, clip_vis, dit, vae = bench.build_models(S, dev)
+    trainable = list(dit.named_parameters()) + [(f"clip_vis.{n}", p) for n, p in clip_vis.named_parameters()]
+    groups = optim.flatten(trainable)
+    broadcast_parameters(groups)
+    opt = optim.FusedAdamW(groups, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=1.0,
+                           engine_managed=[dit])
+    gen = torch.Generator(device=dev)
+    batches = []
+    for i in range(4):
+        gen.manual_seed(1234 + i + 1000 * rank)
+        batches.append(torch.rand(B, 3, S, S, device=dev, generator=gen))
+    L = _lib.lib()
+
+    def run(max_ctas, budget, deferred, bucket_mb=256, steps=6, warm=3, comm=True):
+        pg = None
+        if max_ctas:
+            o = dist.ProcessGroupNCCL.Options()
+            o.config.max_ctas = max_ctas
+            o.config.min_ctas = min(max_ctas, 1)
+            pg = dist.new_group(backend="nccl", pg_options=o)
+        reducer = GradReducer(groups, engine_modules=[dit], process_group=pg, bucket_cap_bytes=bucket_mb << 20)
+        reducer.enabled = comm
+        gscale = 1.0 / world
+        L.gh_set_sm_budget(budget)
+        pend = {"n": 0}
+
+        def flush():
+            if pend["n"]:
+                reducer.wait()
+                opt.step(gscale)
+                opt.zero_grad()
+                pend["n"] = 0
+
+        def one(img):
+            if deferred:
+                loss = step(img, before_trainable=flush)
+                loss.backward()
+                reducer.issue_rest()
+                pend["n"] = 1
+            else:
+                loss = step(img)
+                loss.backward()
+                reducer.finish()
+                opt.step(gscale)
+                opt.zero_grad()
+
+        for i in range(warm):
+            one(batches[i % 4])
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            one(batches[i % 4])
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        flush()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        L.gh_set_sm_budget(0)
+        dit._on_grads_ready = None
+        row = dict(max_ctas=max_ctas, sm_budget=budget, deferred=deferred, bucket_mb=bucket_mb, comm=comm,
+                   ms_per_step=round(float(ms), 3), img_s=round(world * B / float(ms) * 1e3, 1))
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+        return row
+
+    rows = []
+    rows.append(run(0, 0, False, comm=False))          # no exchange at all: the compute floor of the eager step
+    rows.append(run(0, 0, False))                      # what round 1 measured so far (NCCL defaults)
+    rows.append(run(0, 0, True))
+    for ctas, budget in ((8, 0), (8, 132), (4, 0), (4, 140), (2, 0), (2, 144), (1, 146), (1, 0)):
+        rows.append(run(ctas, budget, True))
+    rows.append(run(4, 140, True, bucket_mb=64))
+    rows.append(run(2, 144, False))
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"dp_sweep_n{world}.jsonl"), "w") as f:
+            for r in rows:
+                f.write(json.dumps(r) + "\n")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

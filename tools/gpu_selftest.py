@@ -174,6 +174,40 @@ def time_gemm(M, N, Kd, a_mn=False, b_mn=False, iters=20):
         f"{2.0 * M * N * Kd / ms2 / 1e9:.0f} TFLOP/s")
 
 
+def batched_cases():
+    """gh_gemm_bf16 batch mode (the AE mid-block attention, autoencoder.py:37-52) against torch.bmm, and the split-K
+    dgrad of a 32-row Modulation (layers.py:169-175) against a plain matmul."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for (Bn, L, C) in [(3, 1764, 512), (5, 200, 64), (32, 441, 128), (2, 128, 256)]:
+        qkv = (torch.randn(Bn * L, 3 * C, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        s = K.gemm(q, k, out_dtype=torch.float32, batch=Bn)                       # [Bn*L, L]
+        ref_s = torch.bmm(q.float().view(Bn, L, C), k.float().view(Bn, L, C).transpose(1, 2)).view(Bn * L, L)
+        e = relerr(s, ref_s)
+        say("PASS" if e < 2e-3 else "FAIL", f"batched QK^T B={Bn} L={L} C={C}", f"relerr={e:.3e}")
+        ldp = (L + 7) // 8 * 8
+        p = K.softmax_rows(s, L, C ** -0.5, ldp)
+        o = K.gemm(p[:, :L], v, b_mn=True, batch=Bn)                               # [Bn*L, C]
+        ref_o = torch.bmm(p[:, :L].float().view(Bn, L, L), v.float().view(Bn, L, C)).view(Bn * L, C)
+        e = relerr(o, ref_o)
+        say("PASS" if e < 1e-2 else "FAIL", f"batched PV   B={Bn} L={L} C={C}", f"relerr={e:.3e}")
+        # bias + residual through the batched epilogue rows
+        bias = torch.randn(C, device="cuda", generator=g).to(torch.bfloat16)
+        res = torch.randn(Bn * L, C, device="cuda", generator=g).to(torch.bfloat16)
+        o2 = K.gemm(p[:, :L], v, b_mn=True, batch=Bn, bias=bias, residual=res)
+        e = relerr(o2, ref_o + bias.float() + res.float())
+        say("PASS" if e < 1e-2 else "FAIL", f"batched PV + bias + residual B={Bn} L={L} C={C}", f"relerr={e:.3e}")
+    for (M, N, Kd) in [(32, 3072, 18432), (32, 3072, 9216), (32, 3072, 6144), (2, 768, 1536)]:
+        A = torch.randn(M, Kd, device="cuda", generator=g).to(torch.bfloat16)
+        W = (torch.randn(Kd, N, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+        base = torch.randn(M, N, device="cuda", generator=g)
+        out = base.clone()
+        K.gemm(A, W, b_mn=True, out=out, k_splits=-1)
+        ref = base + A.float() @ W.float()
+        e = relerr(out, ref)
+        say("PASS" if e < 2e-3 else "FAIL", f"split-K dgrad M={M} N={N} K={Kd}", f"relerr={e:.3e}")
+
+
 def fm_cases():
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(1)
@@ -258,6 +292,8 @@ def main():
             e = relerr(out, ref)
             say("PASS" if e < 2e-3 else "FAIL", f"split-K wgrad M={M} N={N} K={Kd}", f"relerr={e:.3e}")
         copy_table_cases()
+    if "batched" in which:
+        batched_cases()
     if "time" in which:
         time_gemm(4096, 4096, 4096)
         time_gemm(8192, 8192, 8192)
