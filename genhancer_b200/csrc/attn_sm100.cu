@@ -193,32 +193,41 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_ld_32x32(t_lane + Cfg::TM_S + (j & 1) * ATT_BKV + 32, s1);
         tmem_ld_wait();
       }
+      // ~300 issue slots per 64-key block and thread (it was ~900: a separate scale multiply, a per-element tail mask,
+      // exp2f's denormal range handling, and a bf16 round trip for the row sum): the tail mask runs only in the last
+      // block, the scale rides in the FFMA that subtracts the running maximum, MUFU.EX2 is issued bare.
       const int kv_left = p.Lk - j * ATT_BKV;  // valid keys in this block
-      float mx = -INFINITY;
+      if (kv_left < ATT_BKV) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float v = __uint_as_float(s[c]) * p.scale_log2;
-        if (c >= kv_left) v = -INFINITY;
-        s[c] = __float_as_uint(v);
-        mx = fmaxf(mx, v);
+        for (int c = 0; c < 64; ++c)
+          if (c >= kv_left) s[c] = 0xff800000u;  // -inf
       }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(s[c + u]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;  // scale > 0
       float factor = 1.f;
       if (j == 0) {
         m_used = mx;
       } else if (mx > m_used + 8.f) {
-        factor = exp2f(m_used - mx);
+        factor = ex2_approx(m_used - mx);
         m_used = mx;
       }
-      float rs = 0.f;
+      const float neg_m = -m_used;
+      float rs0 = 0.f, rs1 = 0.f;
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
-        const float e0 = exp2f(__uint_as_float(s[c]) - m_used);
-        const float e1 = exp2f(__uint_as_float(s[c + 1]) - m_used);
+        const float e0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, neg_m));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, neg_m));
         pk[c >> 1] = pack_bf16x2(e0, e1);
-        const float2 r2 = unpack_bf16x2(pk[c >> 1]);  // sum what the MMA will actually see
-        rs += r2.x + r2.y;
+        rs0 += e0;
+        rs1 += e1;
       }
+      const float rs = rs0 + rs1;
       l_sum = l_sum * factor + rs;
       if (j > 0) {
         mbar_wait(bar_o, (j - 1) & 1);  // PV_{j-1} retired: P buffer reusable, O stable
@@ -491,8 +500,8 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           const int cc = half * 32 + c;
-          float p0 = exp2f(__uint_as_float(s[c]) * p.scale_log2 - st[cc]);
-          float p1 = exp2f(__uint_as_float(s[c + 1]) * p.scale_log2 - st[cc + 1]);
+          float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -st[cc]));
+          float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -st[cc + 1]));
           if (cc >= q_left) p0 = 0.f;
           if (cc + 1 >= q_left) p1 = 0.f;
           const float d0 = p0 * (__uint_as_float(dp[c]) - st[64 + cc]) * p.scale;
@@ -696,8 +705,8 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           const int cc = half * 32 + c;
-          float p0 = exp2f(__uint_as_float(s[c]) * p.scale_log2 - lse);
-          float p1 = exp2f(__uint_as_float(s[c + 1]) * p.scale_log2 - lse);
+          float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse));
+          float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -lse));
           if (cc >= kv_left) p0 = 0.f;
           if (cc + 1 >= kv_left) p1 = 0.f;
           ds[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dl) * p.scale,

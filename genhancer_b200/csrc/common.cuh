@@ -456,6 +456,12 @@ __device__ __forceinline__ void act_bwd_mul8(int act, const float (&x)[8], float
   }
 }
 
+// bare MUFU.EX2 (exp2f without fast-math adds a denormal-range rescale: 2 FMUL + FSETP + FSEL per call)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -233,7 +233,12 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
   }
   // lean epilogue through [32 rows x 64 columns] SWIZZLE_128B tiles: TMA store of D, TMA load of the residual
   static const int no_tma_epi = [] { const char* e = getenv("GH_GEMM_NO_TMA_EPI"); return e ? atoi(e) : 0; }();
-  p.ep.tma = p.ep.fast && !no_tma_epi && batch == 1 && (!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0);
+  // act_grad (dY of an MLP's fc1 = (dH W2) * act'(pre)) rides the same path: the saved pre-activation tile arrives by
+  // TMA where the residual tile would, for the two activations the path trains through (GELU-tanh, QuickGELU)
+  const bool lean_actgrad = a->act_grad && (a->act == GH_ACT_GELU_TANH || a->act == GH_ACT_QUICK_GELU) && p.ep.vec8 &&
+                            a->d_dtype == GH_BF16 && !a->aux_out && !a->gate && !a->residual && a->k_splits == 0;
+  p.ep.tma = (p.ep.fast || lean_actgrad) && !no_tma_epi && batch == 1 &&
+             (!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0);
   tm[4] = tm[0];
   tm[5] = tm[0];
   if (p.ep.tma) {
@@ -241,7 +246,10 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
     uint32_t box[2] = {64, 32};
     uint64_t sd[1] = {static_cast<uint64_t>(a->ldd) * 2};
     if (int e = make_tmap_bf16(&tm[4], a->d, 2, dims, sd, box, nullptr)) return e;
-    if (a->residual) {
+    if (a->act_grad) {
+      uint64_t sr[1] = {static_cast<uint64_t>(a->ld_aux_in) * 2};
+      if (int e = make_tmap_bf16(&tm[5], a->aux_in, 2, dims, sr, box, nullptr)) return e;
+    } else if (a->residual) {
       uint64_t sr[1] = {static_cast<uint64_t>(a->ld_res) * 2};
       if (int e = make_tmap_bf16(&tm[5], a->residual, 2, dims, sr, box, nullptr)) return e;
     }

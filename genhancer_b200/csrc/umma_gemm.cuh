@@ -348,7 +348,9 @@ __device__ __forceinline__ void lean_tile(const EpilogueParams& ep, float* __res
 // the same buffer, read-modify-write in place).  Replaces ~32 partial-line STG wavefronts per 16-column slice.
 // Warp (quad, half) owns rows 32*quad.. and the 64-column groups half, half+2, ...
 // ----------------------------------------------------------------------------------------------------------
-template <int BN, int ACT, bool HAS_RES>
+// RM = 0: no second tile; 1: + bf16 residual; 2: act_grad -- the tile is aux_in (the saved pre-activation) and the
+// result is (alpha*acc + bias) * ACT'(aux_in): the dgrad through a GELU / QuickGELU MLP (fc1's dY) on the lean path.
+template <int BN, int ACT, int RM>
 __device__ __forceinline__ void lean_tile_tma(const EpilogueParams& ep, const CUtensorMap* tmap_d, const CUtensorMap* tmap_r,
                                               uint8_t* stg, uint64_t* res_bar, uint32_t& res_phase, int& buf,
                                               uint32_t t_row, int half, int lane, int row0, int n0, int N,
@@ -365,7 +367,7 @@ __device__ __forceinline__ void lean_tile_tma(const EpilogueParams& ep, const CU
     // the bulk store that last read this buffer must be done with it (one other group may still be in flight)
     if (elect_one()) bulk_wait_group_read<1>();
     __syncwarp();
-    if (HAS_RES) {
+    if (RM != 0) {
       if (elect_one()) {
         mbar_arrive_expect_tx(res_bar, 4096u);
         tma_load_2d(tile, tmap_r, res_bar, gn, row0);
@@ -397,24 +399,32 @@ __device__ __forceinline__ void lean_tile_tma(const EpilogueParams& ep, const CU
         v1[k] = fmaf(__uint_as_float(treg[8 + k]), alpha, b[8 + k]);
       }
       if (c + 1 < 4) tmem_ld_32x16(t_row + g * 64 + (c + 1) * 16, treg);   // next chunk in flight during the math
-      if (ACT != ACT_NONE) {
+      if (ACT != ACT_NONE && RM != 2) {
         act_fwd8(ACT, v0);
         act_fwd8(ACT, v1);
       }
       uint4* p0 = reinterpret_cast<uint4*>(rowp + (((2 * c) ^ sw) << 4));
       uint4* p1 = reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ sw) << 4));
-      if (HAS_RES) {
+      if (RM != 0) {
         if (c == 0) {
           mbar_wait(res_bar, res_phase);
           res_phase ^= 1u;
         }
         float r[8];
         unpack8(*p0, r);
+        if (RM == 2) {
+          act_bwd_mul8(ACT, r, v0);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v0[k] += r[k];
+          for (int k = 0; k < 8; ++k) v0[k] += r[k];
+        }
         unpack8(*p1, r);
+        if (RM == 2) {
+          act_bwd_mul8(ACT, r, v1);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v1[k] += r[k];
+          for (int k = 0; k < 8; ++k) v1[k] += r[k];
+        }
       }
       uint4 o;
       o.x = pack_bf16x2(v0[0], v0[1]); o.y = pack_bf16x2(v0[2], v0[3]);
@@ -684,7 +694,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool tma_epi = MODE == MODE_GEMM && p.ep.tma != 0;
     if (tma_epi && lane == 0) {
       tma_prefetch_desc(&tmap_d);
-      if (p.ep.residual) tma_prefetch_desc(&tmap_r);
+      if (p.ep.residual || p.ep.act_grad) tma_prefetch_desc(&tmap_r);
     }
     const int sub_row = lane & 15;        // 8 consecutive lanes read 8 consecutive staged rows: conflict-free
     const int col8 = (lane >> 4) * 8;
@@ -756,21 +766,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #define GH_LEANT(A, R) \
   lean_tile_tma<BN, A, R>(ep, &tmap_d, &tmap_r, stg, &res_bars[ew], res_phase, stg_buf, t_row, half, lane, row0, n0, p.N, breg)
         if (row0 < p.M) {
-          if (ep.residual) {
+          if (ep.act_grad) {   // (the host only routes GELU-tanh and QuickGELU here: the DiT's and the ViT's MLPs)
+            if (ep.act == ACT_GELU_TANH) GH_LEANT(ACT_GELU_TANH, 2);
+            else GH_LEANT(ACT_QUICK_GELU, 2);
+          } else if (ep.residual) {
             switch (ep.act) {
-              case ACT_GELU_TANH: GH_LEANT(ACT_GELU_TANH, true); break;
-              case ACT_QUICK_GELU: GH_LEANT(ACT_QUICK_GELU, true); break;
-              case ACT_SILU: GH_LEANT(ACT_SILU, true); break;
-              case ACT_GELU_ERF: GH_LEANT(ACT_GELU_ERF, true); break;
-              default: GH_LEANT(ACT_NONE, true); break;
+              case ACT_GELU_TANH: GH_LEANT(ACT_GELU_TANH, 1); break;
+              case ACT_QUICK_GELU: GH_LEANT(ACT_QUICK_GELU, 1); break;
+              case ACT_SILU: GH_LEANT(ACT_SILU, 1); break;
+              case ACT_GELU_ERF: GH_LEANT(ACT_GELU_ERF, 1); break;
+              default: GH_LEANT(ACT_NONE, 1); break;
             }
           } else {
             switch (ep.act) {
-              case ACT_GELU_TANH: GH_LEANT(ACT_GELU_TANH, false); break;
-              case ACT_QUICK_GELU: GH_LEANT(ACT_QUICK_GELU, false); break;
-              case ACT_SILU: GH_LEANT(ACT_SILU, false); break;
-              case ACT_GELU_ERF: GH_LEANT(ACT_GELU_ERF, false); break;
-              default: GH_LEANT(ACT_NONE, false); break;
+              case ACT_GELU_TANH: GH_LEANT(ACT_GELU_TANH, 0); break;
+              case ACT_QUICK_GELU: GH_LEANT(ACT_QUICK_GELU, 0); break;
+              case ACT_SILU: GH_LEANT(ACT_SILU, 0); break;
+              case ACT_GELU_ERF: GH_LEANT(ACT_GELU_ERF, 0); break;
+              default: GH_LEANT(ACT_NONE, 0); break;
             }
           }
         }

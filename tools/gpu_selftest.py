@@ -178,7 +178,7 @@ def batched_cases():
     """gh_gemm_bf16 batch mode (the AE mid-block attention, autoencoder.py:37-52) against torch.bmm, and the split-K
     dgrad of a 32-row Modulation (layers.py:169-175) against a plain matmul."""
     g = torch.Generator(device="cuda").manual_seed(11)
-    for (Bn, L, C) in [(3, 1764, 512), (5, 200, 64), (32, 441, 128), (2, 128, 256)]:
+    for (Bn, L, C) in [(3, 1764, 512), (5, 200, 64), (32, 444, 128), (2, 128, 256)]:
         qkv = (torch.randn(Bn * L, 3 * C, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
         q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
         s = K.gemm(q, k, out_dtype=torch.float32, batch=Bn)                       # [Bn*L, L]
@@ -264,6 +264,9 @@ def main():
         gemm_case(300, 512, 256, bias=True, act=4)
         gemm_case(300, 512, 256, bias=True, act=1, aux_out=True)
         gemm_case(300, 512, 256, act=1, act_grad=True)
+        gemm_case(300, 512, 256, act=2, act_grad=True)             # lean TMA epilogue with the aux_in tile
+        gemm_case(1000, 768, 320, bias=True, act=1, act_grad=True)
+        gemm_case(300, 512, 256, act=4, act_grad=True)             # SiLU': general path
         gemm_case(300, 512, 256, bias=True, gate=100, residual=True)
         gemm_case(300, 512, 256, bias=True, f32=True)
     if "lora" in which:
