@@ -274,12 +274,50 @@ def run_ours(args):
     # ---- end-to-end arm: pinned host batch -> H2D -> step -> loss read back, every step ------------------------
     last = {}
 
-    def e2e_step(i):
-        img = host_batches[i % pool].to(dev, non_blocking=True)
-        last["loss"] = train_step(img).item()
+    # Input pipeline of the public API as a user would drive it: the pinned batch of step i+1 is copied on a copy
+    # stream while step i computes (two device staging buffers), and the loss of step i-1 is read back after step i
+    # has been enqueued -- every step still pays its own H2D copy and its own D2H read inside the timed region, they
+    # just do not serialise with the compute stream.
+    copy_stream = torch.cuda.Stream()
+    staged = [torch.empty_like(dev_batches[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]      # H2D of the buffer finished
+    consumed = [torch.cuda.Event() for _ in range(2)]   # the step that read the buffer has been enqueued past its read
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event() for _ in range(2)]
+    e2e_n = {"steps": args.steps}
 
-    for i in range(min(2, args.warmup)):
+    def stage(i):
+        k = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k])
+            staged[k].copy_(host_batches[i % pool], non_blocking=True)
+            ready[k].record(copy_stream)
+
+    def e2e_step(i):
+        k = i % 2
+        if i == 0:
+            stage(0)
+        torch.cuda.current_stream().wait_event(ready[k])
+        if i + 1 < e2e_n["steps"]:
+            stage(i + 1)
+        loss = train_step(staged[k])
+        consumed[k].record()
+        loss_host[k].copy_(loss.detach().float(), non_blocking=True)
+        loss_done[k].record()
+        if i > 0:
+            loss_done[1 - k].synchronize()
+            last["loss"] = float(loss_host[1 - k])
+        if i + 1 == e2e_n["steps"]:
+            loss_done[k].synchronize()
+            last["loss"] = float(loss_host[k])
+
+    for ev in consumed:
+        ev.record()
+    e2e_n["steps"] = min(2, args.warmup)
+    for i in range(e2e_n["steps"]):
         e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_n["steps"] = args.steps
     ms_e2e = timed(e2e_step, args.steps)
 
     # ---- roofline pass: the same step EAGER with CUDA events around every tcgen05 GEMM / conv launch (events cannot

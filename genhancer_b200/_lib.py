@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgenhancer_b200.so")
+LIB_PATH = os.environ.get("GH_LIB_PATH") or os.path.join(_HERE, "libgenhancer_b200.so")   # (override: A/B builds)
 
 GH_BF16, GH_F32 = 0, 1
 ACT_NONE, ACT_GELU_TANH, ACT_QUICK_GELU, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3, 4
@@ -84,6 +84,7 @@ SIGNATURES: dict[str, list] = {
     "gh_version": [],
     "gh_init": [C.c_int],
     "gh_set_sm_budget": [C.c_int],
+    "gh_set_tile_scheduler": [C.c_int],
     "gh_gemm_bf16": [C.POINTER(GemmArgs), _vp],
     "gh_debug_gemm_prof": [_vp],
     "gh_fm_interp_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _vp],

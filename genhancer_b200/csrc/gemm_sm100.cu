@@ -1,10 +1,18 @@
 // genhancer_b200 -- gh_gemm_bf16: host launcher of the tcgen05 GEMM (see umma_gemm.cuh).
+#include <atomic>
 #include <cstdlib>
 
 #include "internal.h"
 #include "umma_gemm.cuh"
 
 namespace gh {
+
+// dynamic tile schedule (gh_set_tile_scheduler): a pool of {next tile, workers done} counter pairs, one per launch in
+// rotation, so launches on different streams never share a pair; a kernel hands its pair back zeroed
+static constexpr unsigned TILE_CTR_SLOTS = 1024;
+static int* g_tile_ctrs = nullptr;
+static int g_tile_dynamic = 0;
+static std::atomic<unsigned> g_tile_ctr_next{0};
 
 template <int BN, bool A_MN, bool B_MN>
 static int set_attr() {
@@ -18,6 +26,11 @@ static int set_attr() {
 }
 
 int gemm_init() {
+  if (g_tile_ctrs == nullptr) {
+    GH_CHECK_CUDA(cudaMalloc(&g_tile_ctrs, TILE_CTR_SLOTS * 2 * sizeof(int)));
+    GH_CHECK_CUDA(cudaMemset(g_tile_ctrs, 0, TILE_CTR_SLOTS * 2 * sizeof(int)));
+  }
+  if (const char* e = getenv("GH_TILE_SCHEDULER")) g_tile_dynamic = atoi(e) != 0;
 #define GH_SET(BN)                                   \
   if (int e = set_attr<BN, false, false>()) return e; \
   if (int e = set_attr<BN, false, true>()) return e;  \
@@ -174,6 +187,7 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
   p.num_m_blocks = (a->M + 127) / 128;
   p.num_n_blocks = (a->N + bn - 1) / bn;
   p.num_k_blocks = (a->K + 63) / 64;
+  p.tile_ctr = (g_tile_dynamic && g_tile_ctrs) ? g_tile_ctrs + 2 * (g_tile_ctr_next.fetch_add(1) % TILE_CTR_SLOTS) : nullptr;
   p.batch = batch;
   p.a_boff = static_cast<int>(a->a_batch_rows); p.b_boff = static_cast<int>(a->b_batch_rows);
   p.d_brows = static_cast<int>(a->d_batch_rows);
@@ -260,6 +274,11 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
     case 128: return dispatch_major<128>(tc.pair, amn, bmn, tm, p, s);
     default: return dispatch_major<64>(false, amn, bmn, tm, p, s);
   }
+}
+
+extern "C" int gh_set_tile_scheduler(int dynamic) {
+  gh::g_tile_dynamic = dynamic != 0;
+  return GH_OK;
 }
 
 extern "C" int gh_debug_gemm_prof(void* device_buf) {

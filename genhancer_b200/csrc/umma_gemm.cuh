@@ -77,6 +77,12 @@ struct GemmParams {
   // zero fill at the end of the tensor) and are masked by the epilogue; an overrun along K of a K-major operand is
   // zero-filled because the tensor map's K extent is the per-problem K.  batch = 1: plain GEMM.
   int batch, a_boff, b_boff, d_brows;
+  // Dynamic tile schedule (GEMM mode; NULL = the static schedule tile = worker + i * #workers).  tile_ctr[0] hands out
+  // tile indices (atomicAdd), tile_ctr[1] counts workers that ran dry; the last one zeroes both for the next launch.
+  // For data-parallel training: NCCL's all-reduce kernels hold some SMs while the backward GEMMs run, so a few CTAs
+  // of a persistent grid start a whole wave late -- with the static schedule they still owe their full share of
+  // tiles and the GEMM takes twice as long; with the dynamic one they find the queue (nearly) empty and leave.
+  int* tile_ctr;
   uint32_t a_stage_tx_bytes;  // bytes TMA deposits for the A tile of one stage
   uint32_t mn_lbo, mn_sbo, mn_kstep;  // MN-major descriptor geometry (bytes); see common.cuh
   EpilogueParams ep;
@@ -106,7 +112,7 @@ struct GemmCfg {
   static constexpr int EPI_WARP_BYTES = 8192;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_LIMIT = 227 * 1024;
   static constexpr int STAGES_FIT = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
@@ -473,8 +479,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
   uint64_t* res_bars = bars + 2 * STAGES + 4;   // [EPI_WARPS] residual tiles of the TMA epilogue
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + Cfg::EPI_WARPS);
-  static_assert((2 * STAGES + 4 + Cfg::EPI_WARPS) * 8 + 4 <= Cfg::BAR_BYTES, "barrier block too small");
+  uint64_t* tq_full = bars + 2 * STAGES + 4 + Cfg::EPI_WARPS;   // [2] dynamic tile queue: entry published
+  uint64_t* tq_empty = tq_full + 2;                             // [2] entry read by every consumer warp (leader's copy)
+  int* tile_q = reinterpret_cast<int*>(tq_empty + 2);           // [2] tile index or -1 (no more tiles)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tile_q + 2);
+  static_assert((2 * STAGES + 4 + Cfg::EPI_WARPS + 4) * 8 + 8 + 4 <= Cfg::BAR_BYTES, "barrier block too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -502,6 +511,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     mbar_init(&tempty_bar[0], Cfg::EPI_WARPS * (CTA2 ? 2 : 1));  // one arrive per epilogue warp (of both CTAs)
     mbar_init(&tempty_bar[1], Cfg::EPI_WARPS * (CTA2 ? 2 : 1));
     for (int w = 0; w < Cfg::EPI_WARPS; ++w) mbar_init(&res_bars[w], 1);
+    // consumers of a tile-queue entry: producer + issuer + epilogue warps of the leader, producer + epilogue warps of the peer
+    mbar_init(&tq_full[0], 1);
+    mbar_init(&tq_full[1], 1);
+    mbar_init(&tq_empty[0], CTA2 ? 2 * Cfg::EPI_WARPS + 3 : Cfg::EPI_WARPS + 2);
+    mbar_init(&tq_empty[1], CTA2 ? 2 * Cfg::EPI_WARPS + 3 : Cfg::EPI_WARPS + 2);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -514,14 +528,73 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  // the it-th tile of this worker (CTA or CTA pair), or -1: static stride schedule, or the next entry of the dynamic
+  // queue that warp 3 of the (leader) CTA fills from the global counter
+#ifdef GH_NO_DYNAMIC_TILES   // A/B builds: compile the dynamic schedule out
+  constexpr bool dyn = false;
+#else
+  const bool dyn = MODE == MODE_GEMM && p.tile_ctr != nullptr;
+#endif
+  const uint32_t tq_empty_leader[2] = {CTA2 ? mapa_u32(smem_u32(&tq_empty[0]), 0u) : 0u,
+                                       CTA2 ? mapa_u32(smem_u32(&tq_empty[1]), 0u) : 0u};
+  auto fetch_tile = [&](int it) -> int {
+    if (!dyn) {
+      const int t = worker + it * num_workers;
+      return t < num_tiles ? t : -1;
+    }
+    const int slot = it & 1;
+    const uint32_t ph = static_cast<uint32_t>(it >> 1) & 1u;
+    if (CTA2) mbar_wait_cluster(&tq_full[slot], ph);
+    else mbar_wait(&tq_full[slot], ph);
+    const int t = *reinterpret_cast<volatile int*>(&tile_q[slot]);
+    __syncwarp();
+    if (lane == 0) {
+      if (CTA2) mbar_arrive_cluster(tq_empty_leader[slot]);
+      else mbar_arrive(&tq_empty[slot]);
+    }
+    return t;
+  };
+
+  if (warp == 3 && rank == 0 && dyn) {
+    // ===================== tile scheduler (dynamic mode) =====================
+    for (int it = 0;; ++it) {
+      const int slot = it & 1;
+      const uint32_t ph = static_cast<uint32_t>(it >> 1) & 1u;
+      if (CTA2) mbar_wait_cluster(&tq_empty[slot], ph ^ 1u);   // every consumer has read the entry of round it - 2
+      else mbar_wait(&tq_empty[slot], ph ^ 1u);
+      int t = 0;
+      if (lane == 0) {
+        t = atomicAdd(p.tile_ctr, 1);
+        if (t >= num_tiles) t = -1;
+        *reinterpret_cast<volatile int*>(&tile_q[slot]) = t;
+        if (CTA2) {
+          st_shared_cluster_u32(mapa_u32(smem_u32(&tile_q[slot]), 1u), static_cast<uint32_t>(t));
+          mbar_arrive_cluster(mapa_u32(smem_u32(&tq_full[slot]), 1u));   // release.cluster: orders the store above
+        }
+        mbar_arrive(&tq_full[slot]);
+      }
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t < 0) {
+        if (lane == 0) {
+          const int done = atomicAdd(p.tile_ctr + 1, 1);
+          if (done == num_workers - 1) {   // every worker has made its last fetch: hand the counters back zeroed
+            p.tile_ctr[0] = 0;
+            p.tile_ctr[1] = 0;
+          }
+        }
+        break;
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
     long long w_slot = 0;
     const uint32_t tx_bytes = (p.a_stage_tx_bytes + Cfg::B_BYTES) * (CTA2 ? 2u : 1u);
     constexpr int BNL = CTA2 ? BN / 2 : BN;            // B rows this CTA loads
-    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    for (int it = 0;; ++it) {
+      const int tile = fetch_tile(it);
+      if (tile < 0) break;
       int m_blk, n_blk;
       const int bi = (MODE == MODE_GEMM && p.batch > 1) ? tile / tiles_pb : 0;
       const int ptile = tile - bi * tiles_pb;
@@ -619,7 +692,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t acc_phase = 0;
     long long w_full = 0, w_acc = 0, n_tiles = 0;
     const long long t_begin = p.prof ? clock64() : 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    for (int it = 0;; ++it) {
+      const int tile = fetch_tile(it);
+      if (tile < 0) break;
       if (p.prof) {
         const long long t0 = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -705,7 +780,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const long long e_begin = p.prof ? clock64() : 0;
     const uint32_t tempty_leader[2] = {CTA2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0u) : 0u,
                                        CTA2 ? mapa_u32(smem_u32(&tempty_bar[1]), 0u) : 0u};
-    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    for (int it = 0;; ++it) {
+      const int tile = fetch_tile(it);
+      if (tile < 0) break;
       int m_blk, n_blk;
       decode_tile(tile % tiles_mn, m_units, p.num_n_blocks, m_blk, n_blk);
       if (CTA2) m_blk = m_blk * 2 + static_cast<int>(rank);

@@ -28,6 +28,11 @@ class GradReducer:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.bucket_cap_bytes = bucket_cap_bytes
         self.enabled = True          # False on gradient-accumulation micro-steps that do not synchronise
+        # While buckets are in flight NCCL's kernels hold some SMs: the persistent GEMM grids switch to the dynamic
+        # tile schedule (gh_set_tile_scheduler) from the first bucket until wait(), so CTAs that start late find the
+        # tile queue drained instead of owing a full static share (CUDA tensors only; the CPU tests run on gloo).
+        self.dynamic_tiles = bool(groups) and groups[0].flat_g.is_cuda
+        self._dyn_on = False
         self._works = []
         self._done: dict[int, list[tuple[int, int]]] = {}
         self.log: list[tuple[str, int, int]] = []   # (prefix, lo, hi) in issue order, for tests / tracing
@@ -54,6 +59,8 @@ class GradReducer:
         if hi <= lo:
             return
         self._done.setdefault(gi, []).append((lo, hi))
+        if self.dynamic_tiles and not self._dyn_on:
+            self._set_dynamic(True)
         cap = max(1, self.bucket_cap_bytes // g.flat_g.element_size())
         for s in range(lo, hi, cap):
             e = min(hi, s + cap)
@@ -88,6 +95,13 @@ class GradReducer:
             w.wait()
         self._works.clear()
         self._done.clear()
+        if self._dyn_on:
+            self._set_dynamic(False)
+
+    def _set_dynamic(self, on: bool) -> None:
+        from . import _lib
+        _lib.check(_lib.lib().gh_set_tile_scheduler(int(on)))
+        self._dyn_on = on
 
     def finish(self) -> None:
         """``issue_rest()`` + ``wait()``.  The data-parallel loops call the two halves separately: the rest is issued

@@ -44,6 +44,13 @@ int gh_init(int device);
  * few SMs to the concurrent NCCL all-reduce kernels: a persistent grid that finds some SMs taken runs its last CTAs as
  * a second wave (accelerate / DeepSpeed have no analogue: their GEMMs are not persistent). */
 int gh_set_sm_budget(int sms);
+/* Tile schedule of the persistent tcgen05 GEMM grids launched from now on: 0 = static (tile = worker + i * #workers,
+ * the default: no atomics, no start-up latency), 1 = dynamic (each CTA / CTA pair pulls its next tile from a global
+ * counter through a 2-deep queue in shared memory).  Data-parallel training switches to dynamic for the backward,
+ * during which NCCL's all-reduce kernels hold some SMs: CTAs of a persistent grid that start a wave late then find the
+ * queue drained instead of owing a full static share of the tiles (which doubled the GEMM's duration).  Results are
+ * identical (each tile is computed by exactly one worker; only the assignment changes). */
+int gh_set_tile_scheduler(int dynamic);
 
 /* --------------------------------------------------------------------------
  * gh_gemm_bf16 -- tcgen05/TMEM GEMM fed by TMA, fused epilogue.

@@ -27,7 +27,7 @@ def _run(modname, groups):
     return lines
 
 
-@pytest.mark.parametrize("group", ["fm", "gemm", "mn", "epi", "lora", "batched"])
+@pytest.mark.parametrize("group", ["fm", "gemm", "mn", "epi", "lora", "batched", "dyn"])
 def test_gemm_and_flow_matching_kernels(group):
     _run("tools.gpu_selftest", [group])
 

@@ -45,7 +45,10 @@ def main():
         batches.append(torch.rand(B, 3, S, S, device=dev, generator=gen))
     L = _lib.lib()
 
-    def run(max_ctas, budget, deferred, bucket_mb=256, steps=6, warm=3, comm=True):
+    from genhancer_b200.graph import GraphedMicroStep
+    graphs = []
+
+    def run(max_ctas, budget, deferred=False, bucket_mb=256, steps=6, warm=3, comm=True, graph=True, dyn=1):
         pg = None
         if max_ctas:
             o = dist.ProcessGroupNCCL.Options()
@@ -54,6 +57,8 @@ def main():
             pg = dist.new_group(backend="nccl", pg_options=o)
         reducer = GradReducer(groups, engine_modules=[dit], process_group=pg, bucket_cap_bytes=bucket_mb << 20)
         reducer.enabled = comm
+        reducer.dynamic_tiles = dyn == 1      # 1: dynamic tile schedule while buckets are in flight; 2: always; 0: never
+        L.gh_set_tile_scheduler(1 if dyn == 2 else 0)
         gscale = 1.0 / world
         L.gh_set_sm_budget(budget)
         pend = {"n": 0}
@@ -65,18 +70,28 @@ def main():
                 opt.zero_grad()
                 pend["n"] = 0
 
-        def one(img):
-            if deferred:
-                loss = step(img, before_trainable=flush)
-                loss.backward()
-                reducer.issue_rest()
-                pend["n"] = 1
-            else:
-                loss = step(img)
-                loss.backward()
-                reducer.finish()
+        if graph:
+            opt.zero_grad()
+            gm = GraphedMicroStep(step, batches[0], prepare=opt.zero_grad, after_backward=reducer.finish)
+            graphs.append(gm)
+
+            def one(img):
+                gm(img)
                 opt.step(gscale)
                 opt.zero_grad()
+        else:
+            def one(img):
+                if deferred:
+                    loss = step(img, before_trainable=flush)
+                    loss.backward()
+                    reducer.issue_rest()
+                    pend["n"] = 1
+                else:
+                    loss = step(img)
+                    loss.backward()
+                    reducer.finish()
+                    opt.step(gscale)
+                    opt.zero_grad()
 
         for i in range(warm):
             one(batches[i % 4])
@@ -91,30 +106,52 @@ def main():
         torch.cuda.synchronize()
         flush()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        mine = e0.elapsed_time(e1) / steps
+        ms = torch.tensor([mine], device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        lo = torch.tensor([mine], device=dev)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         L.gh_set_sm_budget(0)
+        L.gh_set_tile_scheduler(0)
         dit._on_grads_ready = None
-        row = dict(max_ctas=max_ctas, sm_budget=budget, deferred=deferred, bucket_mb=bucket_mb, comm=comm,
-                   ms_per_step=round(float(ms), 3), img_s=round(world * B / float(ms) * 1e3, 1))
+        if graph:           # a graph keeps its own ~35 GB activation pool: release it before the next configuration
+            graphs.remove(gm)
+            gm.graph.reset()
+            del gm, one
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+        row = dict(max_ctas=max_ctas, sm_budget=budget, deferred=deferred, bucket_mb=bucket_mb, comm=comm, graph=graph, dyn=dyn,
+                   ms_per_step=round(float(ms), 3), ms_fastest_rank=round(float(lo), 3),
+                   img_s=round(world * B / float(ms) * 1e3, 1))
         if rank == 0:
             print(json.dumps(row), flush=True)
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"dp_sweep_n{world}.jsonl"), "a") as f:
+                f.write(json.dumps(row) + "\n")
         return row
 
     rows = []
-    rows.append(run(0, 0, False, comm=False))          # no exchange at all: the compute floor of the eager step
-    rows.append(run(0, 0, False))                      # what round 1 measured so far (NCCL defaults)
-    rows.append(run(0, 0, True))
-    for ctas, budget in ((8, 0), (8, 132), (4, 0), (4, 140), (2, 0), (2, 144), (1, 146), (1, 0)):
-        rows.append(run(ctas, budget, True))
-    rows.append(run(4, 140, True, bucket_mb=64))
-    rows.append(run(2, 144, False))
-    if rank == 0:
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"dp_sweep_n{world}.jsonl"), "w") as f:
-            for r in rows:
-                f.write(json.dumps(r) + "\n")
+    rows.append(run(0, 0, comm=False, dyn=0))          # no exchange at all: the compute floor (max / min over ranks)
+    rows.append(run(0, 0, comm=False, dyn=2))          # ... with the dynamic tile schedule everywhere
+    rows.append(run(0, 0, dyn=0))                      # NCCL defaults, static schedule (round-1 state so far)
+    rows.append(run(0, 0, dyn=1))                      # dynamic schedule while buckets are in flight
+    rows.append(run(0, 0, dyn=2))
+    quick = os.environ.get("DP_SWEEP_QUICK", "0") == "1"
+    if not quick:
+        rows.append(run(16, 0, dyn=1))
+        rows.append(run(8, 0, dyn=1))
+        rows.append(run(0, 0, dyn=1, bucket_mb=64))
+    rows.append(run(0, 0, graph=False, deferred=True, dyn=1))
+    sys.stdout.flush()
+    import threading
+    threading.Timer(30.0, lambda: os._exit(0)).start()
+    for gm in graphs:       # NCCL will not tear a communicator down while a captured graph holds its kernels
+        gm.graph.reset()
+    dist.barrier()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
+    os._exit(0)
 
 
 if __name__ == "__main__":

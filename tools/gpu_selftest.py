@@ -297,6 +297,22 @@ def main():
         copy_table_cases()
     if "batched" in which:
         batched_cases()
+    if "dyn" in which:
+        # dynamic tile schedule (gh_set_tile_scheduler): same results, counters hand themselves back zeroed (repeat)
+        from genhancer_b200 import _lib
+        _lib.lib().gh_set_tile_scheduler(1)
+        try:
+            for rep in range(3):
+                gemm_case(3000, 3072, 1024)                          # CTA pairs, several tiles per pair
+                gemm_case(14112, 3072, 512, bias=True, act=1)        # > 1 wave of 256-row pair tiles
+                gemm_case(200, 328, 588, pad=4)                      # single CTAs, fewer tiles than SMs
+                gemm_case(1000, 3072, 784, b_mn=True)
+                gemm_case(304, 520, 328, a_mn=True, b_mn=True)
+                gemm_case(300, 512, 256, bias=True, gate=100, residual=True)
+            batched_cases()
+        finally:
+            _lib.lib().gh_set_tile_scheduler(0)
+        gemm_case(3000, 3072, 1024)
     if "time" in which:
         time_gemm(4096, 4096, 4096)
         time_gemm(8192, 8192, 8192)
