@@ -342,6 +342,10 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
             dattn[s] = _lin_bwd(du1.view(-1, C), attn.view(-1, C), f"{p}.{s}_attn.proj.weight",
                                 f"{p}.{s}_attn.proj.bias", P, sink).view(B, rpb, C)
             dx_mid[s] = dxm
+            if bi == 0:
+                # the LAST block of the backward: announce its sub-modules as their gradients become final, so the
+                # exposed tail of the data-parallel exchange is one Modulation's worth instead of the whole block
+                sink.flush(f"{p}.{s}_mlp.")
         dq = torch.empty(B, H, L, D, dtype=BF16, device=dev)
         dk = torch.empty_like(dq)
         dv = torch.empty_like(dq)
@@ -357,8 +361,12 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
                                sink.small(f"{p}.{s}_attn.norm.key_norm.scale"))
             h = S[f"{p}.{s}_norm1.h"]
             dh = _lin_bwd(dqkv.view(-1, 3 * C), h.view(-1, C), f"{p}.{s}_attn.qkv.weight", f"{p}.{s}_attn.qkv.bias", P, sink)
+            if bi == 0:
+                sink.flush(f"{p}.{s}_attn.")
             dxs[s] = adaln_bwd(f"{p}.{s}_norm1", dh.view(B, rpb, C), m, 0, dmods[s], dres=dx_mid[s])
             mod_bwd(dmods[s], f"{p}.{s}_mod.lin.weight", f"{p}.{s}_mod.lin.bias")
+            if bi == 0:
+                sink.flush(f"{p}.{s}_mod.")
         sink.flush(p + ".")
 
     # ---- input projections and the conditioning vector ----

@@ -43,6 +43,9 @@ class GradReducer:
 
     # ---- called from the backward schedule -------------------------------------------------------------
     def on_ready(self, prefix: str) -> None:
+        """Every gradient whose parameter name starts with ``prefix`` is final: all-reduce the part of that range
+        that has not been issued yet (prefixes may nest: the last block announces its sub-modules one by one so that
+        only a small tail of the exchange is left when the backward ends, then the whole block)."""
         if not self.enabled or self.world == 1:
             return
         for gi, g in enumerate(self.groups):
@@ -53,7 +56,7 @@ class GradReducer:
                 continue
             rng = g.range_of(prefix)
             if rng is not None:
-                self._issue(gi, g, rng[0], rng[1], prefix)
+                self._reduce_rest(gi, g, prefix, rng[0], rng[1])
 
     def _issue(self, gi: int, g: FlatGroup, lo: int, hi: int, prefix: str) -> None:
         if hi <= lo:
@@ -67,19 +70,21 @@ class GradReducer:
             self.log.append((prefix, s, e))
             self._works.append(dist.all_reduce(g.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
-    def _reduce_rest(self, gi: int, g: FlatGroup, prefix: str = "") -> None:
-        """All-reduce every slice of group ``gi`` that has not been reduced yet."""
-        done = sorted(self._done.get(gi, []))
-        cur = 0
+    def _reduce_rest(self, gi: int, g: FlatGroup, prefix: str = "", lo: int = 0, hi: int | None = None) -> None:
+        """All-reduce every slice of [lo, hi) of group ``gi`` (default: the whole group) not reduced yet."""
+        hi = g.numel if hi is None else hi
+        cur = lo
         gaps = []
-        for lo, hi in done:
-            if lo > cur:
-                gaps.append((cur, lo))
-            cur = max(cur, hi)
-        if cur < g.numel:
-            gaps.append((cur, g.numel))
-        for lo, hi in gaps:
-            self._issue(gi, g, lo, hi, prefix or "<rest>")
+        for a, b in sorted(self._done.get(gi, [])):
+            if b <= cur or a >= hi:
+                continue
+            if a > cur:
+                gaps.append((cur, a))
+            cur = max(cur, b)
+        if cur < hi:
+            gaps.append((cur, hi))
+        for a, b in gaps:
+            self._issue(gi, g, a, b, prefix or "<rest>")
 
     # ---- called by the trainer after loss.backward() ---------------------------------------------------
     def issue_rest(self) -> None:

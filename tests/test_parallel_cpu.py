@@ -77,8 +77,9 @@ def _worker(rank, world, port, out):
         g = groups[0]
         g.flat_g.copy_(torch.arange(g.numel, dtype=torch.float32) * (rank + 1))
         # the engine's backward schedule announces blocks in reverse execution order, then "" for the rest
+        # (the last block announces its sub-modules first, then itself: nested prefixes must not reduce twice)
         for prefix in ["final_layer.", "single_blocks.2.", "single_blocks.1.", "single_blocks.0.", "double_blocks.1.",
-                       "double_blocks.0.", ""]:
+                       "double_blocks.0.lin.", "double_blocks.0.scale", "double_blocks.0.", ""]:
             net._on_grads_ready(prefix)
         red.finish()
         expect = torch.arange(g.numel, dtype=torch.float32) * sum(r + 1 for r in range(world))
