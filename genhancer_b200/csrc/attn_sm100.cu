@@ -52,8 +52,21 @@ struct AttnFwdCfg {
   static constexpr int OFF_P = OFF_V + V_BYTES;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-  static constexpr int TMEM_COLS = 256;                 // S: 2 x 64, O: D (<=128)
-  static constexpr int TM_S = 0, TM_O = 128;
+  // D = 128: S double-buffered (2 x 64 columns) + O (128) = 256 columns, two CTAs per SM.
+  // D = 64 (the ViT towers): the softmax, not the tensor pipe, is the limit (8192 MUFU.EX2 per 64-key block = 512
+  // cycles of the SM's MUFU against 256 of MMA), and with two CTAs per SM the MUFU idled half the time while a CTA
+  // sat in its barrier chain.  S single-buffered + O = 128 columns lets THREE CTAs share an SM (384 of 512 TMEM
+  // columns, 3 x 57 KB of shared memory): what a CTA loses by not overlapping S_{j+1} with softmax_j the third CTA
+  // fills in.
+#ifdef GH_ATTN_FWD_TWO_CTAS   // A/B builds: the double-buffered-S, two-CTA form for every head dim
+  static constexpr bool LEAN64 = false;
+#else
+  static constexpr bool LEAN64 = D == 64;
+#endif
+  static constexpr int S_BUFS = LEAN64 ? 1 : 2;
+  static constexpr int TMEM_COLS = LEAN64 ? 128 : 256;
+  static constexpr int TM_S = 0, TM_O = LEAN64 ? 64 : 128;
+  static constexpr int CTAS_PER_SM = LEAN64 ? 3 : 2;
 };
 
 // write 8 bf16 (16 B) of row r, logical 16-byte chunk c, into a SWIZZLE_128B K-major tile (128 B rows)
@@ -62,7 +75,7 @@ __device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int c, uint4 v) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(160, AttnFwdCfg<D>::CTAS_PER_SM)
 flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
   using Cfg = AttnFwdCfg<D>;
@@ -134,7 +147,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           for (int c = 0; c < DC; ++c)
   #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss(tmem + Cfg::TM_S + (j & 1) * ATT_BKV, umma_desc_at(kdesc, aQ + c * 16384 + k * 32),
+              umma_ss(tmem + Cfg::TM_S + (Cfg::S_BUFS == 2 ? (j & 1) * ATT_BKV : 0), umma_desc_at(kdesc, aQ + c * 16384 + k * 32),
                       umma_desc_at(kdesc, aK + c * 8192 + k * 32), idesc_s, (c | k) != 0 ? 1u : 0u);
           umma_commit(&bar_s[j & 1]);
         }
@@ -152,13 +165,19 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       tc_fence_after();
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {
+        if (Cfg::S_BUFS == 2 && j + 1 < nkv) {
           // S buffer (j+1)&1 was last read by softmax_{j-1}, which arrived on bar_p before we got here
           mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
           tc_fence_after();
           issue_s(j + 1);
         }
-        mbar_wait(bar_p, j & 1);  // P_j is in smem (and O has been rescaled if needed)
+        mbar_wait(bar_p, j & 1);  // P_j is in smem (and O has been rescaled if needed); softmax_j has read S_j
+        if (Cfg::S_BUFS == 1 && j + 1 < nkv) {
+          // single S buffer: S_{j+1} may overwrite S_j now; issued BEFORE PV_j so that softmax_{j+1} starts earlier
+          mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
         mbar_wait(bar_v, j & 1);
         tc_fence_after();
         if (elect_one()) {
@@ -189,8 +208,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       {
         uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
         uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-        tmem_ld_32x32(t_lane + Cfg::TM_S + (j & 1) * ATT_BKV, s0);
-        tmem_ld_32x32(t_lane + Cfg::TM_S + (j & 1) * ATT_BKV + 32, s1);
+        tmem_ld_32x32(t_lane + Cfg::TM_S + (Cfg::S_BUFS == 2 ? (j & 1) * ATT_BKV : 0), s0);
+        tmem_ld_32x32(t_lane + Cfg::TM_S + (Cfg::S_BUFS == 2 ? (j & 1) * ATT_BKV : 0) + 32, s1);
         tmem_ld_wait();
       }
       // ~300 issue slots per 64-key block and thread (it was ~900: a separate scale multiply, a per-element tail mask,
