@@ -351,7 +351,8 @@ def run_ours(args):
     peak_sust, peak_burst, prov = peaks()
     # dram bytes of ONE launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
     try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01c_gemm_ncu_full.json")))
+        import glob
+        ncu = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_ncu_full.json")))[-1]))
     except (OSError, ValueError):
         ncu = {}
     out = {
