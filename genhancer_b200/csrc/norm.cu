@@ -268,18 +268,19 @@ __global__ void __launch_bounds__(512) col_reduce_kernel(const bf16* __restrict_
       }
     };
     int l = l0 + ty, r = r0;
-    for (; l + 3 * ny < l1; l += 4 * ny, r += 4 * ny) {
-      uint4 vd[4], vx[4];
+    constexpr int U = MODE == 2 ? 8 : 4;   // rows in flight per thread (the plain column sum has registers to spare)
+    for (; l + (U - 1) * ny < l1; l += U * ny, r += U * ny) {
+      uint4 vd[U], vx[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         vd[u] = *reinterpret_cast<const uint4*>(pd + u * sd);
         if (MODE != 2) vx[u] = *reinterpret_cast<const uint4*>(px + u * sx);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) one(vd[u], vx[u], r + u * ny, MODE == 1 ? pu + u * su : nullptr);
-      pd += 4 * sd;
-      if (MODE != 2) px += 4 * sx;
-      if (MODE == 1) pu += 4 * su;
+      for (int u = 0; u < U; ++u) one(vd[u], vx[u], r + u * ny, MODE == 1 ? pu + u * su : nullptr);
+      pd += U * sd;
+      if (MODE != 2) px += U * sx;
+      if (MODE == 1) pu += U * su;
     }
     for (; l < l1; l += ny, r += ny) {
       const uint4 vd = *reinterpret_cast<const uint4*>(pd);
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(const bf16* __res
 }
 
 // backward: dq, dk, dv [B,H,Ltot,D] -> dqkv [B,L,3,H,D]; dscale_q/k [D] fp32 accumulated.
-__global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const bf16* __restrict__ dq, const bf16* __restrict__ dk,
+__global__ void __launch_bounds__(256, 3) qk_norm_rope_bwd_kernel(const bf16* __restrict__ dq, const bf16* __restrict__ dk,
                                                                const bf16* __restrict__ dv,
                                                                const bf16* __restrict__ qkv, int64_t ld_qkv, int B,
                                                                int L, int H, int Ltot, int l_off,
@@ -385,64 +386,90 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const bf16* __res
                                                                bf16* __restrict__ dqkv, int64_t ld_dqkv,
                                                                float* __restrict__ dscale_q,
                                                                float* __restrict__ dscale_k, int tokens_per_cta) {
+  // A warp handles TWO heads of one token at a time: 16 lanes per 128-wide head, 8 elements (16 bytes) per lane, so
+  // every load / store is a full 16-byte vector and one 4-step shuffle reduction serves both heads (the first version
+  // used 8-byte accesses, one head per warp and 5-step reductions: issue-bound at 3.2 TB/s).
   constexpr int D = 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __shared__ float red[2][8][D];
-  float acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  const int half = lane >> 4, sl = lane & 15;
+  __shared__ float red[2][16][D];
+  float acc[2][8];
+#pragma unroll
+  for (int w = 0; w < 2; ++w)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[w][j] = 0.f;
+  auto half_sum = [](float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  const int HP = (H + 1) / 2;   // head pairs per token
   const int64_t n_tok = static_cast<int64_t>(B) * L;
   const int64_t t0 = static_cast<int64_t>(blockIdx.x) * tokens_per_cta;
   const int64_t t1 = min(t0 + tokens_per_cta, n_tok);
-  for (int64_t it = t0 * H + warp; it < t1 * H; it += 8) {
-    const int h = static_cast<int>(it % H);
-    const int64_t tok = it / H;
+  float qs[8], ks[8];
+  unpack8(*reinterpret_cast<const uint4*>(q_scale + sl * 8), qs);
+  unpack8(*reinterpret_cast<const uint4*>(k_scale + sl * 8), ks);
+  for (int64_t it = t0 * HP + warp; it < t1 * HP; it += 8) {
+    const int h = 2 * static_cast<int>(it % HP) + half;
+    const bool live = h < H;            // odd H: the upper half of the last pair idles (but joins the shuffles)
+    const int hh = live ? h : H - 1;
+    const int64_t tok = it / HP;
     const int l = static_cast<int>(tok % L);
     const int b = static_cast<int>(tok / L);
-    const bf16* src = qkv + tok * ld_qkv + h * D + lane * 4;
-    bf16* dstp = dqkv + tok * ld_dqkv + h * D + lane * 4;
-    const int64_t hm = ((static_cast<int64_t>(b) * H + h) * Ltot + l_off + l) * D + lane * 4;
-    const float2* csr = cs + b * cs_batch_stride + static_cast<int64_t>(l_off + l) * (D / 2) + lane * 2;
-    const float2 cs0 = csr[0], cs1 = csr[1];
+    const bf16* src = qkv + tok * ld_qkv + hh * D + sl * 8;
+    bf16* dstp = dqkv + tok * ld_dqkv + hh * D + sl * 8;
+    const int64_t hm = ((static_cast<int64_t>(b) * H + hh) * Ltot + l_off + l) * D + sl * 8;
+    const float4* csr = reinterpret_cast<const float4*>(cs + b * cs_batch_stride +
+                                                        static_cast<int64_t>(l_off + l) * (D / 2) + sl * 4);
+    // all loads of the iteration first
+    const float4 c01 = csr[0], c23 = csr[1];   // (cos, sin) of rotation pairs 4 sl .. 4 sl + 3
+    const uint4 gq = *reinterpret_cast<const uint4*>(dq + hm), gk = *reinterpret_cast<const uint4*>(dk + hm);
+    const uint4 gv = *reinterpret_cast<const uint4*>(dv + hm);
+    const uint4 xq = *reinterpret_cast<const uint4*>(src), xk = *reinterpret_cast<const uint4*>(src + H * D);
+    const float cc[4] = {c01.x, c01.z, c23.x, c23.z}, sn[4] = {c01.y, c01.w, c23.y, c23.w};
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      const uint2 graw = *reinterpret_cast<const uint2*>((which ? dk : dq) + hm);
-      const float2 g0 = unpack_bf16x2(graw.x), g1 = unpack_bf16x2(graw.y);
-      // inverse rotation
-      const float dy0 = cs0.x * g0.x + cs0.y * g0.y, dy1 = -cs0.y * g0.x + cs0.x * g0.y;
-      const float dy2 = cs1.x * g1.x + cs1.y * g1.y, dy3 = -cs1.y * g1.x + cs1.x * g1.y;
-      const uint2 raw = *reinterpret_cast<const uint2*>(src + which * H * D);
-      const float2 p0 = unpack_bf16x2(raw.x), p1 = unpack_bf16x2(raw.y);
-      const float ss = warp_sum(p0.x * p0.x + p0.y * p0.y + p1.x * p1.x + p1.y * p1.y);
-      const float rr = rsqrtf(ss / D + 1e-6f);
-      const uint2 sraw = *reinterpret_cast<const uint2*>((which ? k_scale : q_scale) + lane * 4);
-      const float2 s0 = unpack_bf16x2(sraw.x), s1 = unpack_bf16x2(sraw.y);
-      const float xn[4] = {p0.x * rr, p0.y * rr, p1.x * rr, p1.y * rr};
-      const float dyv[4] = {dy0, dy1, dy2, dy3};
-      const float sc[4] = {s0.x, s0.y, s1.x, s1.y};
-      float dxn[4], dot = 0.f;
+      float g[8], x[8];
+      unpack8(which ? gk : gq, g);
+      unpack8(which ? xk : xq, x);
+      float dy[8], ss = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[which][j] += dyv[j] * xn[j];
-        dxn[j] = dyv[j] * sc[j];
-        dot += dxn[j] * xn[j];
+      for (int j = 0; j < 4; ++j) {   // inverse rotation
+        dy[2 * j] = cc[j] * g[2 * j] + sn[j] * g[2 * j + 1];
+        dy[2 * j + 1] = -sn[j] * g[2 * j] + cc[j] * g[2 * j + 1];
       }
-      dot = warp_sum(dot) / D;
-      uint2 o;
-      o.x = pack_bf16x2(rr * (dxn[0] - xn[0] * dot), rr * (dxn[1] - xn[1] * dot));
-      o.y = pack_bf16x2(rr * (dxn[2] - xn[2] * dot), rr * (dxn[3] - xn[3] * dot));
-      *reinterpret_cast<uint2*>(dstp + which * H * D) = o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += x[j] * x[j];
+      ss = half_sum(ss);
+      const float rr = rsqrtf(ss / D + 1e-6f);
+      float dxn[8], dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xn = x[j] * rr;
+        x[j] = xn;
+        if (live) acc[which][j] += dy[j] * xn;
+        dxn[j] = dy[j] * (which ? ks[j] : qs[j]);
+        dot += dxn[j] * xn;
+      }
+      dot = half_sum(dot) / D;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rr * (dxn[j] - x[j] * dot);
+      if (live) *reinterpret_cast<uint4*>(dstp + which * H * D) = pack8(o);
     }
-    *reinterpret_cast<uint2*>(dstp + 2 * H * D) = *reinterpret_cast<const uint2*>(dv + hm);
+    if (live) *reinterpret_cast<uint4*>(dstp + 2 * H * D) = gv;
   }
 #pragma unroll
   for (int which = 0; which < 2; ++which)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[which][warp][lane * 4 + j] = acc[which][j];
+    for (int j = 0; j < 8; ++j) red[which][warp * 2 + half][sl * 8 + j] = acc[which][j];
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
     const int which = i / D, d = i % D;
     float s = 0.f;
 #pragma unroll
-    for (int w8 = 0; w8 < 8; ++w8) s += red[which][w8][d];
+    for (int w16 = 0; w16 < 16; ++w16) s += red[which][w16][d];
     atomicAdd((which ? dscale_k : dscale_q) + d, s);
   }
 }
@@ -682,7 +709,10 @@ extern "C" int gh_qk_norm_rope_bwd(const void* dq, const void* dk, const void* d
   GH_REQUIRE(D == 128, GH_ERR_UNSUPPORTED, "gh_qk_norm_rope_bwd: head dim %d unsupported", D);
   GH_REQUIRE(B >= 0 && L >= 0 && H > 0 && l_off >= 0 && l_off + L <= Ltot, GH_ERR_BAD_SHAPE,
              "gh_qk_norm_rope_bwd: bad shape");
-  GH_REQUIRE(ld_qkv % 4 == 0 && ld_dqkv % 4 == 0, GH_ERR_ALIGN, "gh_qk_norm_rope_bwd: bad ld");
+  GH_REQUIRE(ld_qkv % 8 == 0 && ld_dqkv % 8 == 0 && cs_batch_stride % 2 == 0 && aligned16(dq) && aligned16(dk) &&
+                 aligned16(dv) && aligned16(qkv) && aligned16(dqkv) && aligned16(cos_sin) && aligned16(q_scale) &&
+                 aligned16(k_scale),
+             GH_ERR_ALIGN, "gh_qk_norm_rope_bwd: 16-byte vectors need ld % 8 == 0 and 16-byte aligned pointers");
   const int64_t n_tok = static_cast<int64_t>(B) * L;
   if (n_tok == 0) return GH_OK;
   int tokens_per_cta = 8;
