@@ -37,11 +37,14 @@ template <int WPR>
 __device__ __forceinline__ float row_sum(float v, int warp, int lane, float* red) {
   v = warp_sum(v);
   if (WPR == 1) return v;
-  const int bar = 1 + (warp >> 1);
+  const int grp = warp / WPR;
+  const int bar = 1 + grp;          // one named barrier per group of WPR warps (32 * WPR threads)
   if (lane == 0) red[warp] = v;
-  asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
-  const float t = red[warp] + red[warp ^ 1];
-  asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");  // red[] may be rewritten by the next reduction
+  asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(32 * WPR) : "memory");
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < WPR; ++k) t += red[grp * WPR + k];
+  asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(32 * WPR) : "memory");  // red[] may be rewritten by the next reduction
   return t;
 }
 
@@ -143,7 +146,8 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__
   const bf16* dyr = dy + dym.off(r);
   const int b = r / xm.rpb;
   const float mu = mean[r], rs = rstd[r];
-  uint4 vn[VMAX], vd[VMAX];  // n (as bf16-packed fp... keep raw x) and dn
+  const bf16* drr = dres ? dres + drm.off(r) : nullptr;
+  uint4 vn[VMAX], vd[VMAX], vr[VMAX];  // raw x, dy and (requested with them, used after the reductions) dres
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VMAX; ++i) {
@@ -151,6 +155,7 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__
     if (c < C) {
       vn[i] = *reinterpret_cast<const uint4*>(xr + c);
       vd[i] = *reinterpret_cast<const uint4*>(dyr + c);
+      if (drr) vr[i] = *reinterpret_cast<const uint4*>(drr + c);
       float fx[8], fd[8];
       unpack8(vn[i], fx);
       unpack8(vd[i], fd);
@@ -177,7 +182,6 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__
   }
   const float m1 = row_sum<WPR>(s1, warp, lane, red) / C, m2 = row_sum<WPR>(s2, warp, lane, red) / C;
   bf16* dxr = dx + dxm.off(r);
-  const bf16* drr = dres ? dres + drm.off(r) : nullptr;
 #pragma unroll
   for (int i = 0; i < VMAX; ++i) {
     const int c = (i * 32 * WPR + lane_g) * 8;
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__
       }
       if (drr) {
         float rr[8];
-        unpack8(*reinterpret_cast<const uint4*>(drr + c), rr);
+        unpack8(vr[i], rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += rr[j];
       }
@@ -575,7 +579,8 @@ extern "C" int gh_layernorm_fwd(const void* x, const gh_rows_view* xv, void* y, 
       static_cast<const bf16*>(shift), static_cast<const bf16*>(scale), mod_ld, eps, mean_out, rstd_out)
   if (C <= 1024) GH_LN(4, 1);
   else if (C <= 2048) GH_LN(8, 1);
-  else GH_LN(8, 2);   // wide rows: a pair of warps per row (see row_sum)
+  else if (C <= 3072) GH_LN(3, 4);   // wide rows: four warps per row (see row_sum)
+  else GH_LN(4, 4);
 #undef GH_LN
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
@@ -601,7 +606,8 @@ extern "C" int gh_layernorm_bwd_dx(const void* dy, const gh_rows_view* dyv, cons
       static_cast<const bf16*>(scale), mod_ld, static_cast<const bf16*>(dres), drm, static_cast<bf16*>(dx), dxm)
   if (C <= 1024) GH_LNB(4, 1);
   else if (C <= 2048) GH_LNB(8, 1);
-  else GH_LNB(8, 2);
+  else if (C <= 3072) GH_LNB(3, 4);   // four warps per row: 3 x 16 B per lane and tensor, ~3 blocks per SM
+  else GH_LNB(4, 4);
 #undef GH_LNB
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
