@@ -389,6 +389,18 @@ def run_ours(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_step(S, budget_s=args.cpu_budget)
+    if rank == 0 and world == 1 and not args.no_library_baseline:
+        try:
+            if graphed is not None:     # give the activation pool of the step graph back first
+                graphed.graph.reset()
+                graphed = None
+            del step, clip_vis, dit, vae, opt, groups, trainable, dev_batches, staged
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            out["library_baseline"] = library_baseline_step(S, B, dev)
+        except Exception as e:  # noqa: BLE001  (a baseline that cannot run must not take the measurement down)
+            out["library_baseline"] = {"unavailable": repr(e)[:200]}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -449,6 +461,53 @@ class CpuReferenceStep:
             for v in sd.values():
                 v.grad = None
         return float(out.loss.detach())
+
+
+def library_baseline_step(image_size: int, batch: int, device, steps: int = 5, warmup: int = 2) -> dict:
+    """SURVEY.md 8(d), optional "library baseline": the same oracle port of the reference step, but with its tensors on
+    the B200 -- stock PyTorch ops (cuBLAS / cuDNN / SDPA), fp32 tower + AE and a bf16 DiT as the reference runs them
+    (train_SigLIP_stage1.py:127-133,255-261), forward + backward only (no clip / AdamW).  What a user of the reference
+    gets on this GPU without our kernels; reported beside the CPU baseline, never part of `value`."""
+    from genhancer_b200.train_step import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD
+    from oracle import genhancer_oracle as O
+    tc, fc, ac = O.openai_vit_l14(image_size), O.FluxCfg(), O.AECfg()
+    to = lambda sd, rg: {k: v.detach().to(device).requires_grad_(rg) for k, v in sd.items()}  # noqa: E731
+    sd_t = to(_fast_state_dict(O.tower_key_shapes(tc), False), False)
+    sd_w = to(_fast_state_dict({**O.projector_key_shapes("project_clip", 768, 768),
+                                **O.projector_key_shapes("project_t5", 768, 4096)}, False), True)
+    sd_d = {k: v.to(torch.bfloat16).requires_grad_(True)
+            for k, v in to(_fast_state_dict(O.flux_key_shapes(fc), False), False).items()}
+    sd_a = to(_fast_state_dict(O.ae_encoder_key_shapes(ac), False), False)
+    h = image_size // 8
+    gen = torch.Generator(device=device).manual_seed(7)
+
+    def one():
+        img = torch.rand(batch, 3, image_size, image_size, device=device, generator=gen)
+        noise = torch.randn(batch, 16, h, h, device=device, generator=gen)
+        t = torch.sigmoid(torch.randn(batch, device=device, generator=gen))
+        x_0 = torch.randn(batch, (h // 2) ** 2, 64, device=device, generator=gen)
+        out = O.stage1_image_step(sd_t, sd_w, sd_d, sd_a, img, tc, fc, ac, OPENAI_CLIP_MEAN, OPENAI_CLIP_STD, noise, t,
+                                  x_0, dit_dtype=torch.bfloat16)
+        out.loss.backward()
+        for sd in (sd_w, sd_d):
+            for v in sd.values():
+                v.grad = None
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del sd_t, sd_w, sd_d, sd_a
+    torch.cuda.empty_cache()
+    return {"value": round(batch / ms * 1e3, 2), "unit": UNIT, "ms_per_step": round(ms, 2), "kind": "port-on-gpu",
+            "what": f"oracle port of the reference step through stock PyTorch {torch.__version__} ops on the same GPU "
+                    f"(fp32 tower + AE, bf16 DiT, SDPA), batch {batch}, forward + backward only, {steps} steps"}
 
 
 def cpu_baseline_step(image_size: int, budget_s: float = 45.0, target_s: float = 15.0) -> dict:
@@ -520,6 +579,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (BASELINE configs[1]: 32)")
     ap.add_argument("--image-size", type=int, default=336)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true",
+                    help="skip the stock-PyTorch-on-this-GPU run of the oracle port (SURVEY.md 8d, optional baseline)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
     ap.add_argument("--dump-shapes", default="", help="write the per-shape GEMM/conv timing table (JSON) here")
     ap.add_argument("--cpu-budget", type=float, default=45.0)
