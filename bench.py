@@ -8,7 +8,8 @@ overlapped with the DiT backward.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = pinned-host inputs copied inside the
-timed region + loss read back each step.  `--impl reference` times the oracle port of the reference's step on
+timed region + loss read back each step.  Baselines in the same line (N = 1): `cpu_baseline` (the oracle port on the
+host cores) and `library_baseline` (the same port through stock PyTorch ops on the GPU).  `--impl reference` times the oracle port of the reference's step on
 the host cores (the reference itself has no GPU-free install here: it needs accelerate/diffusers/peft/omegaconf,
 none of which are in the image).
 """
