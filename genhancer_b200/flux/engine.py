@@ -14,6 +14,8 @@ Parameter gradients are written straight into the caller's grad buffers by the w
 """
 from __future__ import annotations
 
+import contextlib
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -42,10 +44,21 @@ class GradSink:
     """Where parameter gradients go.  ``big(name)`` returns the bf16/fp32 [N,K] grad tensor a wgrad GEMM writes
     (accumulating when ``accumulate``); ``small(name)`` returns an fp32 accumulator view flushed by ``flush()``."""
 
+    # Weight gradients are leaves of the backward: dW = dY^T X (and db = colsum dY) of a layer is needed by nothing
+    # until the optimizer, while dX = dY W is the critical path.  With ``overlap_wgrad`` they are issued on a side
+    # stream (forked after dY is ready, joined before the block is flushed / announced to the reducer): the persistent
+    # GEMM grids of the two streams then overlap at their edges -- an SM that has finished its share of one kernel
+    # starts on the other's instead of idling until the kernel boundary (the dgrad with 9.08 waves of tiles left 92 % of
+    # the SMs idle for its last wave).  Inside the step graph the side stream is a forked branch.
+    overlap_wgrad = os.environ.get("GH_WGRAD_STREAM", "1") != "0"
+    _side_streams: dict = {}
+
     def __init__(self, params: dict[str, torch.Tensor], accumulate: bool, on_ready=None):
         self.params = params
         self.accumulate = accumulate
         self.on_ready = on_ready
+        self._keep: list = []       # operands of side-stream kernels, kept alive until join()
+        self._forked = False
         self._flushed: set[str] = set()
         self._discard = None
         self._small: dict[str, torch.Tensor] = {}
@@ -61,6 +74,27 @@ class GradSink:
 
     def wants(self, name: str) -> bool:
         return self.params[name].requires_grad
+
+    def side(self, *operands):
+        """Context in which the caller launches leaf work (wgrad GEMM, bias column sum) that reads ``operands``."""
+        dev = self._scratch.device
+        if not GradSink.overlap_wgrad or dev.type != "cuda":
+            return contextlib.nullcontext()
+        st = GradSink._side_streams.get(dev.index)
+        if st is None:
+            st = GradSink._side_streams[dev.index] = torch.cuda.Stream(device=dev)
+        st.wait_stream(torch.cuda.current_stream(dev))     # dY (and the fp32 scratch) are ready
+        self._keep.extend(operands)
+        self._forked = True
+        return torch.cuda.stream(st)
+
+    def join(self) -> None:
+        """The current stream waits for the side stream; the kept operands may be freed."""
+        if self._forked:
+            dev = self._scratch.device
+            torch.cuda.current_stream(dev).wait_stream(GradSink._side_streams[dev.index])
+            self._forked = False
+        self._keep.clear()
 
     def big(self, name: str):
         """-> (grad tensor, residual-or-None) for a weight matrix."""
@@ -83,6 +117,7 @@ class GradSink:
     def flush(self, prefix: str | None = None) -> None:
         """Write the fp32 accumulators of the 1-D parameters under ``prefix`` (all when None) into ``.grad`` and
         tell ``on_ready`` (the data-parallel bucket launcher) that every gradient under ``prefix`` is final."""
+        self.join()
         for n, acc in self._small.items():
             if n in self._flushed or (prefix is not None and not n.startswith(prefix)):
                 continue
@@ -103,14 +138,17 @@ def _lin_fwd(x2d, w, b, **kw):
 def _lin_bwd(dy2d, x2d, w_name, b_name, P, sink: GradSink, need_dx=True, dx_kw=None):
     """dx = dy @ W ; dW (+)= dy^T x ; db += colsum(dy)."""
     w = P[w_name]
+    want_w, want_b = sink.wants(w_name), b_name is not None and sink.wants(b_name)
+    if want_w or want_b:
+        with sink.side(dy2d, x2d):      # leaves of the backward: off the critical path
+            if want_w:
+                gw, res = sink.big(w_name)
+                K.gemm(dy2d, x2d, a_mn=True, b_mn=True, out=gw, residual=res)
+            if want_b:
+                K.colsum(dy2d, sink.small(b_name))
     dx = None
     if need_dx:
         dx = K.gemm(dy2d, w, b_mn=True, **(dx_kw or {}))
-    if sink.wants(w_name):
-        gw, res = sink.big(w_name)
-        K.gemm(dy2d, x2d, a_mn=True, b_mn=True, out=gw, residual=res)
-    if b_name is not None and sink.wants(b_name):
-        K.colsum(dy2d, sink.small(b_name))
     return dx
 
 
@@ -295,13 +333,14 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
         du2d = du.view(-1, C)
         w2 = P[f"{p}.linear2.weight"]
         dl1 = torch.empty(B * L, 3 * C + mlp, dtype=BF16, device=dev)  # d(linear1 output) = [dqkv | dpre]
+        with sink.side(du2d, catb):
+            if sink.wants(f"{p}.linear2.weight"):
+                gw, res = sink.big(f"{p}.linear2.weight")
+                K.gemm(du2d, catb, a_mn=True, b_mn=True, out=gw, residual=res)
+            if sink.wants(f"{p}.linear2.bias"):
+                K.colsum(du2d, sink.small(f"{p}.linear2.bias"))
         dattn = K.gemm(du2d, w2[:, :C], b_mn=True)
         K.gemm(du2d, w2[:, C:], b_mn=True, act=ACT_GELU_TANH, act_grad=True, aux_in=pre, out=dl1[:, 3 * C:])
-        if sink.wants(f"{p}.linear2.weight"):
-            gw, res = sink.big(f"{p}.linear2.weight")
-            K.gemm(du2d, catb, a_mn=True, b_mn=True, out=gw, residual=res)
-        if sink.wants(f"{p}.linear2.bias"):
-            K.colsum(du2d, sink.small(f"{p}.linear2.bias"))
         # attention
         dq = torch.empty(B, H, L, D, dtype=BF16, device=dev)
         dk = torch.empty_like(dq)
@@ -342,7 +381,7 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
             dattn[s] = _lin_bwd(du1.view(-1, C), attn.view(-1, C), f"{p}.{s}_attn.proj.weight",
                                 f"{p}.{s}_attn.proj.bias", P, sink).view(B, rpb, C)
             dx_mid[s] = dxm
-            if bi == 0:
+            if bi == 0 and sink.on_ready is not None:
                 # the LAST block of the backward: announce its sub-modules as their gradients become final, so the
                 # exposed tail of the data-parallel exchange is one Modulation's worth instead of the whole block
                 sink.flush(f"{p}.{s}_mlp.")
@@ -361,11 +400,11 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
                                sink.small(f"{p}.{s}_attn.norm.key_norm.scale"))
             h = S[f"{p}.{s}_norm1.h"]
             dh = _lin_bwd(dqkv.view(-1, 3 * C), h.view(-1, C), f"{p}.{s}_attn.qkv.weight", f"{p}.{s}_attn.qkv.bias", P, sink)
-            if bi == 0:
+            if bi == 0 and sink.on_ready is not None:
                 sink.flush(f"{p}.{s}_attn.")
             dxs[s] = adaln_bwd(f"{p}.{s}_norm1", dh.view(B, rpb, C), m, 0, dmods[s], dres=dx_mid[s])
             mod_bwd(dmods[s], f"{p}.{s}_mod.lin.weight", f"{p}.{s}_mod.lin.bias")
-            if bi == 0:
+            if bi == 0 and sink.on_ready is not None:
                 sink.flush(f"{p}.{s}_mod.")
         sink.flush(p + ".")
 
