@@ -18,6 +18,8 @@ given seed reproduces the reference's t, x_0 and AE noise bit-for-bit (SURVEY.md
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import Tensor
 
@@ -29,6 +31,31 @@ OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)   # train_MetaCLIP_stage1
 OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 SIGLIP_MEAN = (0.5, 0.5, 0.5)                             # train_SigLIP_stage1.py:54-55
 SIGLIP_STD = (0.5, 0.5, 0.5)
+
+
+# The frozen AE encoder and the tower read the same image and nothing of each other: the AE runs on a side stream,
+# forked at the top of the step and joined before x_1 is first read.  Two independent chains of kernels overlap at
+# their edges (an SM done with a conv's last wave starts on a ViT GEMM instead of idling until the kernel boundary)
+# and the HBM-bound GroupNorm passes run beside tensor-bound GEMMs.  The torch.randn of the AE noise is still the first
+# RNG call of the step in host order, so the draws stay those of the reference.  GH_AE_STREAM=0 switches it off.
+OVERLAP_AE = os.environ.get("GH_AE_STREAM", "1") != "0"
+_SIDE_STREAMS: dict = {}
+
+
+def encode_on_side_stream(vae, img: Tensor, noise):
+    """-> (x_1, join): ``vae.encode_patchified`` issued on the side stream; call ``join()`` on the consumer's stream
+    before reading x_1."""
+    if not (OVERLAP_AE and img.is_cuda):
+        return vae.encode_patchified(img, 0.5, 0.5, noise=noise), (lambda: None)
+    dev = img.device
+    side = _SIDE_STREAMS.get(dev.index)
+    if side is None:
+        side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    side.wait_stream(main)          # the image (and, next step, everything that last read this step's buffers)
+    with torch.cuda.stream(side):
+        x_1 = vae.encode_patchified(img, 0.5, 0.5, noise=noise)
+    return x_1, (lambda: torch.cuda.current_stream(dev).wait_stream(side))
 
 
 class _FlowMatchLoss(torch.autograd.Function):
@@ -90,7 +117,7 @@ class Stage1ImageStep:
         arithmetic is that of the sequential loop (weights are updated before they are next read)."""
         B = img.shape[0]
         dev = img.device
-        x_1 = self.vae.encode_patchified(img, 0.5, 0.5, noise=ae_noise)                 # [B, L, 64] fp32
+        x_1, join_ae = encode_on_side_stream(self.vae, img, ae_noise)                    # [B, L, 64] fp32
         tower_trains = any(p.requires_grad for p in self.clip_vis.model.parameters())
         if before_trainable is not None and tower_trains:
             before_trainable()
@@ -98,6 +125,7 @@ class Stage1ImageStep:
         if before_trainable is not None and not tower_trains:
             before_trainable()
         vec, txt = self.clip_vis.project(cls)
+        join_ae()
         h2 = w2 = int(round(x_1.shape[1] ** 0.5))
         img_ids, txt_ids, guidance = self._static(B, h2, w2, txt.shape[1], dev)
         t, x_0 = sample_t_x0(x_1, self.scale_factor, t, x_0)

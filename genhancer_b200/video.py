@@ -24,7 +24,7 @@ from . import ops
 from .clip_models import vision_tower as vt
 from .clip_models.sampling import make_img_ids
 from .kernels import ACT_SILU, BF16
-from .train_step import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD, flow_match_loss, sample_t_x0
+from .train_step import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD, encode_on_side_stream, flow_match_loss, sample_t_x0
 
 
 class VisualPromptAdapter(nn.Module):
@@ -135,7 +135,7 @@ class VideoStep:
             raise ValueError(f"expected {len(self.cond_times)} conditioning frames, got {len(cond_frames)}")
         B, dev = target.shape[0], target.device
         n = len(cond_frames)
-        x_1 = self.vae.encode_patchified(target, 0.5, 0.5, noise=ae_noise)
+        x_1, join_ae = encode_on_side_stream(self.vae, target, ae_noise)     # beside the tower pass (train_step.py)
         model = self.m.clip_vis.model
         if before_trainable is not None and self.tower_grad:
             before_trainable()
@@ -153,6 +153,7 @@ class VideoStep:
         if before_trainable is not None and not self.tower_grad:
             before_trainable()
         txt = self.m.visual_adapter(visual_context)
+        join_ae()
         h2 = w2 = int(round(x_1.shape[1] ** 0.5))
         img_ids, txt_ids, guidance = self._static(B, h2, w2, g, dev)
         if txt.shape[1] != txt_ids.shape[1]:
