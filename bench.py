@@ -335,8 +335,10 @@ def run_ours(args):
         return loss
 
     # (per-launch event timing wants the launches back to back on ONE stream: no side-stream wgrads in this pass)
+    from genhancer_b200 import train_step as _ts
     from genhancer_b200.flux import engine as _engine
     _overlap, _engine.GradSink.overlap_wgrad = _engine.GradSink.overlap_wgrad, False
+    _overlap_ae, _ts.OVERLAP_AE = _ts.OVERLAP_AE, False
     eager_step(dev_batches[0])
     timer = GemmTimer()
     K.GEMM_TIMER = timer
@@ -344,6 +346,7 @@ def run_ours(args):
     ms_roof = timed(lambda i: eager_step(dev_batches[i % pool]), n_roof)
     K.GEMM_TIMER = None
     _engine.GradSink.overlap_wgrad = _overlap
+    _ts.OVERLAP_AE = _overlap_ae
     gemm_flops, gemm_ms, gemm_n = timer.summary()
     if rank == 0 and args.dump_shapes:
         os.makedirs(os.path.dirname(os.path.abspath(args.dump_shapes)), exist_ok=True)
