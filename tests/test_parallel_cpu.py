@@ -90,6 +90,14 @@ def _worker(rank, world, port, out):
             covered[lo:hi] += 1
         res = dict(ok_sum=bool(ok_sum), once=bool((covered == 1).all()), first=red.log[0][0],
                          n_buckets=len(red.log), p0=float(g.flat_p.double().sum()), scale=red.grad_scale)
+        # second round through the two halves the data-parallel loops use (issue right after backward, wait deferred
+        # into the next step); on CPU tensors the dynamic tile schedule of the CUDA GEMMs is never touched
+        res["dyn_off_on_cpu"] = (red.dynamic_tiles is False) and (red._dyn_on is False)
+        g.flat_g.copy_(torch.ones(g.numel) * (rank + 1))
+        net._on_grads_ready("single_blocks.0.")
+        red.issue_rest()
+        red.wait()
+        res["two_halves"] = bool(torch.equal(g.flat_g, torch.ones(g.numel) * sum(r + 1 for r in range(world))))
         # accumulation micro-step: nothing is exchanged
         red.enabled = False
         before = g.flat_g.clone()
@@ -108,7 +116,21 @@ def test_bucketed_allreduce_world2_gloo():
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     r0, r1 = out[0], out[1]
     for r in (r0, r1):
-        assert r["ok_sum"] and r["once"] and r["no_sync_untouched"]
+        assert r["ok_sum"] and r["once"] and r["no_sync_untouched"] and r["two_halves"] and r["dyn_off_on_cpu"]
         assert r["first"] == "final_layer." and r["n_buckets"] > 7   # 1 KiB cap splits the blocks into several buckets
         assert r["scale"] == 0.5
     assert r0["p0"] == r1["p0"]                                       # broadcast made the replicas identical
+
+
+def test_gradsink_side_stream_is_inert_without_cuda():
+    """The wgrad side stream of the DiT backward (flux/engine.py) only exists for CUDA tensors: on CPU parameters
+    ``side()`` is a no-op context and ``join()`` just releases the kept operands."""
+    from genhancer_b200.flux.engine import GradSink
+    params = {"lin.weight": torch.nn.Parameter(torch.zeros(4, 4)), "lin.bias": torch.nn.Parameter(torch.zeros(4))}
+    sink = GradSink(params, accumulate=False)
+    a = torch.ones(2, 4)
+    with sink.side(a):
+        pass
+    assert sink._forked is False
+    sink.join()
+    assert sink._keep == []
