@@ -40,9 +40,10 @@ const char* gh_last_error(void);
 int gh_version(void);
 /* Resolve the driver entry points, raise the kernels' dynamic-smem limits on `device`. */
 int gh_init(int device);
-/* How many SMs the persistent kernels (one CTA or CTA pair per SM) may fill; 0 = all.  Data-parallel training leaves a
- * few SMs to the concurrent NCCL all-reduce kernels: a persistent grid that finds some SMs taken runs its last CTAs as
- * a second wave (accelerate / DeepSpeed have no analogue: their GEMMs are not persistent). */
+/* How many SMs the persistent kernels (one CTA or CTA pair per SM) may fill; 0 = all (the default).  An experiment
+ * knob: leaving a few SMs to the concurrent NCCL all-reduce kernels was measured to be WORSE than full grids (132 SMs:
+ * +4 ms per step on 2 and 8 GPUs); what data-parallel training uses instead is the dynamic tile
+ * schedule below.  (accelerate / DeepSpeed have no analogue: their GEMMs are not persistent.) */
 int gh_set_sm_budget(int sms);
 /* Tile schedule of the persistent tcgen05 GEMM grids launched from now on: 0 = static (tile = worker + i * #workers,
  * the default: no atomics, no start-up latency), 1 = dynamic (each CTA / CTA pair pulls its next tile from a global
