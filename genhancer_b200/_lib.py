@@ -116,6 +116,7 @@ SIGNATURES: dict[str, list] = {
     "gh_groupnorm_ws_bytes": [_i32, _i64],
     "gh_groupnorm_swish_nhwc": [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _f32, _i32, _vp, _vp],
     "gh_upsample2x_nhwc": [_vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "gh_u8hwc_to_f32chw": [_vp, _vp, _i32, _i32, _i32, _vp],
     "gh_softmax_rows": [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp],
     "gh_ae_sample_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp],
     "gh_sumsq_accum": [_vp, _i32, _i64, _vp, _vp],

@@ -350,7 +350,37 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
     y[i] = __ldg(x + ((static_cast<int64_t>(b) * H + (oh >> 1)) * W + (ow >> 1)) * C8 + c);
   }
 }
+// ToTensor of the reference's image pipeline (image_datasets/dataset_cc3m.py:38-44, torchvision ToTensor on a PIL RGB
+// image): uint8 HWC -> fp32 CHW in [0,1], value / 255 with IEEE division (bit-identical to torch's .div(255)).
+// The decoded image crosses PCIe as 1 byte per value instead of 4; thread = pixel: 96 contiguous bytes per warp in,
+// three coalesced 128-byte rows out.
+__global__ void __launch_bounds__(256) u8hwc_to_f32chw_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                              int64_t hw, int64_t total_pix) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_pix; i += stride) {
+    const int64_t b = i / hw, p = i - b * hw;
+    const uint8_t* s = src + i * 3;
+    float* d = dst + b * 3 * hw + p;
+    d[0] = __fdiv_rn(static_cast<float>(s[0]), 255.f);
+    d[hw] = __fdiv_rn(static_cast<float>(s[1]), 255.f);
+    d[2 * hw] = __fdiv_rn(static_cast<float>(s[2]), 255.f);
+  }
+}
+
 }  // namespace gh
+
+extern "C" int gh_u8hwc_to_f32chw(const void* src_u8, float* dst, int32_t B, int32_t H, int32_t W, void* stream) {
+  using namespace gh;
+  GH_REQUIRE(B >= 0 && H > 0 && W > 0, GH_ERR_BAD_SHAPE, "gh_u8hwc_to_f32chw: bad shape");
+  if (B == 0) return GH_OK;   // (an empty batch has no storage: checked before the pointers)
+  GH_REQUIRE(src_u8 && dst, GH_ERR_NULL, "gh_u8hwc_to_f32chw: NULL pointer");
+  const int64_t hw = static_cast<int64_t>(H) * W, total = hw * B;
+  const int64_t want = (total + 255) / 256, cap = static_cast<int64_t>(num_sms()) * 16;
+  u8hwc_to_f32chw_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(src_u8), dst, hw, total);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
 
 extern "C" int gh_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
   using namespace gh;

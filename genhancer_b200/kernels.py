@@ -450,6 +450,19 @@ def groupnorm_swish_nhwc(x, weight, bias, eps=1e-6, swish=True):
     return y
 
 
+def u8hwc_to_f32chw(x: torch.Tensor) -> torch.Tensor:
+    """uint8 [B,H,W,3] (a decoded RGB batch) -> fp32 [B,3,H,W] in [0,1]: torchvision's ToTensor on the device."""
+    _ensure(x)
+    if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[-1] != 3:
+        raise _lib.GhError(f"u8hwc_to_f32chw: expected uint8 [B,H,W,3], got {x.dtype} {tuple(x.shape)}")
+    xc = x.contiguous()
+    B, H, W, _ = xc.shape
+    y = torch.empty(B, 3, H, W, dtype=F32, device=x.device)
+    check(_lib.lib().gh_u8hwc_to_f32chw(xc.data_ptr(), y.data_ptr(), B, H, W, _stream()))
+    _count()
+    return y
+
+
 def upsample2x_nhwc(x: torch.Tensor) -> torch.Tensor:
     _ensure(x)
     assert x.dtype == BF16 and x.is_contiguous() and x.dim() == 4

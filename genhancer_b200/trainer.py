@@ -309,6 +309,15 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
                 save_checkpoint(args.output_dir, st.step, dit, clip_vis, adapter, opt, video,
                                 save_project_clip=train_project_clip)
 
+    def to_input(t):
+        """A loader may hand over decoded frames as uint8 [B,H,W,3] (1 byte per value over PCIe): ToTensor then runs
+        on the device (gh_u8hwc_to_f32chw); fp32 [B,3,H,W] in [0,1] batches pass through as before."""
+        t = t.to(device, non_blocking=True)
+        if t.dtype == torch.uint8 and t.dim() == 4 and t.shape[-1] == 3:
+            from . import kernels as K
+            return K.u8hwc_to_f32chw(t)
+        return t.float()
+
     for batch in loader:
         if st.step + int(st.pending) >= max_steps:
             break
@@ -316,7 +325,7 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
         if reducer is not None:
             reducer.enabled = sync
         if mode == "image":
-            loss = step_fn(batch["image"].to(device, non_blocking=True).float(), before_trainable=finish_step)
+            loss = step_fn(to_input(batch["image"]), before_trainable=finish_step)
         elif mode == "sliding_windows_nextpredic":
             w = build_windows_with_mask(batch["full_frames"].to(device), batch["frame_mask"].to(device),
                                         int(args.get("window_cond", 3)), int(args.get("window_stride", 1)),
@@ -325,7 +334,7 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
                 continue
             loss = step_fn(list(w[:3]), w[3], before_trainable=finish_step)
         else:
-            f = {k: batch[k].to(device, non_blocking=True).float() for k in ("start_frame", "middle_frame", "end_frame")}
+            f = {k: to_input(batch[k]) for k in ("start_frame", "middle_frame", "end_frame")}
             cond, tgt = {"video": (("start_frame", "end_frame"), "middle_frame"),
                          "nextpredic": (("start_frame",), "middle_frame"),
                          "use2frames_nextpredic": (("start_frame", "middle_frame"), "end_frame")}[mode]

@@ -329,6 +329,10 @@ int gh_groupnorm_swish_nhwc(const void* x, void* y, int32_t B, int64_t HW, int32
 /* nearest-neighbour 2x upsample, NHWC bf16 [B,H,W,C] -> [B,2H,2W,C] (FLUX decoder Upsample, autoencoder.py:98-106;
  * the 3x3 conv that follows is gh_conv2d_nhwc).  C % 8 == 0. */
 int gh_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* ToTensor of the reference's image pipeline (image_datasets/dataset_cc3m.py:38-44,107-113: torchvision ToTensor on
+ * the cropped PIL RGB image): uint8 [B,H,W,3] -> fp32 [B,3,H,W] = value / 255 (IEEE division, bit-identical to torch).
+ * Lets the decoded batch cross PCIe as bytes; NORMALIZE_VAE / NORMALIZE_CLIP stay folded into the im2col gathers. */
+int gh_u8hwc_to_f32chw(const void* src_u8, float* dst, int32_t B, int32_t H, int32_t W, void* stream);
 /* p[r,:n] = softmax(scale * s[r,:n]) fp32 -> bf16, pad columns zeroed (AE mid AttnBlock, autoencoder.py:37-52). */
 int gh_softmax_rows(const float* s, int64_t ld_in, void* p_bf16, int64_t ld_out, int32_t rows, int32_t n, float scale,
                     void* stream);

@@ -64,3 +64,20 @@ def test_empty_and_bad_arguments_fail_loudly():
         K.gemm(b, b)  # row pitch 20 elements: not a multiple of 8 (TMA needs 16-byte row pitch)
     with pytest.raises(_lib.GhError):
         K.gemm(a.float(), a.float())
+
+
+def test_u8_to_tensor_is_bit_identical_to_torch():
+    """gh_u8hwc_to_f32chw == torchvision ToTensor as the reference's DataLoader runs it -- on the CPU, where
+    ``.div(255)`` is an IEEE division (torch's CUDA kernel multiplies by the reciprocal instead and differs in the
+    last bit for 126 of the 256 byte values).  Every byte value, odd sizes, B = 0."""
+    from genhancer_b200 import _lib, kernels as K
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for shape in [(2, 16, 16, 3), (3, 37, 53, 3), (32, 336, 336, 3), (0, 8, 8, 3)]:
+        x = torch.randint(0, 256, shape, device="cuda", dtype=torch.uint8, generator=g)
+        if x.numel() >= 256 * 3:
+            x.view(-1)[:256] = torch.arange(256, device="cuda", dtype=torch.uint8)     # every value at least once
+        y = K.u8hwc_to_f32chw(x)
+        assert y.shape == (shape[0], 3, shape[1], shape[2]) and y.dtype == torch.float32
+        assert torch.equal(y.cpu(), x.cpu().permute(0, 3, 1, 2).to(torch.float32).div(255))
+    with pytest.raises(_lib.GhError):
+        K.u8hwc_to_f32chw(torch.zeros(1, 3, 8, 8, device="cuda", dtype=torch.uint8))       # CHW is not the input layout
