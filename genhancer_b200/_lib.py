@@ -92,7 +92,7 @@ SIGNATURES: dict[str, list] = {
     "gh_layernorm_fwd": [_vp, _rv, _vp, _rv, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp],
     "gh_layernorm_bwd_dx": [_vp, _rv, _vp, _rv, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _rv, _vp, _rv, _vp],
     "gh_layernorm_bwd_params": [_vp, _rv, _vp, _rv, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp],
-    "gh_gate_bwd": [_vp, _rv, _vp, _rv, _i32, _i32, _vp, _i64, _vp, _rv, _vp, _i64, _vp],
+    "gh_gate_bwd": [_vp, _rv, _vp, _rv, _i32, _i32, _vp, _i64, _vp, _rv, _vp, _i64, _vp, _vp],
     "gh_colsum": [_vp, _rv, _i32, _i32, _vp, _i64, _vp],
     "gh_rope_table": [_vp, _vp, _i64, _i32, _i32, _i32, _f64, _vp],
     "gh_qk_norm_rope_fwd": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
@@ -120,7 +120,7 @@ SIGNATURES: dict[str, list] = {
     "gh_softmax_rows": [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp],
     "gh_ae_sample_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp],
     "gh_sumsq_accum": [_vp, _i32, _i64, _vp, _vp],
-    "gh_adamw_step": [_vp, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _f32, _f32, _vp],
+    "gh_adamw_step": [_vp, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _f32, _f32, _vp, _vp],
 }
 
 _lib = None

@@ -219,7 +219,9 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__
 // ============================================================================
 // Column reductions (thread owns 8 columns, loops over a chunk of rows of ONE sample):
 //   MODE 0 (LN params):  acc0[b,c] += sum_l dy            acc1[b,c] += sum_l dy * n(x)
-//   MODE 1 (gate):       du = gate[b] * dy (written)      acc0[b,c] += sum_l dy * u
+//   MODE 1 (gate):       du = gate[b] * dy (written)      acc0[b,c] += sum_l dy * u     acc1[c] += sum_l du  (optional:
+//                        the bias gradient of the linear whose output u is -- du is that linear's dY, so its column
+//                        sum comes out of this pass instead of a separate read of du)
 //   MODE 2 (bias):       acc0[b,c] += sum_l dy
 // grid = (ceil(rpb / ROWS), B, ceil(C / (8 * blockDim.x)))
 // ============================================================================
@@ -229,7 +231,8 @@ __global__ void __launch_bounds__(512) col_reduce_kernel(const bf16* __restrict_
                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                                          const bf16* __restrict__ gate, int64_t gate_ld,
                                                          bf16* __restrict__ du, RowMap dum, float* __restrict__ acc0,
-                                                         float* __restrict__ acc1, int64_t acc_ld, int rows_per_cta) {
+                                                         float* __restrict__ acc1, int64_t acc_ld, int64_t acc1_ld,
+                                                         int rows_per_cta) {
   // blockDim = (C / 8 column groups, ny row lanes): thread (tx, ty) owns 8 columns and the rows l0 + ty + k * ny of
   // its CTA's chunk; the ny partial sums meet in shared memory, so one CTA issues ONE atomic per column however
   // many rows it covers (same-address atomics serialise in L2: fewer, fatter CTAs beat many small ones).
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(512) col_reduce_kernel(const bf16* __restrict_
         float fu[8], o[8];
         unpack8(vx, fu);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a0[j] += fd[j] * fu[j]; o[j] = g[j] * fd[j]; }
+        for (int j = 0; j < 8; ++j) { a0[j] += fd[j] * fu[j]; o[j] = g[j] * fd[j]; a1[j] += o[j]; }
         *reinterpret_cast<uint4*>(out) = pack8(o);
       } else {
 #pragma unroll
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(512) col_reduce_kernel(const bf16* __restrict_
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     atomicAdd(acc0 + static_cast<int64_t>(b) * acc_ld + c + j, a0[j]);
-    if (MODE == 0 && acc1) atomicAdd(acc1 + static_cast<int64_t>(b) * acc_ld + c + j, a1[j]);
+    if (MODE != 2 && acc1) atomicAdd(acc1 + static_cast<int64_t>(b) * acc1_ld + c + j, a1[j]);
   }
 }
 
@@ -616,7 +619,7 @@ extern "C" int gh_layernorm_bwd_dx(const void* dy, const gh_rows_view* dyv, cons
 static int launch_col_reduce(int mode, const void* dy, const gh_rows_view* dyv, const void* x, const gh_rows_view* xv,
                              int32_t batches, int32_t C, const float* mean, const float* rstd, const void* gate,
                              int64_t gate_ld, void* du, const gh_rows_view* duv, float* acc0, float* acc1,
-                             int64_t acc_ld, void* stream, const char* who) {
+                             int64_t acc_ld, int64_t acc1_ld, void* stream, const char* who) {
   GH_REQUIRE(dy && dyv && acc0, GH_ERR_NULL, "%s: NULL pointer", who);
   if (batches == 0 || dyv->rows_per_batch == 0) return GH_OK;
   GH_REQUIRE(C > 0 && C % 8 == 0, GH_ERR_BAD_SHAPE, "%s: C=%d must be a multiple of 8", who, C);
@@ -641,7 +644,7 @@ static int launch_col_reduce(int mode, const void* dy, const gh_rows_view* dyv, 
 #define GH_CR(M)                                                                                                   \
   col_reduce_kernel<M><<<grid, block, smem, s>>>(static_cast<const bf16*>(dy), dym, static_cast<const bf16*>(x), xm, C, \
                                                 mean, rstd, static_cast<const bf16*>(gate), gate_ld,                  \
-                                                static_cast<bf16*>(du), dum, acc0, acc1, acc_ld, rows_per_cta)
+                                                static_cast<bf16*>(du), dum, acc0, acc1, acc_ld, acc1_ld, rows_per_cta)
   if (mode == 0) GH_CR(0);
   else if (mode == 1) GH_CR(1);
   else GH_CR(2);
@@ -655,22 +658,22 @@ extern "C" int gh_layernorm_bwd_params(const void* dy, const gh_rows_view* dyv, 
                                        float* dshift_acc, float* dscale_acc, int64_t acc_ld, void* stream) {
   GH_REQUIRE(x && mean && rstd, GH_ERR_NULL, "gh_layernorm_bwd_params: NULL pointer");
   return launch_col_reduce(0, dy, dyv, x, xv, batches, C, mean, rstd, nullptr, 0, nullptr, nullptr, dshift_acc,
-                           dscale_acc, acc_ld, stream, "gh_layernorm_bwd_params");
+                           dscale_acc, acc_ld, acc_ld, stream, "gh_layernorm_bwd_params");
 }
 
 extern "C" int gh_gate_bwd(const void* dout, const gh_rows_view* dov, const void* u, const gh_rows_view* uv,
                            int32_t batches, int32_t C, const void* gate, int64_t gate_ld, void* du,
-                           const gh_rows_view* duv, float* dgate_acc, int64_t acc_ld, void* stream) {
+                           const gh_rows_view* duv, float* dgate_acc, int64_t acc_ld, float* dbias_acc, void* stream) {
   GH_REQUIRE(u && gate && du, GH_ERR_NULL, "gh_gate_bwd: NULL pointer");
   GH_REQUIRE(gate_ld % 8 == 0, GH_ERR_ALIGN, "gh_gate_bwd: gate_ld must be a multiple of 8");
   return launch_col_reduce(1, dout, dov, u, uv, batches, C, nullptr, nullptr, gate, gate_ld, du, duv, dgate_acc,
-                           nullptr, acc_ld, stream, "gh_gate_bwd");
+                           dbias_acc, acc_ld, 0, stream, "gh_gate_bwd");
 }
 
 extern "C" int gh_colsum(const void* dy, const gh_rows_view* dyv, int32_t batches, int32_t C, float* acc,
                          int64_t acc_ld, void* stream) {
   return launch_col_reduce(2, dy, dyv, nullptr, nullptr, batches, C, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
-                           acc, nullptr, acc_ld, stream, "gh_colsum");
+                           acc, nullptr, acc_ld, 0, stream, "gh_colsum");
 }
 
 extern "C" int gh_rope_table(const float* ids, void* cos_sin, int64_t n_tokens, int32_t axis0, int32_t axis1,

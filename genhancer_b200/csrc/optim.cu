@@ -75,6 +75,11 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ g, int
 
 struct AdamWArgs {
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale, max_norm;
+  // Device-resident step state (NULL: `bc1` / `bc2_sqrt` above were computed by the host from the by-value step):
+  // dev_state[0] = optimizer step count (>= 1), dev_state[1] = 0 -> this launch is a no-op.  Lets the update be
+  // captured into the CUDA graph of the training step (a graph bakes by-value arguments in) and be skipped on
+  // the replay that follows an eager flush (checkpoint / end of training).
+  const int32_t* dev_state;
 };
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamWArgs& a, float clip) {
@@ -91,6 +96,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(T* __restrict__ p, const T* 
                                                     T* __restrict__ v, int64_t n, const float* __restrict__ gnorm_sq,
                                                     AdamWArgs a) {
   constexpr int V = Vec<T>::N;
+  if (a.dev_state != nullptr) {
+    if (a.dev_state[1] == 0) return;
+    const double st = static_cast<double>(a.dev_state[0]);   // once per thread: bias corrections from the device step
+    a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(a.beta1), st));
+    a.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.beta2), st)));
+  }
   // clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)); norm of the grad_scale-d gradients
   float clip = a.grad_scale;
   if (gnorm_sq != nullptr && a.max_norm > 0.f) {
@@ -146,16 +157,19 @@ extern "C" int gh_sumsq_accum(const void* g, int32_t dtype, int64_t numel, float
 
 extern "C" int gh_adamw_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int32_t dtype, int64_t numel,
                              float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                             const float* gnorm_sq, float max_norm, float grad_scale, void* stream) {
+                             const float* gnorm_sq, float max_norm, float grad_scale, const int32_t* dev_state,
+                             void* stream) {
   GH_REQUIRE(param && grad && exp_avg && exp_avg_sq, GH_ERR_NULL, "gh_adamw_step: NULL pointer");
-  GH_REQUIRE(numel > 0 && step >= 1, GH_ERR_BAD_SHAPE, "gh_adamw_step: numel and step must be positive");
+  GH_REQUIRE(numel > 0 && (step >= 1 || dev_state), GH_ERR_BAD_SHAPE,
+             "gh_adamw_step: numel must be positive and step >= 1 (or dev_state given)");
+  if (step < 1) step = 1;
   GH_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq), GH_ERR_ALIGN,
              "gh_adamw_step: buffers must be 16-byte aligned");
   AdamWArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
   a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
   a.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
-  a.grad_scale = grad_scale; a.max_norm = max_norm;
+  a.grad_scale = grad_scale; a.max_norm = max_norm; a.dev_state = dev_state;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == GH_BF16)
     adamw_kernel<__nv_bfloat16><<<grid_for(numel / 8), 256, 0, s>>>(

@@ -135,10 +135,32 @@ def _lin_fwd(x2d, w, b, **kw):
     return K.gemm(x2d, w, bias=b, **kw)
 
 
-def _lin_bwd(dy2d, x2d, w_name, b_name, P, sink: GradSink, need_dx=True, dx_kw=None):
-    """dx = dy @ W ; dW (+)= dy^T x ; db += colsum(dy)."""
+# The conditioning side of the DiT -- the 11 Modulation GEMMs (all functions of `vec` alone) and the txt stream of the
+# double blocks (B rows in image mode) -- is a chain of 32-row GEMMs that each stream a whole weight matrix through
+# 48-144 CTAs in 25-70 us: HBM/latency-bound work that leaves the tensor pipe idle.  It runs on its own stream beside
+# the img stream (which is tensor-bound) and meets it only where the reference's dataflow does: the joint attention
+# (q/k/v of both streams) and the concat before the single blocks.  Inside the step graph it is a forked branch.
+# GH_COND_STREAM=0 switches it off (everything on the caller's stream).
+OVERLAP_COND = os.environ.get("GH_COND_STREAM", "1") != "0"
+_COND_STREAMS: dict = {}
+
+
+def _cond_stream(dev):
+    st = _COND_STREAMS.get(dev.index)
+    if st is None:
+        st = _COND_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def _bias_acc(sink: GradSink, b_name: str):
+    """The fp32 accumulator of a bias gradient when the kernel that PRODUCES dY also sums its columns (gh_gate_bwd)."""
+    return sink.small(b_name) if sink.wants(b_name) else None
+
+
+def _lin_bwd(dy2d, x2d, w_name, b_name, P, sink: GradSink, need_dx=True, dx_kw=None, bias_done=False):
+    """dx = dy @ W ; dW (+)= dy^T x ; db += colsum(dy)  (``bias_done``: db already came out of the producer of dy)."""
     w = P[w_name]
-    want_w, want_b = sink.wants(w_name), b_name is not None and sink.wants(b_name)
+    want_w, want_b = sink.wants(w_name), b_name is not None and sink.wants(b_name) and not bias_done
     if want_w or want_b:
         with sink.side(dy2d, x2d):      # leaves of the backward: off the critical path
             if want_w:
@@ -209,30 +231,71 @@ def flux_forward(P: dict, cfg, img, img_ids, txt, txt_ids, timesteps, y, guidanc
 
     x_img = x_img.view(B, Li, C)
     x_txt = x_txt.view(B, Lt, C)
+
+    # ---- every Modulation of the network: functions of svec alone (layers.py:162-175) ----
+    main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
+    # the txt stream only pays as a separate branch while it is a handful of rows (image mode: Lt = 1); in the video
+    # modes it is 1152-1728 tokens per sample, tensor-bound like the img stream
+    side = _cond_stream(dev) if (OVERLAP_COND and main is not None) else None
+    txt_side = side if (side is not None and B * Lt <= 256) else None
+    mod_names = [(f"double_blocks.{bi}.{s}_mod", f"double_blocks.{bi}.{s}_mod.lin", 6) for bi in range(cfg.depth)
+                 for s in ("img", "txt")]
+    mod_names += [(f"single_blocks.{bi}.mod", f"single_blocks.{bi}.modulation.lin", 3) for bi in range(cfg.depth_single_blocks)]
+    mod_names += [("final.mod", "final_layer.adaLN_modulation.1", 2)]
+    mod_out = {key: torch.empty(B, n * C, dtype=BF16, device=dev) for key, _, n in mod_names}   # (allocated on the caller's stream)
+    mod_ready = {}
+    if side is not None:
+        side.wait_stream(main)                      # svec
+    with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+        for key, lin, _ in mod_names:
+            _lin_fwd(svec, P[f"{lin}.weight"], P[f"{lin}.bias"], out=mod_out[key])
+            S[key] = mod_out[key]
+            if side is not None:
+                mod_ready[key] = torch.cuda.Event()
+                mod_ready[key].record(side)
+
+    def mod_of(key, stream=None):
+        """The modulation tensor ``key``; the consumer's stream waits for the GEMM that produces it."""
+        ev = mod_ready.get(key)
+        if ev is not None:
+            (stream or torch.cuda.current_stream(dev)).wait_event(ev)
+        return mod_out[key]
+
+    def on_txt_stream():
+        return torch.cuda.stream(txt_side) if txt_side is not None else contextlib.nullcontext()
+
+    if txt_side is not None:
+        txt_side.wait_stream(main)                  # x_txt (txt_in ran on the caller's stream)
     for bi in range(cfg.depth):
         p = f"double_blocks.{bi}"
-        mods = {}
-        for s in ("img", "txt"):
-            mods[s] = _lin_fwd(svec, P[f"{p}.{s}_mod.lin.weight"], P[f"{p}.{s}_mod.lin.bias"])  # [B, 6C]
-            S[f"{p}.{s}_mod"] = mods[s]
+        mods = {"img": mod_of(f"{p}.img_mod")}
+        with on_txt_stream():
+            mods["txt"] = mod_of(f"{p}.txt_mod")
         q = torch.empty(B, H, L, D, dtype=BF16, device=dev)
         k = torch.empty_like(q)
         v = torch.empty_like(q)
+        if txt_side is not None:
+            txt_side.wait_stream(main)              # q/k/v are fresh allocations: whatever last used that memory is done
         xs = {"img": x_img, "txt": x_txt}
         for s, l_off in (("txt", 0), ("img", Lt)):
-            m = mods[s]
-            h = adaln(f"{p}.{s}_norm1", xs[s], m[:, 0:C], m[:, C:2 * C])
-            qkv = _lin_fwd(h.view(-1, C), P[f"{p}.{s}_attn.qkv.weight"], P[f"{p}.{s}_attn.qkv.bias"])
-            qkv = qkv.view(B, -1, 3 * C)
-            S[f"{p}.{s}_qkv"] = qkv
-            K.qk_norm_rope_fwd(qkv, H, P[f"{p}.{s}_attn.norm.query_norm.scale"],
-                               P[f"{p}.{s}_attn.norm.key_norm.scale"], cs, q, k, v, l_off)
+            with (on_txt_stream() if s == "txt" else contextlib.nullcontext()):
+                m = mods[s]
+                h = adaln(f"{p}.{s}_norm1", xs[s], m[:, 0:C], m[:, C:2 * C])
+                qkv = _lin_fwd(h.view(-1, C), P[f"{p}.{s}_attn.qkv.weight"], P[f"{p}.{s}_attn.qkv.bias"])
+                qkv = qkv.view(B, -1, 3 * C)
+                S[f"{p}.{s}_qkv"] = qkv
+                K.qk_norm_rope_fwd(qkv, H, P[f"{p}.{s}_attn.norm.query_norm.scale"],
+                                   P[f"{p}.{s}_attn.norm.key_norm.scale"], cs, q, k, v, l_off)
         attn_t = torch.empty(B, Lt, C, dtype=BF16, device=dev)
         attn_i = torch.empty(B, Li, C, dtype=BF16, device=dev)
+        if txt_side is not None:
+            main.wait_stream(txt_side)              # the txt rows of q / k / v
         lse = K.flash_attn_fwd(q, k, v, scale, attn_i, attn_t, Lt)
+        if txt_side is not None:
+            txt_side.wait_stream(main)              # attn_t
         S[f"{p}.q"], S[f"{p}.k"], S[f"{p}.v"], S[f"{p}.lse"] = q, k, v, lse
         S[f"{p}.attn_t"], S[f"{p}.attn_i"] = attn_t, attn_i
-        for s, attn, rpb in (("img", attn_i, Li), ("txt", attn_t, Lt)):
+        def after_attention(s, attn, rpb):
             m = mods[s]
             x = xs[s]
             u1 = torch.empty(B * rpb, C, dtype=BF16, device=dev)
@@ -248,15 +311,20 @@ def flux_forward(P: dict, cfg, img, img_ids, txt, txt_ids, timesteps, y, guidanc
                          rows_per_batch=rpb, residual=x.view(-1, C), aux_out=u2).view(B, rpb, C)
             S[f"{p}.{s}_mlp_pre"], S[f"{p}.{s}_mlp_a"], S[f"{p}.{s}_u2"] = pre, a, u2
             xs[s] = x
+
+        after_attention("img", attn_i, Li)
+        with on_txt_stream():
+            after_attention("txt", attn_t, Lt)
         x_img, x_txt = xs["img"], xs["txt"]
 
+    if txt_side is not None:
+        main.wait_stream(txt_side)                  # x_txt of the last double block
     x = torch.empty(B, L, C, dtype=BF16, device=dev)
     x[:, :Lt].copy_(x_txt)
     x[:, Lt:].copy_(x_img)
     for bi in range(cfg.depth_single_blocks):
         p = f"single_blocks.{bi}"
-        m = _lin_fwd(svec, P[f"{p}.modulation.lin.weight"], P[f"{p}.modulation.lin.bias"])  # [B, 3C]
-        S[f"{p}.mod"] = m
+        m = mod_of(f"{p}.mod")  # [B, 3C]
         h = adaln(f"{p}.pre_norm", x, m[:, 0:C], m[:, C:2 * C])
         w1, b1 = P[f"{p}.linear1.weight"], P[f"{p}.linear1.bias"]
         qkv = _lin_fwd(h.view(-1, C), w1[:3 * C], b1[:3 * C]).view(B, L, 3 * C)
@@ -275,8 +343,9 @@ def flux_forward(P: dict, cfg, img, img_ids, txt, txt_ids, timesteps, y, guidanc
         S[f"{p}.qkv"], S[f"{p}.cat"], S[f"{p}.mlp_pre"], S[f"{p}.u"] = qkv, catb, pre, u
         S[f"{p}.q"], S[f"{p}.k"], S[f"{p}.v"], S[f"{p}.lse"] = q, k, v, lse
 
-    mf = _lin_fwd(svec, P["final_layer.adaLN_modulation.1.weight"], P["final_layer.adaLN_modulation.1.bias"])
-    S["final.mod"] = mf
+    mf = mod_of("final.mod")
+    if side is not None:
+        main.wait_stream(side)                      # (every branch of the forward has joined the caller's stream)
     hf = adaln("final.norm", x[:, Lt:], mf[:, 0:C], mf[:, C:2 * C])  # chunk order: shift, scale (layers.py:569)
     pred = _lin_fwd(hf.view(-1, C), P["final_layer.linear.weight"], P["final_layer.linear.bias"])
     return pred.view(B, Li, in_ch), ctx
@@ -294,17 +363,19 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
     dsvec = torch.zeros(B, C, dtype=F32, device=dev)  # every Modulation feeds it
 
     def mod_bwd(dmod_acc, w_name, b_name):
-        """dmod_acc fp32 [B, n] -> param grads of the modulation linear, dsvec += dmod @ W."""
+        """dmod_acc fp32 [B, n] -> param grads of the modulation linear, dsvec += dmod @ W.  All of it is a leaf of the
+        backward (dsvec is read only after the last block), so it rides the wgrad side stream."""
         dmod = torch.empty(dmod_acc.shape, dtype=BF16, device=dev)
-        K.accum_cast(dmod_acc, dmod)
-        # [B, n] x [n, C] with B = 32 rows: one M tile and 12-48 N tiles would leave most SMs idle while each CTA
-        # streams the whole K = n (up to 18432) alone -> split-K over the machine, partials red.add-ed into dsvec
-        K.gemm(dmod, P[w_name], b_mn=True, out=dsvec, k_splits=-1)
-        if sink.wants(w_name):
-            gw, res = sink.big(w_name)
-            K.gemm(dmod, svec, a_mn=True, b_mn=True, out=gw, residual=res)
-        if sink.wants(b_name):
-            K.colsum(dmod, sink.small(b_name))
+        with sink.side(dmod_acc, dmod):
+            K.accum_cast(dmod_acc, dmod)
+            # [B, n] x [n, C] with B = 32 rows: one M tile and 12-48 N tiles would leave most SMs idle while each CTA
+            # streams the whole K = n (up to 18432) alone -> split-K over the machine, partials red.add-ed into dsvec
+            K.gemm(dmod, P[w_name], b_mn=True, out=dsvec, k_splits=-1)
+            if sink.wants(w_name):
+                gw, res = sink.big(w_name)
+                K.gemm(dmod, svec, a_mn=True, b_mn=True, out=gw, residual=res)
+            if sink.wants(b_name):
+                K.colsum(dmod, sink.small(b_name))
 
     def adaln_bwd(name, dh3d, mod, sh_off, dmod_acc, dres=None, out=None):
         x, mean, rstd = S[f"{name}.x"], S[f"{name}.mean"], S[f"{name}.rstd"]
@@ -328,7 +399,8 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
         dmod = torch.zeros(B, 3 * C, dtype=F32, device=dev)
         catb, pre, qkv = S[f"{p}.cat"], S[f"{p}.mlp_pre"], S[f"{p}.qkv"]
         # out = x + gate * u
-        du = K.gate_bwd(dx, S[f"{p}.u"].view(B, L, C), m[:, 2 * C:3 * C], dmod[:, 2 * C:3 * C])
+        du = K.gate_bwd(dx, S[f"{p}.u"].view(B, L, C), m[:, 2 * C:3 * C], dmod[:, 2 * C:3 * C],
+                        dbias_acc=_bias_acc(sink, f"{p}.linear2.bias"))
         # linear2: u = cat @ W2^T + b2 ;  dcat[:, :C] = dattn, dcat[:, C:] = da -> * gelu'(pre) fused in the dgrad epilogue
         du2d = du.view(-1, C)
         w2 = P[f"{p}.linear2.weight"]
@@ -337,8 +409,6 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
             if sink.wants(f"{p}.linear2.weight"):
                 gw, res = sink.big(f"{p}.linear2.weight")
                 K.gemm(du2d, catb, a_mn=True, b_mn=True, out=gw, residual=res)
-            if sink.wants(f"{p}.linear2.bias"):
-                K.colsum(du2d, sink.small(f"{p}.linear2.bias"))
         dattn = K.gemm(du2d, w2[:, :C], b_mn=True)
         K.gemm(du2d, w2[:, C:], b_mn=True, act=ACT_GELU_TANH, act_grad=True, aux_in=pre, out=dl1[:, 3 * C:])
         # attention
@@ -369,17 +439,19 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
             m = S[f"{p}.{s}_mod"]
             dxo = dxs[s]
             # x_out = x_mid + gate2 * u2 ; u2 = a @ W2^T + b2 ; a = gelu(pre) ; pre = h2 @ W1^T + b1
-            du2 = K.gate_bwd(dxo, S[f"{p}.{s}_u2"].view(B, rpb, C), m[:, 5 * C:6 * C], dmods[s][:, 5 * C:6 * C])
+            du2 = K.gate_bwd(dxo, S[f"{p}.{s}_u2"].view(B, rpb, C), m[:, 5 * C:6 * C], dmods[s][:, 5 * C:6 * C],
+                             dbias_acc=_bias_acc(sink, f"{p}.{s}_mlp.2.bias"))
             dpre = _lin_bwd(du2.view(-1, C), S[f"{p}.{s}_mlp_a"], f"{p}.{s}_mlp.2.weight", f"{p}.{s}_mlp.2.bias", P, sink,
-                            dx_kw=dict(act=ACT_GELU_TANH, act_grad=True, aux_in=S[f"{p}.{s}_mlp_pre"]))
+                            dx_kw=dict(act=ACT_GELU_TANH, act_grad=True, aux_in=S[f"{p}.{s}_mlp_pre"]), bias_done=True)
             h2 = S[f"{p}.{s}_norm2.h"]
             dh2 = _lin_bwd(dpre, h2.view(-1, C), f"{p}.{s}_mlp.0.weight", f"{p}.{s}_mlp.0.bias", P, sink)
             dxm = adaln_bwd(f"{p}.{s}_norm2", dh2.view(B, rpb, C), m, 3 * C, dmods[s], dres=dxo)
             # x_mid = x_in + gate1 * u1 ; u1 = attn @ Wp^T + bp
-            du1 = K.gate_bwd(dxm, S[f"{p}.{s}_u1"].view(B, rpb, C), m[:, 2 * C:3 * C], dmods[s][:, 2 * C:3 * C])
+            du1 = K.gate_bwd(dxm, S[f"{p}.{s}_u1"].view(B, rpb, C), m[:, 2 * C:3 * C], dmods[s][:, 2 * C:3 * C],
+                             dbias_acc=_bias_acc(sink, f"{p}.{s}_attn.proj.bias"))
             attn = S[f"{p}.attn_i"] if s == "img" else S[f"{p}.attn_t"]
             dattn[s] = _lin_bwd(du1.view(-1, C), attn.view(-1, C), f"{p}.{s}_attn.proj.weight",
-                                f"{p}.{s}_attn.proj.bias", P, sink).view(B, rpb, C)
+                                f"{p}.{s}_attn.proj.bias", P, sink, bias_done=True).view(B, rpb, C)
             dx_mid[s] = dxm
             if bi == 0 and sink.on_ready is not None:
                 # the LAST block of the backward: announce its sub-modules as their gradients become final, so the
@@ -411,6 +483,7 @@ def flux_backward(P: dict, cfg, ctx: FluxCtx, dpred: torch.Tensor, sink: GradSin
     # ---- input projections and the conditioning vector ----
     d_img = _lin_bwd(dxs["img"].reshape(-1, C), S["img2d"], "img_in.weight", "img_in.bias", P, sink, need_dx=need_dimg)
     d_txt = _lin_bwd(dxs["txt"].reshape(-1, C), S["txt2d"], "txt_in.weight", "txt_in.bias", P, sink, need_dx=need_dtxt)
+    sink.join()                                     # every Modulation's contribution to dsvec
     dsv = torch.empty(B, C, dtype=BF16, device=dev)
     K.accum_cast(dsvec, dsv)
     dvec = K.act_bwd(dsv, S["vec"], ACT_SILU)  # vec = sum of the three embedders -> same gradient to each

@@ -236,8 +236,9 @@ def layernorm_bwd_params(dy, x, mean, rstd, dshift_acc, dscale_acc):
     _count()
 
 
-def gate_bwd(dout, u, gate, dgate_acc, out=None):
-    """out = res + gate[b]*u  ->  du = gate[b]*dout (returned), dgate_acc[b,:] += sum_l dout*u."""
+def gate_bwd(dout, u, gate, dgate_acc, out=None, dbias_acc=None):
+    """out = res + gate[b]*u  ->  du = gate[b]*dout (returned), dgate_acc[b,:] += sum_l dout*u;
+    ``dbias_acc`` (fp32 [C]) += column sums of du (the bias gradient of the linear that produced u)."""
     _ensure(dout)
     dov, _, Cc, nb = _rows_view(dout)
     uv = _rows_view(u)[0]
@@ -246,7 +247,7 @@ def gate_bwd(dout, u, gate, dgate_acc, out=None):
     duv = _rows_view(out)[0]
     check(_lib.lib().gh_gate_bwd(dout.data_ptr(), C.byref(dov), u.data_ptr(), C.byref(uv), nb, Cc, gate.data_ptr(),
                                  gate.stride(0), out.data_ptr(), C.byref(duv), dgate_acc.data_ptr(),
-                                 dgate_acc.stride(0) if dgate_acc.dim() == 2 else 0, _stream()))
+                                 dgate_acc.stride(0) if dgate_acc.dim() == 2 else 0, _p(dbias_acc), _stream()))
     _count()
     return out
 
@@ -532,14 +533,17 @@ def sumsq_accum(g: torch.Tensor, acc: torch.Tensor) -> None:
     _count()
 
 
-def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0):
-    """In-place AdamW on flat contiguous buffers of one dtype; optional fused clip-by-global-norm."""
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0,
+               dev_state=None):
+    """In-place AdamW on flat contiguous buffers of one dtype; optional fused clip-by-global-norm.
+    ``dev_state`` (int32[2] on the device: step count, enable flag) replaces the by-value ``step`` -- the form a
+    CUDA graph can replay (see gh_adamw_step)."""
     _ensure(p)
     assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
     assert p.dtype == g.dtype == m.dtype == v.dtype and p.numel() == g.numel() == m.numel() == v.numel()
     check(_lib.lib().gh_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _dt(p), p.numel(), lr, beta1,
                                    beta2, eps, weight_decay, int(step), _p(gnorm_sq), float(max_norm),
-                                   float(grad_scale), _stream()))
+                                   float(grad_scale), _p(dev_state), _stream()))
     _count()
 
 

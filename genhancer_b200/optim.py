@@ -93,6 +93,8 @@ class FusedAdamW:
             g.exp_avg = torch.zeros_like(g.flat_p)
             g.exp_avg_sq = torch.zeros_like(g.flat_p)
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=groups[0].flat_p.device)
+        # device-resident [step count, update pending]: what a captured update reads (see step_captured)
+        self.dev_state = torch.zeros(2, dtype=torch.int32, device=groups[0].flat_p.device)
         self._managed_dtypes = {p.dtype for m in self.engine_managed for p in m.parameters()}
         self.zero_grad()
 
@@ -117,15 +119,41 @@ class FusedAdamW:
             K.adamw_step(g.flat_p, g.flat_g, g.exp_avg, g.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
                          self.weight_decay, self.step_count, self.gnorm_sq, self.max_grad_norm, grad_scale)
 
+    @torch.no_grad()
+    def step_captured(self, grad_scale: float = 1.0) -> None:
+        """The same update in a form a CUDA graph can replay (``graph.PipelinedTrainStep``): the step count lives in
+        ``dev_state[0]`` and advances by ``dev_state[1]`` (1 = the gradients of a finished backward are waiting,
+        0 = nothing pending: every kernel below is then a no-op on the parameters).  The caller captures
+        ``mark_pending()`` after the backward and keeps ``step_count`` (the host mirror) in step with the replays."""
+        self.dev_state[0:1] += self.dev_state[1:2]
+        self.gnorm_sq.zero_()
+        for g in self.groups:
+            K.sumsq_accum(g.flat_g, self.gnorm_sq)
+        for g in self.groups:
+            K.adamw_step(g.flat_p, g.flat_g, g.exp_avg, g.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
+                         self.weight_decay, 0, self.gnorm_sq, self.max_grad_norm, grad_scale, dev_state=self.dev_state)
+
+    def mark_pending(self, pending: bool = True) -> None:
+        """dev_state[1] = pending (a stream-ordered fill: capturable)."""
+        self.dev_state[1:2].fill_(1 if pending else 0)
+
+    def sync_device_state(self) -> None:
+        """After an eager ``step()``: the device copy of the step count follows the host's, nothing is pending."""
+        self.dev_state.copy_(torch.tensor([self.step_count, 0], dtype=torch.int32), non_blocking=False)
+
     # ---- checkpoint layout of the reference: optimizer-state-{N}.bin = torch optimizer.state_dict() ----------
     def state_dict(self) -> dict:
+        """torch.optim.AdamW.state_dict() layout (tensors on the host).  Parameter indices follow the flat groups
+        (per dtype, in module order: bf16 DiT first, then the fp32 projectors / adapter), not the reference's
+        ``super_model.parameters()`` order: the file round-trips through ``load_state_dict`` here, it is not
+        index-compatible with a torch optimizer built over the reference's module."""
         state, idx = {}, 0
         for g in self.groups:
             for p, off in zip(g.params, g.offsets):
                 sl = slice(off, off + p.numel())
                 state[idx] = {"step": torch.tensor(float(self.step_count)),
-                              "exp_avg": g.exp_avg[sl].view(p.shape).clone(),
-                              "exp_avg_sq": g.exp_avg_sq[sl].view(p.shape).clone()}
+                              "exp_avg": g.exp_avg[sl].view(p.shape).cpu(),      # straight to the host: no
+                              "exp_avg_sq": g.exp_avg_sq[sl].view(p.shape).cpu()}  # second copy of the moments in HBM
                 idx += 1
         pg = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
               "amsgrad": False, "params": list(range(idx))}
@@ -142,3 +170,4 @@ class FusedAdamW:
                     g.exp_avg_sq[sl].copy_(st["exp_avg_sq"].reshape(-1))
                     self.step_count = int(float(st["step"]))
                 idx += 1
+        self.sync_device_state()

@@ -165,7 +165,7 @@ def load_checkpoint(out_dir: str, step: int, dit, clip_vis, adapter, opt, video:
             clip_vis.project_t5.load_state_dict(ld(f"checkpoint-project-t5-{step}.bin"), strict=strict)
     op = os.path.join(out_dir, f"optimizer-state-{step}.bin")
     if opt is not None and os.path.exists(op):
-        opt.load_state_dict(torch.load(op, map_location="cpu", weights_only=False))
+        opt.load_state_dict(torch.load(op, map_location="cpu", weights_only=True))
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -186,10 +186,12 @@ int gh_layernorm_bwd_params(const void* dy, const gh_rows_view* dyv, const void*
                             int32_t batches, int32_t C, const float* mean, const float* rstd, float* dshift_acc,
                             float* dscale_acc, int64_t acc_ld, void* stream);
 /* Backward of the gated residual  out = res + gate[b] * u  (layers.py:331-336,500):
- *   du = gate[b] * dout ;  dgate_acc[b,c] += sum_l dout * u. */
+ *   du = gate[b] * dout ;  dgate_acc[b,c] += sum_l dout * u ;
+ *   dbias_acc (fp32 [C], may be NULL): dbias_acc[c] += sum_{b,l} du -- u is the output of a biased Linear, so du is that
+ *   Linear's dY and its bias gradient falls out of this pass (no separate gh_colsum read of du). */
 int gh_gate_bwd(const void* dout, const gh_rows_view* dov, const void* u, const gh_rows_view* uv, int32_t batches,
                 int32_t C, const void* gate, int64_t gate_ld, void* du, const gh_rows_view* duv, float* dgate_acc,
-                int64_t acc_ld, void* stream);
+                int64_t acc_ld, float* dbias_acc, void* stream);
 /* acc[b,c] += sum_l dy[b,l,c]  (bias gradients). */
 int gh_colsum(const void* dy, const gh_rows_view* dyv, int32_t batches, int32_t C, float* acc, int64_t acc_ld,
               void* stream);
@@ -350,11 +352,15 @@ int gh_ae_sample_patchify(const float* moments_nhwc, const float* noise_nchw, fl
  *   (gnorm_sq NULL or max_norm <= 0: no clipping).  param/grad/exp_avg/exp_avg_sq share `dtype`
  *   (bf16 DiT with bf16 states, fp32 projectors with fp32 states -- no fp32 master copy, as the
  *   reference); fp32 arithmetic, one rounding on store.  step >= 1 is the bias-correction count.
+ *   dev_state (device int32[2], may be NULL): when given, the bias-correction count is read from
+ *   dev_state[0] on the device instead of `step`, and the launch is a no-op while dev_state[1] == 0.
+ *   That makes the update capturable into the CUDA graph of the training step (graph.PipelinedTrainStep:
+ *   the update of step n runs on a side branch under step n+1's frozen AE / tower forward).
  * -------------------------------------------------------------------------- */
 int gh_sumsq_accum(const void* g, int32_t dtype, int64_t numel, float* acc, void* stream);
 int gh_adamw_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int32_t dtype, int64_t numel,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                  const float* gnorm_sq, float max_norm, float grad_scale, void* stream);
+                  const float* gnorm_sq, float max_norm, float grad_scale, const int32_t* dev_state, void* stream);
 
 #ifdef __cplusplus
 }

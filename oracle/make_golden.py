@@ -74,8 +74,9 @@ def load_subset(module, sd):
     return missing
 
 
-def build_reference_wrapper(tc: O.TowerCfg, clip_dim: int, t5_dim: int, seed: int):
-    """The reference's own OpenAICLIP / SigLIP wrapper around a random-init HF model, then our synthetic weights."""
+def build_reference_wrapper(tc: O.TowerCfg, clip_dim: int, t5_dim: int, seed: int, metaclip: str | None = None):
+    """The reference's own OpenAICLIP / SigLIP / MetaCLIP wrapper around a random-init HF model, then our synthetic
+    weights.  ``metaclip`` = "large" | "huge" takes the MetaCLIP class (CLIP_bank.py:76-122) instead of OpenAICLIP."""
     model = ref_clip_model(tc)
 
     class Cfg:
@@ -83,7 +84,11 @@ def build_reference_wrapper(tc: O.TowerCfg, clip_dim: int, t5_dim: int, seed: in
         pass
     Cfg.clip_dim, Cfg.t5_dim = clip_dim, t5_dim
     shim = type("Shim", (), {"from_pretrained": staticmethod(lambda *a, **k: model)})
-    if tc.kind == "clip":
+    if tc.kind == "clip" and metaclip is not None:
+        bank.CLIPModel = shim
+        Cfg.clip_type = metaclip
+        wrap = bank.MetaCLIP(Cfg())
+    elif tc.kind == "clip":
         bank.CLIPModel = shim
         wrap = bank.OpenAICLIP(Cfg())
     else:
@@ -105,9 +110,9 @@ def build_reference_wrapper(tc: O.TowerCfg, clip_dim: int, t5_dim: int, seed: in
     return wrap, sd_t, sd_w, ks_t, ks_w
 
 
-def golden_tower(name: str, tc: O.TowerCfg, clip_dim=48, t5_dim=96, B=2, seed=11):
+def golden_tower(name: str, tc: O.TowerCfg, clip_dim=48, t5_dim=96, B=2, seed=11, metaclip: str | None = None):
     print(f"[tower:{name}]")
-    wrap, sd_t, sd_w, ks_t, ks_w = build_reference_wrapper(tc, clip_dim, t5_dim, seed)
+    wrap, sd_t, sd_w, ks_t, ks_w = build_reference_wrapper(tc, clip_dim, t5_dim, seed, metaclip)
     g = torch.Generator().manual_seed(seed)
     img = torch.rand(B, 3, tc.image_size, tc.image_size, generator=g)
     mean = torch.tensor(OPENAI_MEAN if tc.kind == "clip" else (0.5,) * 3).view(1, 3, 1, 1)
@@ -209,6 +214,29 @@ def golden_tower_lora(name: str, tc: O.TowerCfg, all_linear: bool, clip_dim=48, 
               class_token=cls.detach(), projection_clip=pc.detach(), projection_t5=pt5.detach(), loss=loss.detach(),
               grads=grads)
     torch.save(fx, os.path.join(GOLD, f"tower_lora_{name}.pt"))
+
+
+def golden_prepare_clip(seed=81):
+    """The reference's ``prepare_clip`` (clip_models/sampling.py:9-42) around its own OpenAICLIP wrapper: the dict the
+    image-mode scripts feed the DiT with (img patchified, (0,row,col) img_ids, zero txt_ids, txt, vec)."""
+    print("[prepare_clip]")
+    tc = O.TowerCfg("clip", 128, 2, 2, 512, 56, 14, 64, 1e-5, "quick_gelu")
+    wrap, sd_t, sd_w, ks_t, ks_w = build_reference_wrapper(tc, 48, 96, seed)
+    g = torch.Generator().manual_seed(seed)
+    B = 3
+    original_img = torch.randn(B, 3, 56, 56, generator=g)          # already CLIP-normalised, as the scripts pass it
+    latent = torch.randn(B, 16, 6, 10, generator=g)                # non-square on purpose: rows / cols must not swap
+    with torch.no_grad():
+        ref = prepare_clip(clip=wrap, original_img=original_img, img=latent)
+    close(O.patchify(latent), ref["img"], 0.0, "img (patchified)")
+    close(O.make_img_ids(B, 3, 5), ref["img_ids"], 0.0, "img_ids")
+    _, opc, opt5 = O.clip_wrapper_forward(sd_t, sd_w, original_img, tc)
+    close(opt5, ref["txt"], 2e-5, "txt")
+    close(opc, ref["vec"], 2e-5, "vec")
+    torch.save(dict(kind="prepare_clip", cfg=tc.__dict__, clip_dim=48, t5_dim=96, seed=seed, key_shapes_tower=ks_t,
+                    key_shapes_wrap=ks_w, original_img=original_img, latent=latent,
+                    out={k: v.detach().clone() for k, v in ref.items()}),
+               os.path.join(GOLD, "prepare_clip_small.pt"))
 
 
 def golden_ae(seed=21):
@@ -601,7 +629,7 @@ def golden_cfg1_full(seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="", help="comma-separated subset: tower,lora,ae,decoder,flux,sampler,step,video")
+    ap.add_argument("--only", default="", help="comma-separated subset: tower,metaclip,prepare,lora,ae,decoder,flux,sampler,step,video")
     ap.add_argument("--full", action="store_true", help="also run BASELINE config 1 at full size (~1-2 min, ~12 GB)")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -611,6 +639,11 @@ def main():
     if want("tower"):
         golden_tower("clip_small", O.TowerCfg("clip", 128, 2, 2, 512, 56, 14, 64, 1e-5, "quick_gelu"))
         golden_tower("siglip_small", O.TowerCfg("siglip", 144, 2, 2, 304, 56, 14, 144, 1e-6, "gelu_tanh"))
+    if want("metaclip"):   # MetaCLIP-H/14 geometry at reduced size: head_dim 80 (1280 / 16), through the reference's MetaCLIP class
+        golden_tower("metaclip_h_small", O.TowerCfg("clip", 160, 2, 2, 320, 56, 14, 64, 1e-5, "quick_gelu"), metaclip="huge",
+                     seed=13)
+    if want("prepare"):
+        golden_prepare_clip()
     if want("lora"):
         golden_tower_lora("clip_small", O.TowerCfg("clip", 128, 2, 2, 512, 56, 14, 64, 1e-5, "quick_gelu"), all_linear=True)
         golden_tower_lora("siglip_small", O.TowerCfg("siglip", 144, 2, 2, 304, 56, 14, 144, 1e-6, "gelu_tanh"), all_linear=False)

@@ -195,3 +195,31 @@ def test_oracle_ae_decoder():
         img = O.ae_decode(sd, fx["z"], ac)
     assert img.shape == fx["image"].shape == (2, 3, 48, 80)
     assert (img - fx["image"]).abs().max().item() <= 2e-5 * fx["image"].abs().max().item()
+
+
+def test_oracle_metaclip_h_geometry_and_prepare_clip():
+    """Fixtures minted from the reference's MetaCLIP(clip_type='huge') wrapper (head_dim 80) and from the reference's
+    prepare_clip (clip_models/sampling.py:9-42)."""
+    fx = load_golden("tower_metaclip_h_small.pt")
+    tc = O.TowerCfg(**fx["cfg"])
+    assert tc.hidden // tc.heads == 80
+    sd_t = O.synth_state_dict(fx["key_shapes_tower"], fx["seed"])
+    sd_w = O.synth_state_dict(fx["key_shapes_wrap"], fx["seed"] + 1)
+    mean = torch.tensor(OPENAI_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(OPENAI_STD).view(1, 3, 1, 1)
+    with torch.no_grad():
+        lhs, pooled = O.tower_forward(sd_t, (fx["img"] - mean) / std, tc)
+        cls, pc, pt5 = O.clip_wrapper_forward(sd_t, sd_w, (fx["img"] - mean) / std, tc)
+    assert rel_err(lhs, fx["last_hidden_state"]) < 1e-5 and rel_err(pooled, fx["pooler_output"]) < 1e-5
+    assert rel_err(cls, fx["class_token"]) < 1e-5 and rel_err(pc, fx["projection_clip"]) < 1e-5
+    assert rel_err(pt5, fx["projection_t5"]) < 1e-5
+    fp = load_golden("prepare_clip_small.pt")
+    ref = fp["out"]
+    B, _, h, w = fp["latent"].shape
+    assert torch.equal(O.patchify(fp["latent"]), ref["img"])
+    assert torch.equal(O.make_img_ids(B, h // 2, w // 2), ref["img_ids"])
+    assert ref["txt_ids"].shape == (B, 1, 3) and not ref["txt_ids"].any()
+    # the product's host-side pieces of prepare_clip on CPU tensors (no kernels involved): bit-equal
+    from genhancer_b200.clip_models.sampling import make_img_ids, patchify
+    assert torch.equal(patchify(fp["latent"]), ref["img"])
+    assert torch.equal(make_img_ids(B, h // 2, w // 2, "cpu"), ref["img_ids"])

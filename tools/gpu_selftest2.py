@@ -92,8 +92,10 @@ def test_gate_colsum():
     u = torch.randn(B, L, C, device=dev, generator=g).to(BF)
     gate = torch.randn(B, 3 * C, device=dev, generator=g).to(BF)[:, C:2 * C]
     acc = torch.zeros(B, C, device=dev)
-    du = K.gate_bwd(dout, u, gate, acc)
+    dbias = torch.zeros(acc.shape[-1], dtype=torch.float32, device=dout.device)
+    du = K.gate_bwd(dout, u, gate, acc, dbias_acc=dbias)
     check("gate_bwd du", du, gate.float()[:, None] * dout.float(), 5e-3)
+    check("gate_bwd dbias", dbias, (gate.float()[:, None] * dout.float()).sum((0, 1)), 5e-3)
     check("gate_bwd dgate", acc, (dout.float() * u.float()).sum(1), 5e-3)
     accb = torch.zeros(C, device=dev)
     K.colsum(dout, accb)
