@@ -104,8 +104,8 @@ SIGNATURES: dict[str, list] = {
     "gh_accum_cast": [_vp, _vp, _i32, _i64, _f32, _i32, _vp],
     "gh_euler_cfg_step": [_vp, _vp, _vp, _f32, _f32, _i64, _vp],
     "gh_batched_copy": [_vp, _i32, _i32, _vp],
-    "gh_dropout_fwd": [_vp, _vp, _i64, _f32, C.c_uint64, C.c_uint64, _vp],
-    "gh_dropout_bwd_add": [_vp, _vp, _i64, _f32, C.c_uint64, C.c_uint64, _vp],
+    "gh_dropout_fwd": [_vp, _vp, _i64, _f32, C.c_uint64, C.c_uint64, _vp, _vp],
+    "gh_dropout_bwd_add": [_vp, _vp, _i64, _f32, C.c_uint64, C.c_uint64, _vp, _vp],
     "gh_flash_attn_fwd": [_at, _at, _at, _i32, _i32, _i32, _i32, _i32, _f32, _ao, _vp, _vp],
     "gh_flash_attn_bwd": [_at, _at, _at, _ao, _ao, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _at, _at, _at, _vp, _vp,
                           _vp],

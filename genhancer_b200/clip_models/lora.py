@@ -107,19 +107,26 @@ def merged_state_dict(model) -> dict:
             name = key.replace("/", ".")
             sd[f"{name}.weight"] = sd[f"{name}.weight"] + cfg.scaling * (pair.B.float() @ pair.A.float()).to(sd[f"{name}.weight"].dtype)
     extra = getattr(model, "_passthrough_state", None)   # text tower etc. of a loaded HF checkpoint, untouched
+    if getattr(model, "_from_checkpoint", None) and extra is None:
+        raise RuntimeError("the tower was loaded from an HF checkpoint but its non-vision tensors were dropped: the merged "
+                           "export would lack the text tower (evaluation loads it with CLIPModel / SiglipModel.from_pretrained)")
+    # `text_projection` of this module is a placeholder (the text tower is not on the path): only a loaded one is saved
+    sd = {k: v for k, v in sd.items() if not k.startswith("text_projection")}
     if extra:
-        for k, v in extra.items():
-            sd.setdefault(k, v)
-    return {k: v for k, v in sd.items() if not k.startswith("text_projection") or (extra and k in extra)}
+        sd.update({k: v.detach().clone() for k, v in extra.items()})
+    return sd
 
 
 def save_pretrained(model, path: str) -> None:
     """``merge_and_unload().save_pretrained(path, safe_serialization=False)``: pytorch_model.bin + config.json."""
     import json
     import os
+    c = model.config
+    if getattr(model, "_from_checkpoint", None) and getattr(model, "_hf_config", None) is None:
+        raise RuntimeError(f"no config.json was found next to the checkpoint {model._from_checkpoint}: cannot write a "
+                           "loadable HF directory (text_config would be missing)")
     os.makedirs(path, exist_ok=True)
     torch.save({k: v.cpu() for k, v in merged_state_dict(model).items()}, os.path.join(path, "pytorch_model.bin"))
-    c = model.config
     cfg = getattr(model, "_hf_config", None) or {
         "model_type": "clip" if c.kind == "clip" else "siglip", "projection_dim": c.projection_dim,
         "vision_config": {"hidden_size": c.hidden_size, "intermediate_size": c.intermediate_size,

@@ -190,6 +190,7 @@ class TowerEngine:
         self.p_drop = float(getattr(self.lora_cfg, "lora_dropout", 0.0) or 0.0)
         self._drop_seed = None
         self._drop_calls = 0
+        self._drop_base = None      # int64 device scalar: advances by _DROP_STRIDE per training forward (graph-replayable)
         self._frozen_key = None
         self._train_key = None
         self._grad_key = None
@@ -342,16 +343,33 @@ class TowerEngine:
         if self._head_gbo is not None:
             self._head_gbo.zero_()
 
-    def _drop(self):
-        """(p, seed, offset) of the next LoRA-dropout mask, or None (eval mode / p = 0).  The seed is taken from torch's
-        generator once (``torch.manual_seed`` reproduces a run); the offset is a host-side call counter: no device sync."""
+    _DROP_STRIDE = 1 << 20
+
+    def _drop_active(self) -> bool:
         training = self.model.training if hasattr(self.model, "training") else self.vm.training
-        if self.p_drop <= 0.0 or not training:
+        return self.p_drop > 0.0 and training
+
+    def _drop_new_step(self, device) -> None:
+        """Start of a training forward: the device-resident part of the mask offset moves on (a stream-ordered add, so a
+        replay of the captured step draws fresh masks), the call index restarts."""
+        if not self._drop_active():
+            return
+        if self._drop_base is None:
+            self._drop_base = torch.zeros(1, dtype=torch.int64, device=device)
+        self._drop_base += self._DROP_STRIDE
+        self._drop_calls = 0
+
+    def _drop(self):
+        """(p, seed, offset, offset_base) of the next LoRA-dropout mask, or None (eval mode / p = 0).  The seed is taken
+        from torch's generator once (``torch.manual_seed`` reproduces a run; the trainer re-seeds per rank); the offset is
+        the call index inside the step (host counter) + a device-resident per-step base: no device sync, and the
+        backward regenerates the forward's masks from the same triple."""
+        if not self._drop_active():
             return None
         if self._drop_seed is None:
             self._drop_seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
         self._drop_calls += 1
-        return (self.p_drop, self._drop_seed, self._drop_calls)
+        return (self.p_drop, self._drop_seed, self._drop_calls, self._drop_base)
 
     # ---- forward ------------------------------------------------------------------------------------------
     def forward(self, pixel_values, _norm=None, save=False):
@@ -361,6 +379,7 @@ class TowerEngine:
         D, H, T, d, dp = self.D, self.H, self.T, self.d, self.dp
         eps, act = c.layer_norm_eps, self.act
         S = {} if save else None
+        self._drop_new_step(pixel_values.device)
         img = pixel_values.float().contiguous()
         mean, std = _norm if _norm is not None else (None, None)
         A = K.patch_im2col(img, c.patch_size, self.patch_ld, mean, std)

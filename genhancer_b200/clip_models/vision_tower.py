@@ -247,6 +247,17 @@ class VisionLanguageModel(nn.Module):
         if missing:
             raise RuntimeError(f"checkpoint {path} lacks vision tensors: {missing[:5]} ...")
         m.load_state_dict(picked, strict=False)
+        # Everything that is not on the vision path (text tower, logit_scale / logit_bias, the real text_projection,
+        # persistent position_ids buffers) rides along untouched, so that the stage-2 export
+        # (lora.save_pretrained = merge_and_unload().save_pretrained of train_SigLIP_stage2_all.py:305-311) writes the
+        # FULL CLIPModel / SiglipModel the evaluation scripts load, not a vision-only file.
+        m._passthrough_state = {k: v for k, v in sd.items() if k not in picked}
+        m._from_checkpoint = path
+        cj = os.path.join(path, "config.json")
+        if os.path.exists(cj):
+            import json
+            with open(cj) as f:
+                m._hf_config = json.load(f)
         return m
 
 

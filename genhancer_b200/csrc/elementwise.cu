@@ -104,7 +104,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 }
 template <bool BWD_ADD>
 __global__ void __launch_bounds__(256) dropout_kernel(const uint2* __restrict__ in, uint2* __restrict__ out, int64_t n4,
-                                                      uint32_t thresh, float inv_keep, uint2 key, uint2 off) {
+                                                      uint32_t thresh, float inv_keep, uint2 key, unsigned long long offset,
+                                                      const unsigned long long* __restrict__ offset_base) {
+  // the mask is keyed by offset + *offset_base: the by-value part is the call index inside a step, the device-resident
+  // part advances once per step -- a CUDA graph bakes by-value arguments in, so without it every replay would draw
+  // the SAME masks
+  const unsigned long long o64 = offset + (offset_base != nullptr ? *offset_base : 0ull);
+  const uint2 off = make_uint2(static_cast<uint32_t>(o64), static_cast<uint32_t>(o64 >> 32));
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), off.x, off.y), key);
@@ -198,7 +204,7 @@ extern "C" int gh_batched_copy(const gh_copy_desc* descs_device, int32_t n_desc,
 }
 
 static int launch_dropout(bool bwd_add, const void* in, void* out, int64_t numel, float p, uint64_t seed, uint64_t offset,
-                          void* stream, const char* who) {
+                          const uint64_t* offset_base, void* stream, const char* who) {
   using namespace gh;
   GH_REQUIRE(in && out, GH_ERR_NULL, "%s: NULL pointer", who);
   GH_REQUIRE(numel >= 0 && numel % 4 == 0, GH_ERR_BAD_SHAPE, "%s: numel=%lld must be a multiple of 4", who, (long long)numel);
@@ -210,25 +216,26 @@ static int launch_dropout(bool bwd_add, const void* in, void* out, int64_t numel
   const double t = static_cast<double>(p) * 4294967296.0;
   const uint32_t thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
   const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-  const uint2 off = make_uint2(static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32));
+  const unsigned long long off = offset;
+  const unsigned long long* base = reinterpret_cast<const unsigned long long*>(offset_base);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (bwd_add)
     dropout_kernel<true><<<ew_grid(n4, 256), 256, 0, s>>>(static_cast<const uint2*>(in), static_cast<uint2*>(out), n4, thresh,
-                                                          1.f / (1.f - p), key, off);
+                                                          1.f / (1.f - p), key, off, base);
   else
     dropout_kernel<false><<<ew_grid(n4, 256), 256, 0, s>>>(static_cast<const uint2*>(in), static_cast<uint2*>(out), n4, thresh,
-                                                           1.f / (1.f - p), key, off);
+                                                           1.f / (1.f - p), key, off, base);
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
 }
 
 extern "C" int gh_dropout_fwd(const void* x_bf16, void* y_bf16, int64_t numel, float p, uint64_t seed, uint64_t offset,
-                              void* stream) {
-  return launch_dropout(false, x_bf16, y_bf16, numel, p, seed, offset, stream, "gh_dropout_fwd");
+                              const uint64_t* offset_base, void* stream) {
+  return launch_dropout(false, x_bf16, y_bf16, numel, p, seed, offset, offset_base, stream, "gh_dropout_fwd");
 }
 extern "C" int gh_dropout_bwd_add(const void* t_bf16, void* dx_bf16, int64_t numel, float p, uint64_t seed, uint64_t offset,
-                                  void* stream) {
-  return launch_dropout(true, t_bf16, dx_bf16, numel, p, seed, offset, stream, "gh_dropout_bwd_add");
+                                  const uint64_t* offset_base, void* stream) {
+  return launch_dropout(true, t_bf16, dx_bf16, numel, p, seed, offset, offset_base, stream, "gh_dropout_bwd_add");
 }
 
 extern "C" int gh_euler_cfg_step(void* x_bf16, const void* pred_bf16, const void* neg_pred_bf16, float dt, float true_gs,

@@ -558,21 +558,25 @@ def euler_cfg_step(x: torch.Tensor, pred: torch.Tensor, neg_pred: torch.Tensor |
     _count()
 
 
-def dropout_fwd(x: torch.Tensor, p: float, seed: int, offset: int) -> torch.Tensor:
-    """bf16 inverted dropout with a counter-based mask (seed, offset): see gh_dropout_fwd."""
+def dropout_fwd(x: torch.Tensor, p: float, seed: int, offset: int, offset_base: torch.Tensor | None = None) -> torch.Tensor:
+    """bf16 inverted dropout with a counter-based mask (seed, offset [+ *offset_base, an int64 device scalar]): see
+    gh_dropout_fwd."""
     _ensure(x)
     assert x.dtype == BF16 and x.is_contiguous()
     y = torch.empty_like(x)
-    check(_lib.lib().gh_dropout_fwd(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), int(offset), _stream()))
+    check(_lib.lib().gh_dropout_fwd(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), int(offset),
+                                    _p(offset_base), _stream()))
     _count()
     return y
 
 
-def dropout_bwd_add(t: torch.Tensor, dx: torch.Tensor, p: float, seed: int, offset: int) -> None:
+def dropout_bwd_add(t: torch.Tensor, dx: torch.Tensor, p: float, seed: int, offset: int,
+                    offset_base: torch.Tensor | None = None) -> None:
     """dx += mask(seed, offset) * t / (1 - p), in place."""
     _ensure(t)
     assert t.dtype == BF16 and dx.dtype == BF16 and t.is_contiguous() and dx.is_contiguous() and t.numel() == dx.numel()
-    check(_lib.lib().gh_dropout_bwd_add(t.data_ptr(), dx.data_ptr(), t.numel(), float(p), int(seed), int(offset), _stream()))
+    check(_lib.lib().gh_dropout_bwd_add(t.data_ptr(), dx.data_ptr(), t.numel(), float(p), int(seed), int(offset),
+                                        _p(offset_base), _stream()))
     _count()
 
 

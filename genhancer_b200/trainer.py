@@ -9,12 +9,24 @@ accelerate / DeepSpeed / diffusers / omegaconf (not in the image) are replaced b
 (torchrun), ``parallel.GradReducer`` for the data-parallel exchange, ``optim.FusedAdamW`` for the update.
 
 Data: the reference's loaders (``image_datasets/``: webdataset tars, CPU JPEG decode) are out of scope (SURVEY.md
-2.1 #13).  ``data_config.img_dir`` / ``video_dir`` == "synthetic" (or a missing directory) selects seeded synthetic
-batches with the reference's batch-dict schema; otherwise ``$GENHANCER_DATA_MODULE`` names a module exposing
-``loader(**data_config)`` that yields such dicts.
+2.1 #13).  ``data_config.img_dir`` / ``video_dir`` == "synthetic" selects seeded synthetic batches with the
+reference's batch-dict schema; a directory selects ``$GENHANCER_DATA_MODULE``, a module exposing
+``loader(**data_config)`` that yields such dicts.  A path that does not exist is an error (as in the reference, which
+crashes), never a silent switch to synthetic data.
+
+Execution: whenever the micro-step has static shapes (every mode but sliding windows over ragged clips) the loop
+replays ``graph.PipelinedTrainStep`` -- forward, backward, the overlapped NCCL exchange AND clip + AdamW as one CUDA
+graph per micro-step, the update of step n on a forked branch under the frozen forward of step n + 1 -- i.e. the path
+``bench.py`` measures.  ``cuda_graph: false`` in the YAML (or GH_TRAINER_GRAPH=0) selects plain eager launches.
 
 Resume: the reference's resume logic is dead code; here ``resume_from_checkpoint: latest`` really
-resumes from the newest ``checkpoint-dit-N.bin`` + ``optimizer-state-N.bin`` in ``output_dir``.
+resumes from the newest ``checkpoint-dit-N.bin`` + ``optimizer-state-N.bin`` in ``output_dir`` (stage 2: plus
+``checkpoint-tower-lora-N.bin``, the un-merged LoRA pairs and trainable biases, which the merged HF export cannot
+give back).
+
+Seeds: ``seed`` (YAML, default 0) fixes the initial weights on every rank; after the parameter broadcast each rank
+re-seeds with ``seed + 1000003 * rank`` so that t, x_0, the AE noise and the LoRA dropout masks differ across ranks
+(the reference never seeds, so its ranks draw independently).
 """
 from __future__ import annotations
 
@@ -90,9 +102,12 @@ def synthetic_loader(mode: str, batch: int, size: int, seed: int, device, frames
 def make_loader(args: Config, mode: str, device, rank: int):
     dc = args.data_config
     src = dc.get("img_dir") if mode == "image" else dc.get("video_dir")
-    if src in (None, "synthetic") or not os.path.isdir(str(src)):
-        if src not in (None, "synthetic"):
-            print(f"[genhancer_b200] data directory {src!r} not found: using synthetic batches")
+    if src is None:
+        raise KeyError(f"data_config.{'img_dir' if mode == 'image' else 'video_dir'} is missing (use 'synthetic' for seeded "
+                       "synthetic batches)")
+    if src != "synthetic" and not os.path.isdir(str(src)):
+        raise FileNotFoundError(f"data directory {src!r} does not exist (use 'synthetic' for seeded synthetic batches)")
+    if src == "synthetic":
         return synthetic_loader(mode, dc.train_batch_size, dc.img_size, int(dc.get("seed", 0)) + 100003 * rank, device,
                                 int(dc.get("max_frames_per_video", 8)))
     modname = os.environ.get("GENHANCER_DATA_MODULE")
@@ -108,7 +123,7 @@ def make_loader(args: Config, mode: str, device, rank: int):
 # ---------------------------------------------------------------------------------------------------------------
 def save_checkpoint(out_dir: str, step: int, dit, clip_vis, adapter, opt, video: bool, save_project_clip: bool = True):
     os.makedirs(out_dir, exist_ok=True)
-    sd = lambda m: {k: v.detach().clone().cpu() for k, v in m.state_dict().items()}  # no deepcopy of the module on the GPU
+    sd = lambda m: {k: v.detach().cpu() for k, v in m.state_dict().items()}  # no deepcopy of the module on the GPU
     torch.save(sd(dit), os.path.join(out_dir, f"checkpoint-dit-{step}.bin"))
     if save_project_clip:
         torch.save(sd(clip_vis.project_clip), os.path.join(out_dir, f"checkpoint-project-clip-{step}.bin"))
@@ -137,12 +152,42 @@ def save_stage2(out_dir: str, step: int, family: str, args, dit, clip_vis, adapt
     from .clip_models import lora
     os.makedirs(out_dir, exist_ok=True)
     lora.save_pretrained(clip_vis.model, os.path.join(out_dir, merged_dir_name(family, args, step)))
+    # Resumable state.  The video scripts write these files themselves; the image scripts write only the merged
+    # directory, from which a run cannot continue (the LoRA pairs are gone) -- the extra flat files are what makes
+    # `resume_from_checkpoint: latest` real in stage 2.
+    sd = lambda m: {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    torch.save(sd(dit), os.path.join(out_dir, f"checkpoint-dit-{step}.bin"))
+    torch.save(sd(clip_vis.project_clip), os.path.join(out_dir, f"checkpoint-project-clip-{step}.bin"))
     if video:
-        sd = lambda m: {k: v.detach().clone().cpu() for k, v in m.state_dict().items()}
-        torch.save(sd(dit), os.path.join(out_dir, f"checkpoint-dit-{step}.bin"))
-        torch.save(sd(clip_vis.project_clip), os.path.join(out_dir, f"checkpoint-project-clip-{step}.bin"))
         torch.save(sd(adapter), os.path.join(out_dir, f"checkpoint-visual-adapter-{step}.bin"))
-        torch.save(opt.state_dict(), os.path.join(out_dir, f"optimizer-state-{step}.bin"))
+    else:
+        torch.save(sd(clip_vis.project_t5), os.path.join(out_dir, f"checkpoint-project-t5-{step}.bin"))
+    torch.save(tower_adapter_state(clip_vis), os.path.join(out_dir, f"checkpoint-tower-lora-{step}.bin"))
+    torch.save(opt.state_dict(), os.path.join(out_dir, f"optimizer-state-{step}.bin"))
+
+
+def tower_adapter_state(clip_vis) -> dict:
+    """What the merged HF export cannot give back: the un-merged LoRA pairs and the trainable (``bias='lora_only'``)
+    biases of the tower -- the resumable half of a stage-2 checkpoint."""
+    model = clip_vis.model
+    sd = {f"lora.{k}": v.detach().cpu() for k, v in model.lora.state_dict().items()} if hasattr(model, "lora") else {}
+    for n, p in model.named_parameters():
+        if p.requires_grad and not n.startswith("lora."):
+            sd[n] = p.detach().cpu()
+    return sd
+
+
+def load_tower_adapter_state(clip_vis, sd: dict) -> None:
+    model = clip_vis.model
+    own = dict(model.named_parameters())
+    with torch.no_grad():
+        for k, v in sd.items():
+            if k not in own:
+                raise KeyError(f"checkpoint-tower-lora: unexpected tensor {k}")
+            own[k].copy_(v)
+    missing = [n for n, p in own.items() if p.requires_grad and n not in sd]
+    if missing:
+        raise KeyError(f"checkpoint-tower-lora lacks trainable tower tensors: {missing[:4]} ...")
 
 
 def latest_step(out_dir: str) -> int | None:
@@ -152,8 +197,16 @@ def latest_step(out_dir: str) -> int | None:
     return max(steps) if steps else None
 
 
-def load_checkpoint(out_dir: str, step: int, dit, clip_vis, adapter, opt, video: bool, strict: bool = True):
+def load_checkpoint(out_dir: str, step: int, dit, clip_vis, adapter, opt, video: bool, strict: bool = True,
+                    tower_lora: bool = False):
+    """``tower_lora``: resuming a stage-2 run -- the un-merged LoRA pairs / trainable biases must be there too."""
     ld = lambda name: torch.load(os.path.join(out_dir, name), map_location="cpu", weights_only=True)
+    if tower_lora:
+        tl = os.path.join(out_dir, f"checkpoint-tower-lora-{step}.bin")
+        if not os.path.exists(tl):
+            raise FileNotFoundError(f"cannot resume stage 2 from step {step}: {tl} is missing (the merged HF directory "
+                                    "alone does not hold the LoRA pairs or the optimizer's view of them)")
+        load_tower_adapter_state(clip_vis, ld(os.path.basename(tl)))
     with torch.no_grad():
         dit.load_state_dict(ld(f"checkpoint-dit-{step}.bin"), strict=strict)
         pc = os.path.join(out_dir, f"checkpoint-project-clip-{step}.bin")
@@ -247,21 +300,26 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
     else:
         trainable += [(f"clip_vis.{n}", p) for n, p in clip_vis.named_parameters()]
         step_fn = Stage1ImageStep(clip_vis, dit, vae, mean, std, scale_factor=float(args.scale_factor))
-    if stage2 and args.get("load_dir") is not None and args.get("load_step") is not None:
-        # stage 2 starts from the stage-1 DiT / projectors / adapter (train_SigLIP_stage2_all.py:146-156)
-        if os.path.exists(os.path.join(str(args.load_dir), f"checkpoint-dit-{args.load_step}.bin")):
-            load_checkpoint(str(args.load_dir), int(args.load_step), dit, clip_vis, adapter, None, video, strict=True)
-            if is_main:
-                print(f"[genhancer_b200] loaded stage-1 weights from {args.load_dir} step {args.load_step}")
-        elif is_main:
-            print(f"[genhancer_b200] stage-1 checkpoint {args.load_dir}/checkpoint-dit-{args.load_step}.bin not found: "
-                  "starting stage 2 from the current (random) initialisation")
+    if stage2 and args.get("load_dir") is not None and args.get("load_step") is not None and str(args.load_dir).lower() != "none":
+        # stage 2 starts from the stage-1 DiT / projectors / adapter (train_SigLIP_stage2_all.py:146-156); a missing file
+        # is an error, as in the reference (torch.load raises) -- never a silent start from random weights
+        f0 = os.path.join(str(args.load_dir), f"checkpoint-dit-{args.load_step}.bin")
+        if not os.path.exists(f0):
+            raise FileNotFoundError(f"stage-1 checkpoint {f0} not found (load_dir / load_step of the YAML); set load_dir: none "
+                                    "to start stage 2 from the current initialisation on purpose")
+        load_checkpoint(str(args.load_dir), int(args.load_step), dit, clip_vis, adapter, None, video, strict=True)
+        if is_main:
+            print(f"[genhancer_b200] loaded stage-1 weights from {args.load_dir} step {args.load_step}")
     groups = optim.flatten(trainable)
     broadcast_parameters(groups)
+    # identical weights everywhere; from here on every rank draws its own t / x_0 / AE noise / dropout masks
+    seed = int(args.get("seed", 0))
+    torch.manual_seed(seed + 1000003 * rank)
     opt = optim.FusedAdamW(groups, lr=float(args.learning_rate), betas=(float(args.adam_beta1), float(args.adam_beta2)),
                            eps=float(args.adam_epsilon), weight_decay=float(args.adam_weight_decay),
                            max_grad_norm=float(args.max_grad_norm), engine_managed=[dit])
     reducer = GradReducer(groups, engine_modules=[dit]) if world > 1 else None
+    gscale = reducer.grad_scale if reducer else 1.0
     ga = int(args.get("gradient_accumulation_steps", 1))
 
     global_step = 0
@@ -269,45 +327,21 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
         last = latest_step(args.output_dir) if args.resume_from_checkpoint == "latest" else \
             int(re.findall(r"\d+", str(args.resume_from_checkpoint))[-1])
         if last is not None:
-            load_checkpoint(args.output_dir, last, dit, clip_vis, adapter, opt, video, strict=True)
+            load_checkpoint(args.output_dir, last, dit, clip_vis, adapter, opt, video, strict=True, tower_lora=stage2)
             global_step = last
             if is_main:
                 print(f"[genhancer_b200] resumed from step {last}")
     max_steps = max_steps_override or int(args.max_train_steps)
     loader = make_loader(args, mode, device, rank)
     ckpt_extra = STAGE2_CKPT_STEPS if stage2 else IMAGE_CKPT_STEPS
-    losses, micro = [], 0
-    st = SimpleNamespace(step=global_step, pending=False, t_last=time.time())
+    losses = []
+    st = SimpleNamespace(step=global_step, micro=0, t_last=time.time(), pipe=None, graph_steps=0, eager_steps=0)
     train_loss = torch.zeros((), device=device)
-    pending_loss = torch.zeros((), device=device)
-
-    def finish_step():
-        """Gradient exchange (wait) + clip + AdamW + bookkeeping of the optimizer step whose backward has been issued.
-        With data parallelism it runs INSIDE the next micro-step, right before the first kernel that reads a trainable
-        parameter (``before_trainable``), so the all-reduce tail hides under the frozen AE / tower forward."""
-        if not st.pending:
-            return
-        st.pending = False
-        if reducer is not None:
-            reducer.wait()
-        opt.step(reducer.grad_scale if reducer else 1.0)
-        opt.zero_grad()
-        st.step += 1
-        if st.step % 10 == 0 or st.step == max_steps:
-            lv = float(pending_loss)        # one host sync per logged step (the reference syncs every micro-step)
-            losses.append(lv)
-            if is_main:
-                dt = time.time() - st.t_last
-                print(f"[genhancer_b200] step {st.step} loss {lv:.4f} grad-norm {float(opt.grad_norm()):.3f} "
-                      f"({dt:.2f} s since last log)", flush=True)
-            st.t_last = time.time()
-        if is_main and args.get("output_dir") and (st.step % int(args.checkpointing_steps) == 0
-                                                   or st.step in ckpt_extra or st.step >= max_steps):
-            if stage2:
-                save_stage2(args.output_dir, st.step, family, args, dit, clip_vis, adapter, opt, video)
-            else:
-                save_checkpoint(args.output_dir, st.step, dit, clip_vis, adapter, opt, video,
-                                save_project_clip=train_project_clip)
+    use_graph = bool(args.get("cuda_graph", True)) and os.environ.get("GH_TRAINER_GRAPH", "1") != "0"
+    # ragged clips give a different number of windows per batch: graph replay only where the shapes repeat, and only
+    # without accumulation (a cycle cannot switch between replay and eager half way)
+    if mode == "sliding_windows_nextpredic" and ga > 1:
+        use_graph = False
 
     def to_input(t):
         """A loader may hand over decoded frames as uint8 [B,H,W,3] (1 byte per value over PCIe): ToTensor then runs
@@ -318,42 +352,99 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
             return K.u8hwc_to_f32chw(t)
         return t.float()
 
-    for batch in loader:
-        if st.step + int(st.pending) >= max_steps:
-            break
-        sync = (micro + 1) % ga == 0
-        if reducer is not None:
-            reducer.enabled = sync
+    if mode == "image":
+        call = lambda img, before_trainable=None: step_fn(img, before_trainable=before_trainable)      # noqa: E731
+    else:
+        call = lambda *fr, before_trainable=None: step_fn(list(fr[:-1]), fr[-1], before_trainable=before_trainable)  # noqa: E731
+
+    def batch_inputs(batch):
         if mode == "image":
-            loss = step_fn(to_input(batch["image"]), before_trainable=finish_step)
-        elif mode == "sliding_windows_nextpredic":
+            return (to_input(batch["image"]),)
+        if mode == "sliding_windows_nextpredic":
             w = build_windows_with_mask(batch["full_frames"].to(device), batch["frame_mask"].to(device),
                                         int(args.get("window_cond", 3)), int(args.get("window_stride", 1)),
                                         args.get("max_windows_per_video", 8))
-            if w is None:
-                continue
-            loss = step_fn(list(w[:3]), w[3], before_trainable=finish_step)
+            return None if w is None else tuple(w[:-2])
+        f = {k: to_input(batch[k]) for k in ("start_frame", "middle_frame", "end_frame")}
+        cond, tgt = {"video": (("start_frame", "end_frame"), "middle_frame"),
+                     "nextpredic": (("start_frame",), "middle_frame"),
+                     "use2frames_nextpredic": (("start_frame", "middle_frame"), "end_frame")}[mode]
+        return tuple(f[k] for k in cond) + (f[tgt],)
+
+    def flush():
+        if st.pipe is not None:
+            st.pipe.flush()
+
+    def after_optimizer_step(loss_value):
+        """Bookkeeping once the backward of optimizer step ``st.step`` has been issued: logging (one host sync per
+        logged step; the reference syncs every micro-step) and checkpoints (which first apply the pending update)."""
+        if st.step % 10 == 0 or st.step >= max_steps:
+            lv = float(loss_value)
+            losses.append(lv)
+            flush()
+            if is_main:
+                dt = time.time() - st.t_last
+                print(f"[genhancer_b200] step {st.step} loss {lv:.4f} grad-norm {float(opt.grad_norm()):.3f} "
+                      f"({dt:.2f} s since last log)", flush=True)
+            st.t_last = time.time()
+        if is_main and args.get("output_dir") and (st.step % int(args.checkpointing_steps) == 0
+                                                   or st.step in ckpt_extra or st.step >= max_steps):
+            flush()
+            if stage2:
+                save_stage2(args.output_dir, st.step, family, args, dit, clip_vis, adapter, opt, video)
+            else:
+                save_checkpoint(args.output_dir, st.step, dit, clip_vis, adapter, opt, video,
+                                save_project_clip=train_project_clip)
+
+    first = True
+    for batch in loader:
+        if st.step >= max_steps:
+            break
+        inputs = batch_inputs(batch)
+        if inputs is None:
+            continue
+        sync = (st.micro + 1) % ga == 0
+        replay = False
+        if use_graph:
+            if st.pipe is None:
+                from .graph import PipelinedTrainStep
+                st.pipe = PipelinedTrainStep(call, inputs, opt, reducer, grad_accum=ga)
+            replay = st.pipe.matches(*inputs)
+        if first:
+            # capture + warm-up consumed RNG draws: both execution modes start the real steps from the same generator
+            # state, so a graph run and an eager run of one config see the same t / x_0 / noise sequence
+            torch.manual_seed(seed + 1000003 * rank + 1)
+            first = False
+        if replay:
+            loss = st.pipe(*inputs)
+            st.graph_steps += 1
         else:
-            f = {k: to_input(batch[k]) for k in ("start_frame", "middle_frame", "end_frame")}
-            cond, tgt = {"video": (("start_frame", "end_frame"), "middle_frame"),
-                         "nextpredic": (("start_frame",), "middle_frame"),
-                         "use2frames_nextpredic": (("start_frame", "middle_frame"), "end_frame")}[mode]
-            loss = step_fn([f[k] for k in cond], f[tgt], before_trainable=finish_step)
-        finish_step()                   # (no-op if the step object already called it)
-        (loss / ga).backward()          # accelerator.backward divides by gradient_accumulation_steps
-        train_loss += loss.detach() / ga
-        micro += 1
+            # eager micro-step (variable shapes, or graphs switched off): the sequential loop of the reference,
+            # train_SigLIP_stage1.py:238-275, with the exchange still overlapped with the backward
+            flush()
+            if reducer is not None:
+                reducer.enabled = sync
+            loss = call(*inputs)
+            (loss / ga).backward()          # accelerator.backward divides by gradient_accumulation_steps
+            if sync:
+                if reducer is not None:
+                    reducer.finish()
+                opt.step(gscale)
+                opt.zero_grad()
+                opt.sync_device_state()
+            st.eager_steps += 1
+        train_loss += loss.detach().reshape(()) / ga
+        st.micro = (st.micro + 1) % ga
         if not sync:
             continue
-        if reducer is not None:
-            reducer.issue_rest()        # projector / adapter groups: issued now, waited for in finish_step()
-        pending_loss.copy_(train_loss)
+        st.step += 1
+        after_optimizer_step(train_loss)
         train_loss.zero_()
-        st.pending = True
-        if reducer is None:
-            finish_step()               # single GPU: nothing to hide
-    finish_step()
+    flush()
     global_step = st.step
     if world > 1:
         dist.barrier()
-    return SimpleNamespace(global_step=global_step, losses=losses, dit=dit, clip_vis=clip_vis, adapter=adapter, opt=opt)
+    if st.pipe is not None and world > 1:
+        st.pipe.reset()        # a graph that holds NCCL kernels must go before the communicator does
+    return SimpleNamespace(global_step=global_step, losses=losses, dit=dit, clip_vis=clip_vis, adapter=adapter, opt=opt,
+                           graph_steps=st.graph_steps, eager_steps=st.eager_steps)

@@ -248,11 +248,14 @@ int gh_batched_copy(const gh_copy_desc* descs_device, int32_t n_desc, int32_t bl
 /* LoRA input dropout (peft lora.Linear: lora_B(lora_A(dropout(x))), lora_dropout 0.1 in the stage-2 YAMLs,
  * train_SigLIP_stage2_all.py:139).  y = keep ? x / (1-p) : 0 on bf16; the keep mask is a pure function of
  * (seed, offset, element index) -- Philox-4x32-10 -- so the backward regenerates it:
- * gh_dropout_bwd_add: dx += keep ? t / (1-p) : 0.  numel % 4 == 0, contiguous. */
+ * gh_dropout_bwd_add: dx += keep ? t / (1-p) : 0.  numel % 4 == 0, contiguous.
+ * offset_base (device uint64, may be NULL) is added to `offset` on the device: the caller advances it once per step
+ * (a stream-ordered add), so a CUDA-graph replay -- which bakes the by-value `offset` in -- still draws fresh masks,
+ * and the backward of the same step regenerates the forward's. */
 int gh_dropout_fwd(const void* x_bf16, void* y_bf16, int64_t numel, float p, uint64_t seed, uint64_t offset,
-                   void* stream);
+                   const uint64_t* offset_base, void* stream);
 int gh_dropout_bwd_add(const void* t_bf16, void* dx_bf16, int64_t numel, float p, uint64_t seed, uint64_t offset,
-                       void* stream);
+                       const uint64_t* offset_base, void* stream);
 
 /* --------------------------------------------------------------------------
  * Flash attention (tcgen05 S/O accumulators in TMEM, TMA-staged tiles, online softmax).

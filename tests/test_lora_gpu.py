@@ -147,6 +147,15 @@ def test_lora_dropout_mask_is_regenerated_and_group_matches_torch():
     acc = torch.zeros_like(ones)
     K.dropout_bwd_add(ones, acc, p, seed, off)
     assert torch.equal(acc, m1)                                            # backward regenerates the same mask
+    # the device-resident part of the offset (what a CUDA-graph replay advances): offset + *base
+    base = torch.tensor([5], dtype=torch.int64, device="cuda")
+    assert torch.equal(K.dropout_fwd(ones, p, seed, off - 5, base), m1)
+    base += 1 << 20
+    m2 = K.dropout_fwd(ones, p, seed, off - 5, base)
+    assert not torch.equal(m2, m1)
+    acc.zero_()
+    K.dropout_bwd_add(ones, acc, p, seed, off - 5, base)
+    assert torch.equal(acc, m2)
 
     lin = torch.nn.Linear(256, 384).cuda()
     lin.bias.requires_grad_(True)

@@ -90,3 +90,55 @@ def test_state_dict_keys_match_the_reference_checkpoint_contract():
     tk = O.tower_key_shapes(O.openai_vit_l14(336))
     mine = {k: tuple(v.shape) for k, v in tower.state_dict().items() if not k.startswith("text_projection")}
     assert mine == {k: tuple(v) for k, v in tk.items()}
+
+
+def test_stage2_export_round_trips_a_full_hf_checkpoint(tmp_path):
+    """the merged stage-2 export must be the FULL CLIPModel (text tower, logit_scale, the real
+    text_projection, config.json with text_config), as ``merge_and_unload().save_pretrained`` writes it
+    (train_SigLIP_stage2_all.py:305-311) -- evaluation loads the directory with CLIPModel.from_pretrained."""
+    import json
+    import pytest
+    from transformers import CLIPConfig, CLIPModel
+    from genhancer_b200.clip_models import lora, vision_tower as vt
+    vis = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=1, image_size=28,
+               patch_size=14, hidden_act="quick_gelu", projection_dim=32)
+    txt = dict(hidden_size=48, intermediate_size=96, num_hidden_layers=1, num_attention_heads=2, projection_dim=32,
+               vocab_size=50, max_position_embeddings=8)
+    torch.manual_seed(0)
+    hf = CLIPModel(CLIPConfig(text_config=txt, vision_config=vis, projection_dim=32)).eval()
+    src = tmp_path / "hf_src"
+    src.mkdir()
+    hf_sd = {k: v.clone() for k, v in hf.state_dict().items()}
+    torch.save(hf_sd, src / "pytorch_model.bin")
+    (src / "config.json").write_text(json.dumps(hf.config.to_dict(), default=str))
+    cfg = vt.TowerConfig("clip", 64, 2, 1, 128, 28, 14, 32, 1e-5, "quick_gelu")
+    m = vt.VisionLanguageModel.from_pretrained(str(src), cfg)
+    assert any(k.startswith("text_model.") for k in m._passthrough_state) and "logit_scale" in m._passthrough_state
+    assert tuple(m._passthrough_state["text_projection.weight"].shape) == (32, 48)
+    m = lora.get_peft_model(m, lora.LoraConfig(r=16, lora_alpha=16, target_modules="all-linear", bias="lora_only"))
+    with torch.no_grad():
+        for pair in m.lora.values():
+            pair.B.normal_(0, 0.05)
+    out = tmp_path / "merged"
+    lora.save_pretrained(m, str(out))
+    saved = torch.load(out / "pytorch_model.bin", weights_only=True)
+    assert set(saved) == set(hf_sd), set(saved) ^ set(hf_sd)                      # no key lost, none invented
+    for k, v in hf_sd.items():
+        if not (k.startswith("vision_model.") or k.startswith("visual_projection")):
+            assert torch.equal(saved[k], v), k                                   # text side: untouched
+    k = "vision_model.encoder.layers.1.mlp.fc1.weight"
+    pair = m.lora["vision_model/encoder/layers/1/mlp/fc1"]
+    assert torch.allclose(saved[k], hf_sd[k] + pair.B @ pair.A, atol=1e-6) and not torch.equal(saved[k], hf_sd[k])
+    assert json.loads((out / "config.json").read_text())["text_config"]["hidden_size"] == 48
+    # what evaluation does: the directory loads as a complete CLIPModel, text features included
+    re = CLIPModel.from_pretrained(str(out)).eval()
+    ids = torch.tensor([[1, 5, 7, 2]])
+    def text_features(model):   # (a tensor in transformers 4.x, an output object in 5.x)
+        o = model.get_text_features(input_ids=ids)
+        return o if isinstance(o, torch.Tensor) else o.pooler_output
+    with torch.no_grad():
+        assert torch.equal(text_features(re), text_features(hf))
+    # a checkpoint-loaded tower that lost its passthrough tensors must refuse to export a vision-only file
+    m._passthrough_state = None
+    with pytest.raises(RuntimeError, match="text tower"):
+        lora.save_pretrained(m, str(tmp_path / "bad"))

@@ -76,6 +76,40 @@ def test_image_stage1_trains_checkpoints_and_resumes(tmp_path):
     assert res2.opt.step_count == 6
 
 
+def test_graph_trainer_and_eager_trainer_agree(tmp_path):
+    """The entry points run the measured path (graph.PipelinedTrainStep: update of step n captured under the frozen
+    forward of step n + 1); with ``cuda_graph: false`` they run the sequential eager loop.  Same config, same seed:
+    same losses and the same weights after 4 optimizer steps (up to fp32-atomic ordering)."""
+    import warnings
+    from genhancer_b200 import trainer
+    warnings.simplefilter("ignore")
+    res = {}
+    for tag, flag in (("graph", "true"), ("eager", "false")):
+        out = str(tmp_path / f"out_{tag}")
+        cfg = tmp_path / f"cfg_{tag}.yaml"
+        cfg.write_text(CFG.format(dirkey="img_dir", out=out, steps=4, ga=1).replace("checkpointing_steps: 2", "checkpointing_steps: 100")
+                       + f"cuda_graph: {flag}\n")
+        r = trainer.main("OpenAICLIP", "image", "stage1", argv=["--config", str(cfg)])
+        res[tag] = dict(losses=r.losses, w={k: v.detach().float().cpu() for k, v in r.dit.state_dict().items()
+                                           if k in ("final_layer.linear.weight", "single_blocks.2.linear1.weight", "img_in.bias")},
+                        p5=r.clip_vis.project_t5[3].weight.detach().float().cpu(),
+                        m=r.opt.groups[0].exp_avg[:8_000_000].float().cpu(), graph_steps=r.graph_steps,
+                        eager_steps=r.eager_steps, step_count=r.opt.step_count)
+        del r
+        torch.cuda.empty_cache()
+    assert res["graph"]["graph_steps"] == 4 and res["graph"]["eager_steps"] == 0
+    assert res["eager"]["graph_steps"] == 0 and res["eager"]["eager_steps"] == 4
+    assert res["graph"]["step_count"] == res["eager"]["step_count"] == 4
+    for a, b in zip(res["graph"]["losses"], res["eager"]["losses"]):
+        assert abs(a - b) <= 2e-3 * abs(b), (res["graph"]["losses"], res["eager"]["losses"])
+    from conftest import cosine
+    for k in res["graph"]["w"]:
+        assert cosine(res["graph"]["w"][k], res["eager"]["w"][k]) >= 0.99999, k
+    assert cosine(res["graph"]["p5"], res["eager"]["p5"]) >= 0.99999
+    # Adam's first moments carry the gradients of all 4 steps: a skipped, doubled or stale update would show here
+    assert cosine(res["graph"]["m"], res["eager"]["m"]) >= 0.999
+
+
 @pytest.mark.parametrize("mode", ["use2frames_nextpredic", "sliding_windows_nextpredic"])
 def test_video_stage1_modes_train(tmp_path, mode):
     import warnings
