@@ -119,7 +119,8 @@ SIGNATURES: dict[str, list] = {
     "gh_u8hwc_to_f32chw": [_vp, _vp, _i32, _i32, _i32, _vp],
     "gh_softmax_rows": [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp],
     "gh_ae_sample_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp],
-    "gh_sumsq_accum": [_vp, _i32, _i64, _vp, _vp],
+    "gh_sumsq_workspace_bytes": [],
+    "gh_sumsq_accum": [_vp, _i32, _i64, _vp, _vp, _vp],
     "gh_adamw_step": [_vp, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _f32, _f32, _vp, _vp],
 }
 
@@ -132,7 +133,7 @@ def _declare(lib):
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = (C.c_char_p if name == "gh_last_error" else C.c_int64 if name.endswith("_ws_bytes") else C.c_int)
+        fn.restype = (C.c_char_p if name == "gh_last_error" else C.c_int64 if name.endswith(("_ws_bytes", "_workspace_bytes")) else C.c_int)
 
 
 def lib():

@@ -7,6 +7,7 @@
 // Replaces nn.Conv2d at autoencoder.py:62-67 (ResnetBlock 3x3), :89 (Downsample), :157 (conv_out).
 #include <cstdlib>
 
+#include "conv3x3_res.cuh"
 #include "internal.h"
 #include "umma_gemm.cuh"
 
@@ -24,6 +25,8 @@ static int conv_set_attr() {
 }
 
 int conv_init() {
+  GH_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Conv3x3ResCfg::SMEM_BYTES));
   if (int e = conv_set_attr<256>()) return e;
   if (int e = conv_set_attr<128>()) return e;
   if (int e = conv_set_attr<64>()) return e;
@@ -60,6 +63,59 @@ static int conv_launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const 
   return GH_OK;
 }
 
+// 3x3 / stride 1 / pad 1, Cin = Cout = 128: weights resident in shared memory, one input box per column shift
+// (conv3x3_res.cuh).  Returns GH_OK after launching, or 1 when the shape is not this kernel's.
+static int conv3x3_res_try(const gh_conv_args* a, cudaStream_t s) {
+  using Cfg = Conv3x3ResCfg;
+  static const int enabled = [] { const char* e = getenv("GH_CONV_RES"); return e ? atoi(e) : 1; }();
+  if (!enabled || a->Cin != 128 || a->Cout != 128 || a->KH != 3 || a->KW != 3 || a->stride != 1 || a->pad != 1 ||
+      a->Ho != a->H || a->Wo != a->W || a->act != 0 || a->y_dtype != GH_BF16 || (a->residual && a->res_dtype != GH_BF16))
+    return 1;
+  GemmParams p{};
+  p.cv.B = a->B; p.cv.Ho = a->Ho; p.cv.Wo = a->Wo; p.cv.TW = Cfg::TW; p.cv.TH = Cfg::TH;
+  p.cv.tiles_w = (a->Wo + Cfg::TW - 1) / Cfg::TW;
+  p.cv.tiles_h = (a->Ho + Cfg::TH - 1) / Cfg::TH;
+  p.num_m_blocks = a->B * p.cv.tiles_w * p.cv.tiles_h;
+  if (p.num_m_blocks < 2 * num_sms()) return 1;           // too few patches to amortise the 144 KB weight load per CTA
+  p.M = a->B * a->Ho * a->Wo; p.N = 128; p.K = 9 * 128;
+  p.ep.d = a->y; p.ep.ldd = a->Cout; p.ep.d_f32 = 0;
+  p.ep.alpha = 1.f;
+  p.ep.bias = a->bias; p.ep.bias_f32 = (a->bias_dtype == GH_F32);
+  p.ep.rows_per_batch = 1;
+  p.ep.residual = a->residual; p.ep.ld_res = a->Cout; p.ep.res_f32 = 0;
+  p.ep.vec8 = 1;
+  finalize_epilogue(p.ep);
+  CUtensorMap tx, tw;
+  {
+    const uint64_t dims[4] = {128, static_cast<uint64_t>(a->W), static_cast<uint64_t>(a->H), static_cast<uint64_t>(a->B)};
+    const uint64_t strides[3] = {128 * 2, static_cast<uint64_t>(a->W) * 128 * 2, static_cast<uint64_t>(a->H) * a->W * 128 * 2};
+    const uint32_t box[4] = {64, Cfg::TW, Cfg::TH + 2, 1};
+    if (int e = make_tmap_bf16(&tx, a->x, 4, dims, strides, box, nullptr)) return e;
+  }
+  {
+    const uint64_t dims[2] = {9 * 128, 128};
+    const uint64_t strides[1] = {9 * 128 * 2};
+    const uint32_t box[2] = {64, 64};
+    if (int e = make_tmap_bf16(&tw, a->w, 2, dims, strides, box, nullptr)) return e;
+  }
+  const int tiles = (p.num_m_blocks + 1) / 2;
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  GH_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_res_kernel, tx, tw, p));
+  return GH_OK;
+}
+
 // output patch (TW x TH <= 128 pixels) that wastes the fewest MMA rows
 static void pick_patch(int Wo, int Ho, int* tw, int* th) {
   double best = -1;
@@ -88,6 +144,10 @@ extern "C" int gh_conv2d_nhwc(const gh_conv_args* a, void* stream) {
   GH_REQUIRE(aligned16(a->x) && aligned16(a->w) && aligned16(a->y), GH_ERR_ALIGN, "gh_conv2d_nhwc: 16B alignment");
   GH_REQUIRE(a->act >= 0 && a->act <= 4, GH_ERR_UNSUPPORTED, "gh_conv2d_nhwc: unknown act");
 
+  if (aligned16(a->bias) && aligned16(a->residual)) {
+    const int r = conv3x3_res_try(a, static_cast<cudaStream_t>(stream));
+    if (r <= 0) return r;            // launched (GH_OK) or failed; 1 = not this kernel's shape
+  }
   int TW = 1, TH = 1;
   pick_patch(a->Wo, a->Ho, &TW, &TH);
   const int K = a->KH * a->KW * a->Cin;

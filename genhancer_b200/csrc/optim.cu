@@ -1,6 +1,6 @@
 // genhancer_b200 -- HBM-bound optimizer kernels over FLAT parameter / gradient buffers:
 //   gh_sumsq_accum : acc += sum(g^2)                (global grad-norm, accelerator.clip_grad_norm_,
-//                                                     train_SigLIP_stage1.py:271-272)
+//                                                     train_SigLIP_stage1.py:271-272); bit-reproducible
 //   gh_adamw_step  : clip-by-global-norm + AdamW    (torch.optim.AdamW(lr, betas, eps, weight_decay),
 //                                                     train_SigLIP_stage1.py:147-153,273)
 // Parameters, gradients and both moment buffers share one dtype (the reference keeps bf16 Adam states for the
@@ -46,8 +46,15 @@ struct Vec<float> {  // 4 x fp32 = 16 B
   static __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
 };
 
+// Deterministic: every block leaves its partial sum in ws[blockIdx.x]; the block that draws the last ticket adds the
+// partials up in a FIXED order (independent of which block that is) and adds the total to *acc.  The same gradients
+// therefore give bit-identical norms -- and, through the clip coefficient, bit-identical AdamW updates -- on every
+// rank of a data-parallel job (an atomicAdd per block rounded differently from rank to rank, and the replicas drifted
+// apart by an ulp per step).  ws = [gridDim.x partials | 1 ticket counter], zeroed once by the caller; the last block
+// hands the counter back zeroed.
 template <typename T>
-__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ g, int64_t n, float* __restrict__ acc) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ g, int64_t n, float* __restrict__ acc,
+                                                    float* __restrict__ ws) {
   constexpr int V = Vec<T>::N;
   float s = 0.f;
   const int64_t nv = n / V;
@@ -64,12 +71,33 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ g, int
   }
   s = warp_sum(s);
   __shared__ float part[8];
+  __shared__ int last;
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x < 32) {
     float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(acc, v);
+    if (threadIdx.x == 0) {
+      ws[blockIdx.x] = v;
+      __threadfence();
+      int* ticket = reinterpret_cast<int*>(ws + gridDim.x);
+      last = atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1;
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x) t += __ldcg(ws + i);
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += part[i];
+    *acc += tot;
+    *reinterpret_cast<int*>(ws + gridDim.x) = 0;
   }
 }
 
@@ -140,15 +168,17 @@ static int grid_for(int64_t n_vec) {
 
 using namespace gh;
 
-extern "C" int gh_sumsq_accum(const void* g, int32_t dtype, int64_t numel, float* acc, void* stream) {
-  GH_REQUIRE(g && acc, GH_ERR_NULL, "gh_sumsq_accum: NULL pointer");
+extern "C" int64_t gh_sumsq_workspace_bytes() { return (8L * num_sms() + 1) * static_cast<int64_t>(sizeof(float)); }
+
+extern "C" int gh_sumsq_accum(const void* g, int32_t dtype, int64_t numel, float* acc, float* ws, void* stream) {
+  GH_REQUIRE(g && acc && ws, GH_ERR_NULL, "gh_sumsq_accum: NULL pointer");
   GH_REQUIRE(numel > 0, GH_ERR_BAD_SHAPE, "gh_sumsq_accum: numel must be positive");
   GH_REQUIRE(aligned16(g), GH_ERR_ALIGN, "gh_sumsq_accum: buffer must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == GH_BF16)
-    sumsq_kernel<__nv_bfloat16><<<grid_for(numel / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(g), numel, acc);
+    sumsq_kernel<__nv_bfloat16><<<grid_for(numel / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(g), numel, acc, ws);
   else if (dtype == GH_F32)
-    sumsq_kernel<float><<<grid_for(numel / 4), 256, 0, s>>>(static_cast<const float*>(g), numel, acc);
+    sumsq_kernel<float><<<grid_for(numel / 4), 256, 0, s>>>(static_cast<const float*>(g), numel, acc, ws);
   else
     return set_error(GH_ERR_UNSUPPORTED, "gh_sumsq_accum: dtype %d", dtype);
   GH_CHECK_CUDA(cudaGetLastError());

@@ -525,11 +525,25 @@ def flash_attn_bwd(q, k, v, lse, scale, o1, do1, dq, dk, dv, o0=None, do0=None, 
     _count(3)
 
 
-def sumsq_accum(g: torch.Tensor, acc: torch.Tensor) -> None:
-    """acc[0] (fp32) += sum(g^2) over a flat contiguous bf16 / fp32 buffer."""
+_SUMSQ_WS: dict = {}
+
+
+def sumsq_workspace(device) -> torch.Tensor:
+    """The zeroed scratch gh_sumsq_accum reduces through (block partials + a ticket counter), one per device; calls
+    that share it must be ordered on one stream (the optimizer's)."""
+    ws = _SUMSQ_WS.get(device)
+    if ws is None:
+        ws = _SUMSQ_WS[device] = torch.zeros(_lib.lib().gh_sumsq_workspace_bytes() // 4, dtype=F32, device=device)
+    return ws
+
+
+def sumsq_accum(g: torch.Tensor, acc: torch.Tensor, ws: torch.Tensor | None = None) -> None:
+    """acc[0] (fp32) += sum(g^2) over a flat contiguous bf16 / fp32 buffer; bit-reproducible (fixed summation order)."""
     _ensure(g)
     assert g.is_contiguous() and acc.dtype == F32
-    check(_lib.lib().gh_sumsq_accum(g.data_ptr(), _dt(g), g.numel(), acc.data_ptr(), _stream()))
+    if ws is None:
+        ws = sumsq_workspace(g.device)
+    check(_lib.lib().gh_sumsq_accum(g.data_ptr(), _dt(g), g.numel(), acc.data_ptr(), ws.data_ptr(), _stream()))
     _count()
 
 

@@ -93,10 +93,18 @@ class FusedAdamW:
             g.exp_avg = torch.zeros_like(g.flat_p)
             g.exp_avg_sq = torch.zeros_like(g.flat_p)
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=groups[0].flat_p.device)
+        self._sumsq_ws = None       # scratch of the deterministic norm reduction (allocated on the first step, on the device)
         # device-resident [step count, update pending]: what a captured update reads (see step_captured)
         self.dev_state = torch.zeros(2, dtype=torch.int32, device=groups[0].flat_p.device)
         self._managed_dtypes = {p.dtype for m in self.engine_managed for p in m.parameters()}
         self.zero_grad()
+
+    def _ws(self) -> torch.Tensor:
+        if self._sumsq_ws is None:   # private to this optimizer: its calls are ordered on whichever stream runs the update
+            from . import _lib
+            self._sumsq_ws = torch.zeros(_lib.lib().gh_sumsq_workspace_bytes() // 4, dtype=torch.float32,
+                                         device=self.gnorm_sq.device)
+        return self._sumsq_ws
 
     def zero_grad(self) -> None:
         for m in self.engine_managed:
@@ -114,7 +122,7 @@ class FusedAdamW:
         self.step_count += 1
         self.gnorm_sq.zero_()
         for g in self.groups:
-            K.sumsq_accum(g.flat_g, self.gnorm_sq)
+            K.sumsq_accum(g.flat_g, self.gnorm_sq, self._ws())
         for g in self.groups:
             K.adamw_step(g.flat_p, g.flat_g, g.exp_avg, g.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
                          self.weight_decay, self.step_count, self.gnorm_sq, self.max_grad_norm, grad_scale)
@@ -128,7 +136,7 @@ class FusedAdamW:
         self.dev_state[0:1] += self.dev_state[1:2]
         self.gnorm_sq.zero_()
         for g in self.groups:
-            K.sumsq_accum(g.flat_g, self.gnorm_sq)
+            K.sumsq_accum(g.flat_g, self.gnorm_sq, self._ws())
         for g in self.groups:
             K.adamw_step(g.flat_p, g.flat_g, g.exp_avg, g.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
                          self.weight_decay, 0, self.gnorm_sq, self.max_grad_norm, grad_scale, dev_state=self.dev_state)

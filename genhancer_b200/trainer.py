@@ -144,7 +144,8 @@ def merged_dir_name(family: str, args, step: int) -> str:
     return f"clip-vit-large-patch14-336-{step}" if size == 336 else f"clip-vit-large-patch14-{step}"  # OpenAI video scripts
 
 
-def save_stage2(out_dir: str, step: int, family: str, args, dit, clip_vis, adapter, opt, video: bool):
+def save_stage2(out_dir: str, step: int, family: str, args, dit, clip_vis, adapter, opt, video: bool,
+                dit_trains: bool = True):
     """Stage-2 outputs: the tower with LoRA merged as an HF directory (pytorch_model.bin, safe_serialization=False;
     train_SigLIP_stage2_all.py:305-311); the video scripts also write the DiT / project_clip / visual_adapter /
     optimizer files (train_OpenAICLIP_use2frames_nextpredic_stage2_all.py:469-494).  No deepcopy of the model on the
@@ -156,12 +157,13 @@ def save_stage2(out_dir: str, step: int, family: str, args, dit, clip_vis, adapt
     # directory, from which a run cannot continue (the LoRA pairs are gone) -- the extra flat files are what makes
     # `resume_from_checkpoint: latest` real in stage 2.
     sd = lambda m: {k: v.detach().cpu() for k, v in m.state_dict().items()}
-    torch.save(sd(dit), os.path.join(out_dir, f"checkpoint-dit-{step}.bin"))
-    torch.save(sd(clip_vis.project_clip), os.path.join(out_dir, f"checkpoint-project-clip-{step}.bin"))
-    if video:
-        torch.save(sd(adapter), os.path.join(out_dir, f"checkpoint-visual-adapter-{step}.bin"))
-    else:
-        torch.save(sd(clip_vis.project_t5), os.path.join(out_dir, f"checkpoint-project-t5-{step}.bin"))
+    if dit_trains or video:          # (stage2_only: the DiT / projectors are the frozen stage-1 files, nothing to re-save)
+        torch.save(sd(dit), os.path.join(out_dir, f"checkpoint-dit-{step}.bin"))
+        torch.save(sd(clip_vis.project_clip), os.path.join(out_dir, f"checkpoint-project-clip-{step}.bin"))
+        if video:
+            torch.save(sd(adapter), os.path.join(out_dir, f"checkpoint-visual-adapter-{step}.bin"))
+        else:
+            torch.save(sd(clip_vis.project_t5), os.path.join(out_dir, f"checkpoint-project-t5-{step}.bin"))
     torch.save(tower_adapter_state(clip_vis), os.path.join(out_dir, f"checkpoint-tower-lora-{step}.bin"))
     torch.save(opt.state_dict(), os.path.join(out_dir, f"optimizer-state-{step}.bin"))
 
@@ -193,7 +195,8 @@ def load_tower_adapter_state(clip_vis, sd: dict) -> None:
 def latest_step(out_dir: str) -> int | None:
     if not os.path.isdir(out_dir):
         return None
-    steps = [int(m.group(1)) for f in os.listdir(out_dir) if (m := re.fullmatch(r"checkpoint-dit-(\d+)\.bin", f))]
+    steps = [int(m.group(1)) for f in os.listdir(out_dir)
+             if (m := re.fullmatch(r"checkpoint-(?:dit|tower-lora)-(\d+)\.bin", f))]
     return max(steps) if steps else None
 
 
@@ -207,15 +210,17 @@ def load_checkpoint(out_dir: str, step: int, dit, clip_vis, adapter, opt, video:
             raise FileNotFoundError(f"cannot resume stage 2 from step {step}: {tl} is missing (the merged HF directory "
                                     "alone does not hold the LoRA pairs or the optimizer's view of them)")
         load_tower_adapter_state(clip_vis, ld(os.path.basename(tl)))
-    with torch.no_grad():
-        dit.load_state_dict(ld(f"checkpoint-dit-{step}.bin"), strict=strict)
-        pc = os.path.join(out_dir, f"checkpoint-project-clip-{step}.bin")
-        if os.path.exists(pc):
-            clip_vis.project_clip.load_state_dict(ld(os.path.basename(pc)), strict=strict)
-        if video:
-            adapter.load_state_dict(ld(f"checkpoint-visual-adapter-{step}.bin"), strict=strict)
-        else:
-            clip_vis.project_t5.load_state_dict(ld(f"checkpoint-project-t5-{step}.bin"), strict=strict)
+    # (stage2_only writes no DiT / projector files: they stay the stage-1 weights loaded through load_dir / load_step)
+    if not tower_lora or os.path.exists(os.path.join(out_dir, f"checkpoint-dit-{step}.bin")):
+        with torch.no_grad():
+            dit.load_state_dict(ld(f"checkpoint-dit-{step}.bin"), strict=strict)
+            pc = os.path.join(out_dir, f"checkpoint-project-clip-{step}.bin")
+            if os.path.exists(pc):
+                clip_vis.project_clip.load_state_dict(ld(os.path.basename(pc)), strict=strict)
+            if video:
+                adapter.load_state_dict(ld(f"checkpoint-visual-adapter-{step}.bin"), strict=strict)
+            else:
+                clip_vis.project_t5.load_state_dict(ld(f"checkpoint-project-t5-{step}.bin"), strict=strict)
     op = os.path.join(out_dir, f"optimizer-state-{step}.bin")
     if opt is not None and os.path.exists(op):
         opt.load_state_dict(torch.load(op, map_location="cpu", weights_only=True))
@@ -391,7 +396,8 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
                                                    or st.step in ckpt_extra or st.step >= max_steps):
             flush()
             if stage2:
-                save_stage2(args.output_dir, st.step, family, args, dit, clip_vis, adapter, opt, video)
+                save_stage2(args.output_dir, st.step, family, args, dit, clip_vis, adapter, opt, video,
+                            dit_trains=stage != "stage2_only")
             else:
                 save_checkpoint(args.output_dir, st.step, dit, clip_vis, adapter, opt, video,
                                 save_project_clip=train_project_clip)

@@ -349,7 +349,9 @@ int gh_ae_sample_patchify(const float* moments_nhwc, const float* noise_nchw, fl
 /* --------------------------------------------------------------------------
  * Optimizer step over FLAT buffers (one launch per dtype group instead of one per tensor).
  * gh_sumsq_accum: *acc += sum(g^2) -- the global gradient norm of accelerator.clip_grad_norm_
- *   (train_SigLIP_stage1.py:271-272); acc is ONE fp32 the caller zeroes.
+ *   (train_SigLIP_stage1.py:271-272); acc is ONE fp32 the caller zeroes.  Bit-reproducible: block partials go through
+ *   `ws` (gh_sumsq_workspace_bytes() bytes, zeroed ONCE by the caller, reusable by calls on the same stream) and are
+ *   added up in a fixed order, so every data-parallel rank derives the same clip coefficient from the same gradients.
  * gh_adamw_step: torch.optim.AdamW semantics (train_SigLIP_stage1.py:147-153,273) with the clip
  *   coefficient min(1, max_norm / (grad_scale * sqrt(*gnorm_sq) + 1e-6)) applied on the fly
  *   (gnorm_sq NULL or max_norm <= 0: no clipping).  param/grad/exp_avg/exp_avg_sq share `dtype`
@@ -360,7 +362,8 @@ int gh_ae_sample_patchify(const float* moments_nhwc, const float* noise_nchw, fl
  *   That makes the update capturable into the CUDA graph of the training step (graph.PipelinedTrainStep:
  *   the update of step n runs on a side branch under step n+1's frozen AE / tower forward).
  * -------------------------------------------------------------------------- */
-int gh_sumsq_accum(const void* g, int32_t dtype, int64_t numel, float* acc, void* stream);
+int64_t gh_sumsq_workspace_bytes(void);
+int gh_sumsq_accum(const void* g, int32_t dtype, int64_t numel, float* acc, float* ws, void* stream);
 int gh_adamw_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int32_t dtype, int64_t numel,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                   const float* gnorm_sq, float max_norm, float grad_scale, const int32_t* dev_state, void* stream);

@@ -81,3 +81,28 @@ def test_u8_to_tensor_is_bit_identical_to_torch():
         assert torch.equal(y.cpu(), x.cpu().permute(0, 3, 1, 2).to(torch.float32).div(255))
     with pytest.raises(_lib.GhError):
         K.u8hwc_to_f32chw(torch.zeros(1, 3, 8, 8, device="cuda", dtype=torch.uint8))       # CHW is not the input layout
+
+
+@pytest.mark.parametrize("B,H,W,res", [(4, 90, 100, False), (4, 90, 100, True), (4, 112, 112, True), (2, 336, 336, True)])
+def test_conv3x3_resident_weight_kernel_matches_torch(B, H, W, res):
+    """conv3x3_res_kernel (Cin = Cout = 128, 3x3 / s1 / p1: weights resident in smem, one input box per column shift,
+    taps as 1024-byte offsets into it) against torch conv2d, incl. ragged right / bottom patches and zero padding."""
+    import torch.nn.functional as F
+    from genhancer_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H)
+    C = 128
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    w4 = (torch.randn(C, C, 3, 3, device="cuda", generator=g) * 0.05)
+    wk = w4.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous().to(torch.bfloat16)     # k = (kh * 3 + kw) * Cin + ci
+    bias = torch.randn(C, device="cuda", generator=g)
+    r = torch.randn(B, H, W, C, device="cuda", generator=g).to(torch.bfloat16) if res else None
+    y = K.conv2d_nhwc(x, wk, 3, 3, 1, 1, bias=bias, residual=r)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wk.float().view(C, 3, 3, C).permute(0, 3, 1, 2), bias, padding=1)
+    ref = ref.permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r.float()
+    err = (y.float() - ref).norm() / ref.norm()
+    assert err < 6e-3, err
+    # borders (zero padding through TMA out-of-bounds fill) and the ragged last patches on their own
+    for a, b in zip((y[:, 0], y[:, -1], y[:, :, 0], y[:, :, -1]), (ref[:, 0], ref[:, -1], ref[:, :, 0], ref[:, :, -1])):
+        assert (a.float() - b).norm() / b.norm() < 6e-3

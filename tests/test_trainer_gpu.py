@@ -3,6 +3,7 @@ size (1.31 B-parameter DiT, ViT-L/14-224, full AE) on synthetic data, writes the
 resumes from them, and the loss goes down."""
 import math
 import os
+import shutil
 
 import pytest
 import torch
@@ -74,6 +75,7 @@ def test_image_stage1_trains_checkpoints_and_resumes(tmp_path):
     res2 = trainer.main("OpenAICLIP", "image", "stage1", argv=["--config", str(cfg)])
     assert res2.global_step == 6 and "checkpoint-dit-6.bin" in os.listdir(out)
     assert res2.opt.step_count == 6
+    shutil.rmtree(out, ignore_errors=True)      # (8 GB per checkpoint: the box's scratch disk is small)
 
 
 def test_graph_trainer_and_eager_trainer_agree(tmp_path):
@@ -108,6 +110,7 @@ def test_graph_trainer_and_eager_trainer_agree(tmp_path):
     assert cosine(res["graph"]["p5"], res["eager"]["p5"]) >= 0.99999
     # Adam's first moments carry the gradients of all 4 steps: a skipped, doubled or stale update would show here
     assert cosine(res["graph"]["m"], res["eager"]["m"]) >= 0.999
+    shutil.rmtree(str(tmp_path), ignore_errors=True)
 
 
 @pytest.mark.parametrize("mode", ["use2frames_nextpredic", "sliding_windows_nextpredic"])
@@ -121,6 +124,7 @@ def test_video_stage1_modes_train(tmp_path, mode):
     assert "checkpoint-project-t5-2.bin" not in files
     ad = torch.load(os.path.join(out, "checkpoint-visual-adapter-2.bin"), weights_only=True)
     assert tuple(ad["proj.0.weight"].shape) == (2048, 1024) and tuple(ad["proj.2.weight"].shape) == (4096, 2048)
+    shutil.rmtree(out, ignore_errors=True)
 
 
 LORA = """lora_config:
@@ -174,6 +178,8 @@ def test_image_stage2_all_and_only_train_lora_and_export_merged_tower(tmp_path):
     assert torch.equal(res.dit.final_layer.linear.weight.detach().cpu(), ref)       # DiT frozen in stage2_only
     assert not torch.equal(dit_w.cpu(), ref)                                         # ... and trained in stage2_all
     assert os.path.isdir(os.path.join(out, "siglip-so400m-patch14-224-2"))
+    assert "checkpoint-tower-lora-2.bin" in os.listdir(out) and "checkpoint-dit-2.bin" not in os.listdir(out)
+    shutil.rmtree(str(tmp_path), ignore_errors=True)
 
 
 def test_video_stage2_all_trains_tower_lora_through_the_adapter(tmp_path):
@@ -189,3 +195,17 @@ def test_video_stage2_all_trains_tower_lora_through_the_adapter(tmp_path):
     lo = res.clip_vis.model.lora
     assert "visual_projection" in lo and lo["visual_projection"].B.abs().max().item() > 0
     assert lo["vision_model/encoder/layers/0/mlp/fc2"].B.abs().max().item() > 0
+    # stage-2 resume is real: the un-merged LoRA pairs + trainable biases + optimizer state come back
+    b_before = lo["vision_model/encoder/layers/0/mlp/fc2"].B.detach().cpu().clone()
+    assert "checkpoint-tower-lora-2.bin" in files
+    del res, lo
+    torch.cuda.empty_cache()
+    from genhancer_b200 import trainer
+    cfg = tmp_path / "cfg_stage2_all.yaml"
+    res2 = trainer.main("OpenAICLIP", "use2frames_nextpredic", "stage2_all", argv=["--config", str(cfg)])   # nothing left to do:
+    assert res2.global_step == 2 and res2.opt.step_count == 2                                # what was loaded is what we see
+    b_after = res2.clip_vis.model.lora["vision_model/encoder/layers/0/mlp/fc2"].B.detach().cpu()
+    assert torch.equal(b_after, b_before), "resume did not restore the un-merged LoRA pairs"
+    m = res2.opt.groups[0].exp_avg
+    assert m.abs().max().item() > 0, "resume did not restore the optimizer moments"
+    shutil.rmtree(str(tmp_path), ignore_errors=True)
