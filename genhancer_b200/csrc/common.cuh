@@ -190,6 +190,18 @@ __device__ __forceinline__ void st_shared_cluster_u32(uint32_t cluster_addr, uin
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Arrive WITHOUT release semantics: for barriers that guard no memory, only "I am done reading TMEM" (the accumulator
+// hand-back of the epilogue warps, ordered by tcgen05.fence::before_thread_sync).  The releasing form costs a
+// MEMBAR.ALL.CTA + ERRBAR per arrive at cluster scope -- 15 % of all warp-stall samples of the K = 1024 GEMMs
+// (ncu source page, profiles/r02_gemm_vit_fc1_hot_instructions.txt), once per epilogue warp and tile, on the path that
+// frees the accumulator for the next tile's MMAs.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+#ifdef GH_TEMPTY_RELEASE   // A/B builds (tools/build_ab.sh): the releasing form
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
+}
 // TMA loads of a CTA pair: data lands in THIS CTA's smem, the transaction bytes are counted on the mbarrier at
 // cluster address `bar_cluster` (the leader CTA's full barrier).
 __device__ __forceinline__ void tma2_load_2d(void* smem, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {

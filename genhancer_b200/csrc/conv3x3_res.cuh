@@ -217,7 +217,7 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       if (ep.residual) lean_tile<BN, ACT_NONE, true>(ep, st, bias_s, t_row, half, lane, sub_row, col8, 0, rows, rowmask);
       else lean_tile<BN, ACT_NONE, false>(ep, st, bias_s, t_row, half, lane, sub_row, col8, 0, rows, rowmask);
       tc_fence_before();
-      if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
+      if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }

@@ -955,7 +955,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       if (lane == 0) {
-        if (CTA2) mbar_arrive_cluster(tempty_leader[acc]);   // the leader's issuer waits for both CTAs' epilogues
+        if (CTA2) mbar_arrive_cluster_relaxed(tempty_leader[acc]);   // the leader's issuer waits for both CTAs' epilogues
         else mbar_arrive(&tempty_bar[acc]);
       }
       acc ^= 1;
