@@ -394,7 +394,7 @@ class TowerEngine:
             qkv = qkv.view(B, T, 3, H, dp)
             q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
             attn = torch.empty(B, T, H * dp, dtype=BF16, device=x.device)
-            lse = K.flash_attn_fwd(q, k, v, d ** -0.5, attn, want_lse=save)
+            lse = K.flash_attn_fwd(q, k, v, d ** -0.5, attn, want_lse=save, d_valid=d)
             xm, u_o = L.o.fwd(attn.view(-1, H * dp), drop=self._drop(), residual=x.view(-1, D))
             xm = xm.view(B, T, D)
             g, m2, r2 = K.layernorm_fwd(xm, weight=W["ln2"][li][0], bias=W["ln2"][li][1], eps=eps, save_stats=save)
@@ -420,7 +420,7 @@ class TowerEngine:
         kv = K.gemm(xp.view(-1, D), Hd["wkv"], bias=Hd["bkv"]).view(B, T, 2, H, dp)
         k, v = (kv[:, :, i].permute(0, 2, 1, 3) for i in range(2))
         o = torch.empty(B, 1, H * dp, dtype=BF16, device=x.device)
-        lse = K.flash_attn_fwd(q, k, v, d ** -0.5, o, want_lse=save)
+        lse = K.flash_attn_fwd(q, k, v, d ** -0.5, o, want_lse=save, d_valid=d)
         a = K.gemm(o.view(B, H * dp), Hd["wo"], bias=Hd["bo"])                              # [B, D]
         y, my, ry = K.layernorm_fwd(a, weight=Hd["ln"][0], bias=Hd["ln"][1], eps=eps, save_stats=save)
         pre = torch.empty(B, c.intermediate_size, dtype=BF16, device=x.device) if save else None
@@ -477,7 +477,7 @@ class TowerEngine:
                 dkv = torch.empty_like(Hs["kv"])
                 k, v = (Hs["kv"][:, :, i].permute(0, 2, 1, 3) for i in range(2))
                 dk, dv = (dkv[:, :, i].permute(0, 2, 1, 3) for i in range(2))
-                K.flash_attn_bwd(Hs["q"], k, v, Hs["lse"], d ** -0.5, Hs["o"], do, dq, dk, dv)
+                K.flash_attn_bwd(Hs["q"], k, v, Hs["lse"], d ** -0.5, Hs["o"], do, dq, dk, dv, d_valid=d)
                 kw = dict(residual=dxp.view(-1, D)) if dxp is not None else {}
                 dxp = K.gemm(dkv.view(-1, 2 * H * dp), Hd["wkv"], b_mn=True, **kw).view(B, T, D)
             if dxp is None:
@@ -493,7 +493,7 @@ class TowerEngine:
             dqkv = torch.empty_like(s["qkv"])
             q, k, v = (s["qkv"][:, :, i].permute(0, 2, 1, 3) for i in range(3))
             dq, dk, dv = (dqkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
-            K.flash_attn_bwd(q, k, v, s["lse"], d ** -0.5, s["attn"], dattn.view(B, T, H * dp), dq, dk, dv)
+            K.flash_attn_bwd(q, k, v, s["lse"], d ** -0.5, s["attn"], dattn.view(B, T, H * dp), dq, dk, dv, d_valid=d)
             need_dx = li > 0  # nothing trainable below the first layer's LN1
             dh = L.qkv.bwd(dqkv.view(-1, 3 * H * dp), s["h"], s["u_qkv"], need_dx=need_dx)
             if need_dx:

@@ -36,6 +36,11 @@ struct SegOut {  // two-segment token-major addressing: rows [0,n_split) -> seg0
 struct AttnFwdParams {
   int B, H, Lq, Lk;
   float scale_log2;  // softmax scale * log2(e)
+  // Leading lanes of the head dim that hold data (multiple of 16, <= D).  SigLIP's 72-wide and MetaCLIP-H's 80-wide
+  // heads live zero-padded in 128-lane slots: the MMAs whose K runs over the head dim issue only dvalid / 16 of their D / 16
+  // k-steps, the MMAs whose N is the head dim run with N = dvalid, and the pad lanes of the output are written as zeros
+  // without being computed -- 5/8 of the tensor work of the full 128-lane form at dvalid = 80.
+  int dvalid;
   SegOut o;
   float* lse2;       // [B, H, Lq]  log2-domain logsumexp of the scaled scores
 };
@@ -122,7 +127,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // ELECTED lane (elect.sync), so its operands sit in uniform registers -- under `lane == 0` the compiler wraps
       // each UTCHMMA / UTMALDG / UTCBAR in an ELECT/R2UR/BRA.U.ANY waterfall (~100+ cycles per instruction).
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, ATT_BKV, false, false);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
+      const uint32_t idesc_o = umma_idesc_bf16(128, p.dvalid, false, true);   // N = the lanes that hold data
+      const int ksteps = p.dvalid >> 4;                                       // k-steps of the MMAs that reduce over the head dim
       const uint64_t kdesc = umma_desc_base(16u, 1024u);      // K-major tiles (Q, K, P)
       const uint64_t vdesc = umma_desc_base(8192u, 1024u);    // V as MN-major B operand
       auto load_k = [&](int j) {
@@ -147,8 +153,9 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           for (int c = 0; c < DC; ++c)
   #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss(tmem + Cfg::TM_S + (Cfg::S_BUFS == 2 ? (j & 1) * ATT_BKV : 0), umma_desc_at(kdesc, aQ + c * 16384 + k * 32),
-                      umma_desc_at(kdesc, aK + c * 8192 + k * 32), idesc_s, (c | k) != 0 ? 1u : 0u);
+              if (c * 4 + k < ksteps)
+                umma_ss(tmem + Cfg::TM_S + (Cfg::S_BUFS == 2 ? (j & 1) * ATT_BKV : 0), umma_desc_at(kdesc, aQ + c * 16384 + k * 32),
+                        umma_desc_at(kdesc, aK + c * 8192 + k * 32), idesc_s, (c | k) != 0 ? 1u : 0u);
           umma_commit(&bar_s[j & 1]);
         }
       };
@@ -254,6 +261,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (__any_sync(0xffffffffu, factor != 1.f)) {
 #pragma unroll
           for (int c = 0; c < D / 32; ++c) {
+            if (c * 32 >= p.dvalid) break;     // (columns >= dvalid were never written by the PV MMA)
             uint32_t o[32];
             tmem_ld_32x32(t_lane + Cfg::TM_O + c * 32, o);
             tmem_ld_wait();
@@ -282,16 +290,20 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
     for (int c = 0; c < D / 32; ++c) {
       uint32_t o[32];
-      tmem_ld_32x32(t_lane + Cfg::TM_O + c * 32, o);
-      tmem_ld_wait();
+      if (c * 32 < p.dvalid) {                 // (a warp-uniform branch: tcgen05.ld is .sync.aligned)
+        tmem_ld_32x32(t_lane + Cfg::TM_O + c * 32, o);
+        tmem_ld_wait();
+      }
       if (orow) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          uint4 w = make_uint4(0u, 0u, 0u, 0u);          // pad lanes: exact zeros
+          if (c * 32 + i * 8 < p.dvalid) {
+            w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          }
           *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = w;
         }
       }
@@ -315,6 +327,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 struct AttnBwdParams {
   int B, H, Lq, Lk;
   float scale, scale_log2;
+  int dvalid;          // valid leading lanes of the head dim (see AttnFwdParams)
   const float* lse2;   // [B,H,Lq]
   const float* delta;  // [B,H,Lq]
   bf16 *dq, *dk, *dv;  // element [b,h,l,:] at ptr + b*bs + h*hs + l*rs
@@ -417,7 +430,8 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
   if (warp == 8) {
     {  // control warp: see flash_fwd_kernel (all lanes run the flow, one elected lane issues)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
-      constexpr uint32_t idesc_a = umma_idesc_bf16(128, D, false, true);
+      const uint32_t idesc_a = umma_idesc_bf16(128, p.dvalid, false, true);   // accumulators: N = the lanes that hold data
+      const int ksteps = p.dvalid >> 4;                                       // k-steps of the MMAs that reduce over the head dim
       const uint64_t kdesc = umma_desc_base(16u, 1024u);
       const uint64_t mdesc = umma_desc_base(8192u, 1024u);
       auto load_qd = [&](int i) {
@@ -441,14 +455,16 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
           for (int c = 0; c < DC; ++c)
   #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss(tS, umma_desc_at(kdesc, aK + c * 16384 + k * 32), umma_desc_at(kdesc, aQ + c * 8192 + k * 32),
-                      idesc_s, (c | k) != 0 ? 1u : 0u);
+              if (c * 4 + k < ksteps)
+                umma_ss(tS, umma_desc_at(kdesc, aK + c * 16384 + k * 32), umma_desc_at(kdesc, aQ + c * 8192 + k * 32),
+                        idesc_s, (c | k) != 0 ? 1u : 0u);
   #pragma unroll
           for (int c = 0; c < DC; ++c)
   #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss(tP, umma_desc_at(kdesc, aV + c * 16384 + k * 32), umma_desc_at(kdesc, aD + c * 8192 + k * 32),
-                      idesc_s, (c | k) != 0 ? 1u : 0u);
+              if (c * 4 + k < ksteps)
+                umma_ss(tP, umma_desc_at(kdesc, aV + c * 16384 + k * 32), umma_desc_at(kdesc, aD + c * 8192 + k * 32),
+                        idesc_s, (c | k) != 0 ? 1u : 0u);
           umma_commit(&bar_sd[i & 1]);
         }
       };
@@ -550,16 +566,20 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
 #pragma unroll
       for (int c = half; c < D / 32; c += 2) {   // the two threads of a row take alternate 32-column chunks
         uint32_t o[32];
-        tmem_ld_32x32(t_lane + (which ? Cfg::TM_DK : Cfg::TM_DV) + c * 32, o);
-        tmem_ld_wait();
+        if (c * 32 < p.dvalid) {                     // (warp-uniform: half is per warp)
+          tmem_ld_32x32(t_lane + (which ? Cfg::TM_DK : Cfg::TM_DV) + c * 32, o);
+          tmem_ld_wait();
+        }
         if (kl < p.Lk) {
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]), __uint_as_float(o[8 * q4 + 1]));
-            w.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]), __uint_as_float(o[8 * q4 + 3]));
-            w.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]), __uint_as_float(o[8 * q4 + 5]));
-            w.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]), __uint_as_float(o[8 * q4 + 7]));
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);   // pad lanes: exact zeros
+            if (c * 32 + q4 * 8 < p.dvalid) {
+              w.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]), __uint_as_float(o[8 * q4 + 1]));
+              w.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]), __uint_as_float(o[8 * q4 + 3]));
+              w.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]), __uint_as_float(o[8 * q4 + 5]));
+              w.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]), __uint_as_float(o[8 * q4 + 7]));
+            }
             *reinterpret_cast<uint4*>(dstp + c * 32 + q4 * 8) = w;
           }
         }
@@ -634,7 +654,8 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 8) {
     {  // control warp: see flash_fwd_kernel (all lanes run the flow, one elected lane issues)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
-      constexpr uint32_t idesc_a = umma_idesc_bf16(128, D, false, true);
+      const uint32_t idesc_a = umma_idesc_bf16(128, p.dvalid, false, true);   // accumulators: N = the lanes that hold data
+      const int ksteps = p.dvalid >> 4;                                       // k-steps of the MMAs that reduce over the head dim
       const uint64_t kdesc = umma_desc_base(16u, 1024u);
       const uint64_t mdesc = umma_desc_base(8192u, 1024u);
       auto load_kv = [&](int j) {
@@ -658,14 +679,16 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           for (int c = 0; c < DC; ++c)
   #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss(tS, umma_desc_at(kdesc, aQ + c * 16384 + k * 32), umma_desc_at(kdesc, aK + c * 8192 + k * 32),
-                      idesc_s, (c | k) != 0 ? 1u : 0u);
+              if (c * 4 + k < ksteps)
+                umma_ss(tS, umma_desc_at(kdesc, aQ + c * 16384 + k * 32), umma_desc_at(kdesc, aK + c * 8192 + k * 32),
+                        idesc_s, (c | k) != 0 ? 1u : 0u);
   #pragma unroll
           for (int c = 0; c < DC; ++c)
   #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss(tP, umma_desc_at(kdesc, aD + c * 16384 + k * 32), umma_desc_at(kdesc, aV + c * 8192 + k * 32),
-                      idesc_s, (c | k) != 0 ? 1u : 0u);
+              if (c * 4 + k < ksteps)
+                umma_ss(tP, umma_desc_at(kdesc, aD + c * 16384 + k * 32), umma_desc_at(kdesc, aV + c * 8192 + k * 32),
+                        idesc_s, (c | k) != 0 ? 1u : 0u);
           umma_commit(&bar_sd[j & 1]);
         }
       };
@@ -747,16 +770,20 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
     for (int c = half; c < D / 32; c += 2) {
       uint32_t o[32];
-      tmem_ld_32x32(t_lane + Cfg::TM_DQ + c * 32, o);
-      tmem_ld_wait();
+      if (c * 32 < p.dvalid) {
+        tmem_ld_32x32(t_lane + Cfg::TM_DQ + c * 32, o);
+        tmem_ld_wait();
+      }
       if (ql < p.Lq) {
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]), __uint_as_float(o[8 * q4 + 1]));
-          w.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]), __uint_as_float(o[8 * q4 + 3]));
-          w.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]), __uint_as_float(o[8 * q4 + 5]));
-          w.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]), __uint_as_float(o[8 * q4 + 7]));
+          uint4 w = make_uint4(0u, 0u, 0u, 0u);   // pad lanes: exact zeros
+          if (c * 32 + q4 * 8 < p.dvalid) {
+            w.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]), __uint_as_float(o[8 * q4 + 1]));
+            w.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]), __uint_as_float(o[8 * q4 + 3]));
+            w.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]), __uint_as_float(o[8 * q4 + 5]));
+            w.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]), __uint_as_float(o[8 * q4 + 7]));
+          }
           *reinterpret_cast<uint4*>(dstp + c * 32 + q4 * 8) = w;
         }
       }
@@ -803,12 +830,14 @@ int attn_init() {
 using namespace gh;
 
 extern "C" int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh_attn_tensor* v,
-                                 int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t D, float scale,
+                                 int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t D, int32_t d_valid, float scale,
                                  const gh_attn_out* o, float* lse2, void* stream) {
   GH_REQUIRE(attn_tensor_ok(q) && attn_tensor_ok(k) && attn_tensor_ok(v), GH_ERR_ALIGN,
              "gh_flash_attn_fwd: q/k/v must be non-NULL, 16B aligned, strides multiples of 8 elements");
   GH_REQUIRE(o && o->seg1, GH_ERR_NULL, "gh_flash_attn_fwd: output is NULL");
   GH_REQUIRE(D == 64 || D == 128, GH_ERR_UNSUPPORTED, "gh_flash_attn_fwd: head dim %d unsupported (64, 128)", D);
+  if (d_valid <= 0) d_valid = D;
+  GH_REQUIRE(d_valid % 16 == 0 && d_valid <= D, GH_ERR_BAD_SHAPE, "gh_flash_attn_fwd: d_valid=%d must be a multiple of 16, <= D", d_valid);
   GH_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, GH_ERR_BAD_SHAPE, "gh_flash_attn_fwd: bad shape");
   if (B == 0 || Lq == 0) return GH_OK;
   GH_REQUIRE(o->n_split >= 0 && o->n_split <= Lq && (o->n_split == 0 || o->seg0), GH_ERR_BAD_SHAPE,
@@ -823,6 +852,7 @@ extern "C" int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* 
   AttnFwdParams p{};
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.dvalid = d_valid;
   p.o.p0 = static_cast<bf16*>(o->seg0); p.o.bs0 = o->seg0_batch_stride; p.o.rs0 = o->seg0_row_stride;
   p.o.p1 = static_cast<bf16*>(o->seg1); p.o.bs1 = o->seg1_batch_stride; p.o.rs1 = o->seg1_row_stride;
   p.o.n_split = o->n_split;
@@ -837,6 +867,11 @@ extern "C" int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* 
   return GH_OK;
 }
 
+extern "C" int64_t gh_flash_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t Lq, int32_t D, int32_t which) {
+  const int64_t rows = static_cast<int64_t>(B) * H * Lq;
+  return which == 0 ? rows * D * 2 : rows * 4;
+}
+
 static void seg_from(const gh_attn_out* o, SegOut* s) {
   s->p0 = static_cast<bf16*>(o->seg0); s->bs0 = o->seg0_batch_stride; s->rs0 = o->seg0_row_stride;
   s->p1 = static_cast<bf16*>(o->seg1); s->bs1 = o->seg1_batch_stride; s->rs1 = o->seg1_row_stride;
@@ -845,7 +880,7 @@ static void seg_from(const gh_attn_out* o, SegOut* s) {
 
 extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh_attn_tensor* v,
                                  const gh_attn_out* o, const gh_attn_out* d_o, const float* lse2, int32_t B,
-                                 int32_t H, int32_t Lq, int32_t Lk, int32_t D, float scale, const gh_attn_tensor* dq,
+                                 int32_t H, int32_t Lq, int32_t Lk, int32_t D, int32_t d_valid, float scale, const gh_attn_tensor* dq,
                                  const gh_attn_tensor* dk, const gh_attn_tensor* dv, void* ws_do_headmajor,
                                  float* ws_delta, void* stream) {
   GH_REQUIRE(attn_tensor_ok(q) && attn_tensor_ok(k) && attn_tensor_ok(v) && attn_tensor_ok(dq) && attn_tensor_ok(dk) &&
@@ -854,6 +889,8 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
   GH_REQUIRE(o && d_o && o->seg1 && d_o->seg1 && lse2 && ws_do_headmajor && ws_delta, GH_ERR_NULL,
              "gh_flash_attn_bwd: NULL pointer");
   GH_REQUIRE(D == 64 || D == 128, GH_ERR_UNSUPPORTED, "gh_flash_attn_bwd: head dim %d unsupported (64, 128)", D);
+  if (d_valid <= 0) d_valid = D;
+  GH_REQUIRE(d_valid % 16 == 0 && d_valid <= D, GH_ERR_BAD_SHAPE, "gh_flash_attn_bwd: d_valid=%d must be a multiple of 16, <= D", d_valid);
   GH_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, GH_ERR_BAD_SHAPE, "gh_flash_attn_bwd: bad shape");
   if (B == 0 || Lq == 0) return GH_OK;
   GH_REQUIRE(aligned16(ws_do_headmajor), GH_ERR_ALIGN, "gh_flash_attn_bwd: workspace must be 16B aligned");
@@ -879,6 +916,7 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.dvalid = d_valid;
   p.lse2 = lse2; p.delta = ws_delta;
   p.dq = static_cast<bf16*>(const_cast<void*>(dq->ptr)); p.dq_bs = dq->batch_stride; p.dq_hs = dq->head_stride; p.dq_rs = dq->row_stride;
   p.dk = static_cast<bf16*>(const_cast<void*>(dk->ptr)); p.dk_bs = dk->batch_stride; p.dk_hs = dk->head_stride; p.dk_rs = dk->row_stride;

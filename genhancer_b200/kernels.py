@@ -351,9 +351,10 @@ def _attn_tensor(t: torch.Tensor) -> AttnTensor:
     return AttnTensor(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
 
 
-def flash_attn_fwd(q, k, v, scale, out1, out0=None, n_split=0, want_lse=True):
+def flash_attn_fwd(q, k, v, scale, out1, out0=None, n_split=0, want_lse=True, d_valid=0):
     """q,k,v: [B,H,L,D] views (any strides, D contiguous). out1/out0: token-major [B, L(seg), H*D] (row pitch free).
-    Rows l < n_split go to out0.  Returns lse2 [B,H,Lq] fp32 (log2 domain) or None."""
+    Rows l < n_split go to out0.  Returns lse2 [B,H,Lq] fp32 (log2 domain) or None.
+    ``d_valid``: leading lanes of D that hold data (heads zero-padded into a wider slot); 0 = all."""
     _ensure(q)
     B, H, Lq, D = q.shape
     Lk = k.shape[2]
@@ -366,8 +367,8 @@ def flash_attn_fwd(q, k, v, scale, out1, out0=None, n_split=0, want_lse=True):
     o.seg1, o.seg1_batch_stride, o.seg1_row_stride = out1.data_ptr(), out1.stride(0), out1.stride(1)
     o.n_split = n_split
     lse = torch.empty(B, H, Lq, dtype=F32, device=q.device) if want_lse else None
-    check(_lib.lib().gh_flash_attn_fwd(C.byref(at[0]), C.byref(at[1]), C.byref(at[2]), B, H, Lq, Lk, D, float(scale),
-                                       C.byref(o), _p(lse), _stream()))
+    check(_lib.lib().gh_flash_attn_fwd(C.byref(at[0]), C.byref(at[1]), C.byref(at[2]), B, H, Lq, Lk, D, _dvalid(d_valid, D),
+                                       float(scale), C.byref(o), _p(lse), _stream()))
     _count()
     return lse
 
@@ -508,7 +509,11 @@ def _attn_out(out1, out0, n_split) -> AttnOut:
     return o
 
 
-def flash_attn_bwd(q, k, v, lse, scale, o1, do1, dq, dk, dv, o0=None, do0=None, n_split=0):
+def _dvalid(d_valid: int, D: int) -> int:
+    return 0 if not d_valid or d_valid >= D else (int(d_valid) + 15) // 16 * 16
+
+
+def flash_attn_bwd(q, k, v, lse, scale, o1, do1, dq, dk, dv, o0=None, do0=None, n_split=0, d_valid=0):
     """Backward of flash_attn_fwd.  o*/do* token-major (same split as forward); dq/dk/dv [B,H,L,D] views (any
     strides, D contiguous) are written."""
     _ensure(q)
@@ -517,10 +522,10 @@ def flash_attn_bwd(q, k, v, lse, scale, o1, do1, dq, dk, dv, o0=None, do0=None, 
     at = [_attn_tensor(x) for x in (q, k, v, dq, dk, dv)]
     o = _attn_out(o1, o0, n_split)
     do = _attn_out(do1, do0, n_split)
-    ws_do = torch.empty(B, H, Lq, D, dtype=BF16, device=q.device)
-    ws_delta = torch.empty(B, H, Lq, dtype=F32, device=q.device)
+    ws_do = torch.empty(_lib.lib().gh_flash_attn_bwd_workspace_bytes(B, H, Lq, D, 0) // 2, dtype=BF16, device=q.device)
+    ws_delta = torch.empty(_lib.lib().gh_flash_attn_bwd_workspace_bytes(B, H, Lq, D, 1) // 4, dtype=F32, device=q.device)
     check(_lib.lib().gh_flash_attn_bwd(C.byref(at[0]), C.byref(at[1]), C.byref(at[2]), C.byref(o), C.byref(do),
-                                       lse.data_ptr(), B, H, Lq, Lk, D, float(scale), C.byref(at[3]), C.byref(at[4]),
+                                       lse.data_ptr(), B, H, Lq, Lk, D, _dvalid(d_valid, D), float(scale), C.byref(at[3]), C.byref(at[4]),
                                        C.byref(at[5]), ws_do.data_ptr(), ws_delta.data_ptr(), _stream()))
     _count(3)
 

@@ -248,7 +248,8 @@ int gh_batched_copy(const gh_copy_desc* descs_device, int32_t n_desc, int32_t bl
 /* LoRA input dropout (peft lora.Linear: lora_B(lora_A(dropout(x))), lora_dropout 0.1 in the stage-2 YAMLs,
  * train_SigLIP_stage2_all.py:139).  y = keep ? x / (1-p) : 0 on bf16; the keep mask is a pure function of
  * (seed, offset, element index) -- Philox-4x32-10 -- so the backward regenerates it:
- * gh_dropout_bwd_add: dx += keep ? t / (1-p) : 0.  numel % 4 == 0, contiguous.
+ * gh_dropout_bwd_add: dx += keep ? t / (1-p) : 0.  numel % 8 == 0, contiguous, 16-byte aligned
+ * (one Philox block per 8 elements, 16 random bits each: p is quantised to 1/65536).
  * offset_base (device uint64, may be NULL) is added to `offset` on the device: the caller advances it once per step
  * (a stream-ordered add), so a CUDA-graph replay -- which bakes the by-value `offset` in -- still draws fresh masks,
  * and the backward of the same step regenerates the forward's. */
@@ -278,8 +279,12 @@ typedef struct {
   int64_t seg1_batch_stride, seg1_row_stride;
   int32_t n_split;
 } gh_attn_out;
+/* d_valid (multiple of 16, <= D; 0 = D): leading lanes of the head dim that hold data.  Heads narrower than the 64- /
+ * 128-lane slot they are stored in (SigLIP 72, MetaCLIP-H 80: zero-padded) run only d_valid / 16 of the k-steps of the
+ * MMAs that reduce over the head dim and N = d_valid in the ones that produce it; pad lanes of O / dQ / dK / dV are
+ * written as exact zeros. */
 int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh_attn_tensor* v, int32_t B, int32_t H,
-                      int32_t Lq, int32_t Lk, int32_t D, float scale, const gh_attn_out* o, float* lse2,
+                      int32_t Lq, int32_t Lk, int32_t D, int32_t d_valid, float scale, const gh_attn_out* o, float* lse2,
                       void* stream);
 /* Backward of the above (autograd of math.py:9 / modeling_clip.py:319-331): three launches --
  * prep (delta = rowsum(dO*O), dO gathered head-major), dK/dV pass, dQ pass (S and dP recomputed; no atomics).
@@ -288,8 +293,10 @@ int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh
  * Workspaces: ws_do_headmajor bf16 [B,H,Lq,D], ws_delta fp32 [B,H,Lq]. */
 int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh_attn_tensor* v, const gh_attn_out* o,
                       const gh_attn_out* d_o, const float* lse2, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
-                      int32_t D, float scale, const gh_attn_tensor* dq, const gh_attn_tensor* dk,
+                      int32_t D, int32_t d_valid, float scale, const gh_attn_tensor* dq, const gh_attn_tensor* dk,
                       const gh_attn_tensor* dv, void* ws_do_headmajor, float* ws_delta, void* stream);
+/* bytes of the two workspaces of gh_flash_attn_bwd: [0] = ws_do_headmajor, [1] = ws_delta */
+int64_t gh_flash_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t Lq, int32_t D, int32_t which);
 
 /* --------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05, NHWC bf16 activations (frozen FLUX AE encoder,

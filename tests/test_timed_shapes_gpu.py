@@ -130,12 +130,12 @@ def test_attention_fwd_bwd_at_benchmarked_lengths(L, Dreal):
     q, k, v = mk(), mk(), mk()
     scale = Dreal ** -0.5
     o = torch.empty(B, L, H * D, device=dev, dtype=torch.bfloat16)
-    lse = K.flash_attn_fwd(q, k, v, scale, o)
+    lse = K.flash_attn_fwd(q, k, v, scale, o, d_valid=Dreal)          # (72 -> 80 lanes of work, as the towers call it)
     do = torch.zeros(B, L, H, D, device=dev, dtype=torch.bfloat16)
     do[..., :Dreal] = torch.randn(B, L, H, Dreal, device=dev, generator=g).to(torch.bfloat16)
     do = do.view(B, L, H * D)
     dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
-    K.flash_attn_bwd(q, k, v, lse, scale, o, do, dq, dk, dv)
+    K.flash_attn_bwd(q, k, v, lse, scale, o, do, dq, dk, dv, d_valid=Dreal)
     do_h = do.view(B, L, H, D).permute(0, 2, 1, 3)
     ro, rq, rk, rv = _sdpa_ref(q[..., :Dreal], k[..., :Dreal], v[..., :Dreal], do_h[..., :Dreal], scale)
     o_h = o.view(B, L, H, D).permute(0, 2, 1, 3)
