@@ -380,7 +380,13 @@ class TowerEngine:
         eps, act = c.layer_norm_eps, self.act
         S = {} if save else None
         self._drop_new_step(pixel_values.device)
-        img = pixel_values.float().contiguous()
+        if K.is_u8_image(pixel_values):    # the decoded uint8 HWC batch itself: u8 / 255 happens inside the gather
+            if _norm is None:
+                raise ValueError("a uint8 image batch needs `_norm=(mean3, std3)`: the tower takes NORMALISED pixels, and "
+                                 "raw [0, 255] bytes are not that")
+            img = pixel_values.contiguous()
+        else:
+            img = pixel_values.float().contiguous()
         mean, std = _norm if _norm is not None else (None, None)
         A = K.patch_im2col(img, c.patch_size, self.patch_ld, mean, std)
         patch = K.gemm(A, W["patch_w"], bias=W["patch_b"])

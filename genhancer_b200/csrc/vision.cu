@@ -14,17 +14,30 @@ using bf16 = __nv_bfloat16;
 // per-channel normalisation (x - mean) / std fused in.  One CTA per (b, patch-row).
 // HF CLIPVisionEmbeddings.patch_embedding, modeling_clip.py:147-153,208-209.
 // ---------------------------------------------------------------------------
-__global__ void patch_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int S, int p, int G,
+// Pixel (b, c, y, x) of the batch as the fp32 value in [0, 1] the reference's loader hands over: either an fp32 NCHW
+// tensor, or -- U8 -- the decoded uint8 HWC image itself, value / 255 with IEEE division (torchvision's ToTensor,
+// image_datasets/dataset_cc3m.py:107-113).  With U8 the batch crosses PCIe AND is read from HBM at 1 byte per value
+// and the 43 MB fp32 copy of a 32 x 336 x 336 batch never exists.
+template <bool U8>
+__device__ __forceinline__ float load_px(const void* img, int b, int c, int y, int x, int H, int W) {
+  if (U8) {
+    const uint8_t* s = static_cast<const uint8_t*>(img);
+    return __fdiv_rn(static_cast<float>(s[((static_cast<int64_t>(b) * H + y) * W + x) * 3 + c]), 255.f);
+  }
+  return static_cast<const float*>(img)[((static_cast<int64_t>(b) * 3 + c) * H + y) * W + x];
+}
+
+template <bool U8>
+__global__ void patch_im2col_kernel(const void* __restrict__ img, bf16* __restrict__ out, int S, int p, int G,
                                     int64_t ld, float m0, float m1, float m2, float is0, float is1, float is2) {
   const int b = blockIdx.y, py = blockIdx.x;
   const float mean[3] = {m0, m1, m2}, istd[3] = {is0, is1, is2};
   const int row_elems = G * p;  // pixels of one image row that belong to patches
   for (int ci = 0; ci < 3 * p; ++ci) {
     const int c = ci / p, i = ci % p;
-    const float* src = img + ((static_cast<int64_t>(b) * 3 + c) * S + py * p + i) * S;
     for (int x = threadIdx.x; x < row_elems; x += blockDim.x) {
       const int px = x / p, j = x - px * p;
-      const float v = (src[x] - mean[c]) * istd[c];
+      const float v = (load_px<U8>(img, b, c, py * p + i, x, S, S) - mean[c]) * istd[c];
       out[(static_cast<int64_t>(b) * G * G + py * G + px) * ld + c * p * p + i * p + j] = __float2bfloat16_rn(v);
     }
   }
@@ -32,7 +45,8 @@ __global__ void patch_im2col_kernel(const float* __restrict__ img, bf16* __restr
 
 // 3x3 / pad 1 im2col for the AE's conv_in (Cin = 3): image fp32 NCHW -> bf16 [B*H*W, 32], k = (kh*3+kw)*3 + c,
 // columns 27..31 zero; normalisation fused.  autoencoder.py:126.
-__global__ void im2col3x3_c3_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int H, int W,
+template <bool U8>
+__global__ void im2col3x3_c3_kernel(const void* __restrict__ img, bf16* __restrict__ out, int B, int H, int W,
                                     float mean, float istd) {
   const int64_t n = static_cast<int64_t>(B) * H * W;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -51,7 +65,7 @@ __global__ void im2col3x3_c3_kernel(const float* __restrict__ img, bf16* __restr
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          v[(kh * 3 + kw) * 3 + c] = (img[((static_cast<int64_t>(b) * 3 + c) * H + yy) * W + xx] - mean) * istd;
+          v[(kh * 3 + kw) * 3 + c] = (load_px<U8>(img, b, c, yy, xx, H, W) - mean) * istd;
       }
     }
   uint4* dst = reinterpret_cast<uint4*>(out + i * 32);
@@ -259,8 +273,9 @@ static inline int grid1d(int64_t n, int block) { return static_cast<int>((n + bl
 
 using namespace gh;
 
-extern "C" int gh_patch_im2col(const float* img, void* out_bf16, int32_t B, int32_t S, int32_t patch, int64_t ld,
-                               const float* mean3, const float* std3, void* stream) {
+static int patch_im2col_any(bool u8, const void* img, void* out_bf16, int32_t B, int32_t S, int32_t patch, int64_t ld,
+                            const float* mean3, const float* std3, void* stream) {
+  using namespace gh;
   GH_REQUIRE(img && out_bf16, GH_ERR_NULL, "gh_patch_im2col: NULL pointer");
   GH_REQUIRE(B > 0 && S > 0 && patch > 0 && S / patch > 0 && ld >= 3 * patch * patch, GH_ERR_BAD_SHAPE,
              "gh_patch_im2col: bad shape");
@@ -268,21 +283,48 @@ extern "C" int gh_patch_im2col(const float* img, void* out_bf16, int32_t B, int3
   float m[3] = {0, 0, 0}, is[3] = {1, 1, 1};
   if (mean3 && std3)
     for (int c = 0; c < 3; ++c) { m[c] = mean3[c]; is[c] = 1.f / std3[c]; }  // host pointers (3 floats)
-  patch_im2col_kernel<<<dim3(G, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      img, static_cast<bf16*>(out_bf16), S, patch, G, ld, m[0], m[1], m[2], is[0], is[1], is[2]);
+  if (u8)
+    patch_im2col_kernel<true><<<dim3(G, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        img, static_cast<bf16*>(out_bf16), S, patch, G, ld, m[0], m[1], m[2], is[0], is[1], is[2]);
+  else
+    patch_im2col_kernel<false><<<dim3(G, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        img, static_cast<bf16*>(out_bf16), S, patch, G, ld, m[0], m[1], m[2], is[0], is[1], is[2]);
+  GH_CHECK_CUDA(cudaGetLastError());
+  return GH_OK;
+}
+
+extern "C" int gh_patch_im2col(const float* img, void* out_bf16, int32_t B, int32_t S, int32_t patch, int64_t ld,
+                               const float* mean3, const float* std3, void* stream) {
+  return patch_im2col_any(false, img, out_bf16, B, S, patch, ld, mean3, std3, stream);
+}
+extern "C" int gh_patch_im2col_u8hwc(const void* img_u8, void* out_bf16, int32_t B, int32_t S, int32_t patch, int64_t ld,
+                                     const float* mean3, const float* std3, void* stream) {
+  return patch_im2col_any(true, img_u8, out_bf16, B, S, patch, ld, mean3, std3, stream);
+}
+
+static int im2col3x3_c3_any(bool u8, const void* img, void* out_bf16, int32_t B, int32_t H, int32_t W, float mean,
+                            float std, void* stream) {
+  using namespace gh;
+  GH_REQUIRE(img && out_bf16 && aligned16(out_bf16), GH_ERR_NULL, "gh_im2col3x3_c3: NULL / misaligned pointer");
+  GH_REQUIRE(B > 0 && H > 0 && W > 0 && std != 0.f, GH_ERR_BAD_SHAPE, "gh_im2col3x3_c3: bad shape");
+  const int64_t n = static_cast<int64_t>(B) * H * W;
+  if (u8)
+    im2col3x3_c3_kernel<true><<<grid1d(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        img, static_cast<bf16*>(out_bf16), B, H, W, mean, 1.f / std);
+  else
+    im2col3x3_c3_kernel<false><<<grid1d(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        img, static_cast<bf16*>(out_bf16), B, H, W, mean, 1.f / std);
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
 }
 
 extern "C" int gh_im2col3x3_c3(const float* img, void* out_bf16, int32_t B, int32_t H, int32_t W, float mean,
                                float std, void* stream) {
-  GH_REQUIRE(img && out_bf16 && aligned16(out_bf16), GH_ERR_NULL, "gh_im2col3x3_c3: NULL / misaligned pointer");
-  GH_REQUIRE(B > 0 && H > 0 && W > 0 && std != 0.f, GH_ERR_BAD_SHAPE, "gh_im2col3x3_c3: bad shape");
-  const int64_t n = static_cast<int64_t>(B) * H * W;
-  im2col3x3_c3_kernel<<<grid1d(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      img, static_cast<bf16*>(out_bf16), B, H, W, mean, 1.f / std);
-  GH_CHECK_CUDA(cudaGetLastError());
-  return GH_OK;
+  return im2col3x3_c3_any(false, img, out_bf16, B, H, W, mean, std, stream);
+}
+extern "C" int gh_im2col3x3_c3_u8hwc(const void* img_u8, void* out_bf16, int32_t B, int32_t H, int32_t W, float mean,
+                                     float std, void* stream) {
+  return im2col3x3_c3_any(true, img_u8, out_bf16, B, H, W, mean, std, stream);
 }
 
 extern "C" int gh_embed_assemble(const void* patch_bf16, const float* cls, const float* pos, void* out_bf16, int32_t B,

@@ -183,11 +183,12 @@ class Encoder(_ConvStack):
 
     def moments_nhwc(self, img: Tensor, mean: float = 0.0, std: float = 1.0) -> Tensor:
         """img fp32 NCHW; (img - mean) / std is folded into the conv_in gather. -> fp32 [B, H/8, W/8, 2z]."""
-        if img.dim() != 4 or img.shape[1] != 3:
+        u8 = K.is_u8_image(img)                 # the decoded uint8 HWC batch: u8 / 255 happens inside the conv_in gather
+        if not u8 and (img.dim() != 4 or img.shape[1] != 3):
             raise ValueError(f"AutoEncoder expects [B,3,H,W] images, got {tuple(img.shape)}")
         W = self._prepared()
-        B, _, H, Wd = img.shape
-        a = K.im2col3x3_c3(img.float().contiguous(), mean, std)
+        B, H, Wd = K.image_bhw(img)
+        a = K.im2col3x3_c3(img.contiguous() if u8 else img.float().contiguous(), mean, std)
         h = K.gemm(a, W["conv_in"][0], bias=W["conv_in"][1]).view(B, H, Wd, self.ch)
         for lvl in range(self.num_resolutions):
             for j, blk in enumerate(self.down[lvl].block):

@@ -407,26 +407,46 @@ def conv2d_nhwc(x, w, KH, KW, stride=1, pad=0, Ho=None, Wo=None, bias=None, act=
     return out
 
 
+def is_u8_image(img: torch.Tensor) -> bool:
+    """A decoded RGB batch as the loader's workers produce it: uint8 [B, H, W, 3]."""
+    return img.dtype == torch.uint8 and img.dim() == 4 and img.shape[-1] == 3
+
+
+def image_bhw(img: torch.Tensor) -> tuple[int, int, int]:
+    """(B, H, W) of an fp32 NCHW [B,3,H,W] or uint8 HWC [B,H,W,3] batch."""
+    if is_u8_image(img):
+        return img.shape[0], img.shape[1], img.shape[2]
+    if img.dim() != 4 or img.shape[1] != 3:
+        raise _lib.GhError(f"expected an image batch [B,3,H,W] (float) or [B,H,W,3] (uint8), got {img.dtype} {tuple(img.shape)}")
+    return img.shape[0], img.shape[2], img.shape[3]
+
+
 def patch_im2col(img, patch, ld, mean=None, std=None):
-    """img fp32 NCHW [B,3,S,S] -> bf16 [B*G*G, ld] view of width 3*p*p (row pitch ld)."""
+    """img fp32 NCHW [B,3,S,S] in [0,1] -- or the decoded uint8 HWC [B,S,S,3] batch itself (u8 / 255 on the fly) --
+    -> bf16 [B*G*G, ld] view of width 3*p*p (row pitch ld)."""
     _ensure(img)
-    assert img.dtype == F32 and img.is_contiguous()
-    B, _, S, _ = img.shape
+    u8 = is_u8_image(img)
+    assert (u8 or img.dtype == F32) and img.is_contiguous()
+    B, S, _ = image_bhw(img)
     G = S // patch
     buf = torch.empty(B * G * G, ld, dtype=BF16, device=img.device)
     m3 = (C.c_float * 3)(*mean) if mean is not None else None
     s3 = (C.c_float * 3)(*std) if std is not None else None
-    check(_lib.lib().gh_patch_im2col(img.data_ptr(), buf.data_ptr(), B, S, patch, ld, m3, s3, _stream()))
+    fn = _lib.lib().gh_patch_im2col_u8hwc if u8 else _lib.lib().gh_patch_im2col
+    check(fn(img.data_ptr(), buf.data_ptr(), B, S, patch, ld, m3, s3, _stream()))
     _count()
     return buf[:, : 3 * patch * patch]
 
 
 def im2col3x3_c3(img, mean=0.0, std=1.0):
+    """fp32 NCHW [B,3,H,W] or uint8 HWC [B,H,W,3] -> bf16 [B*H*W, 32] (the AE conv_in gather, normalisation fused)."""
     _ensure(img)
-    assert img.dtype == F32 and img.is_contiguous()
-    B, _, H, W = img.shape
+    u8 = is_u8_image(img)
+    assert (u8 or img.dtype == F32) and img.is_contiguous()
+    B, H, W = image_bhw(img)
     out = torch.empty(B * H * W, 32, dtype=BF16, device=img.device)
-    check(_lib.lib().gh_im2col3x3_c3(img.data_ptr(), out.data_ptr(), B, H, W, float(mean), float(std), _stream()))
+    fn = _lib.lib().gh_im2col3x3_c3_u8hwc if u8 else _lib.lib().gh_im2col3x3_c3
+    check(fn(img.data_ptr(), out.data_ptr(), B, H, W, float(mean), float(std), _stream()))
     _count()
     return out
 

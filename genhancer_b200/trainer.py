@@ -349,12 +349,13 @@ def main(family: str, mode: str = "image", stage: str = "stage1", argv=None, max
         use_graph = False
 
     def to_input(t):
-        """A loader may hand over decoded frames as uint8 [B,H,W,3] (1 byte per value over PCIe): ToTensor then runs
-        on the device (gh_u8hwc_to_f32chw); fp32 [B,3,H,W] in [0,1] batches pass through as before."""
+        """A loader may hand over decoded frames as uint8 [B,H,W,3]: they cross PCIe at 1 byte per value and go to the
+        step AS THEY ARE -- ToTensor (u8 / 255) and the two Normalize transforms happen inside the patch-embed / conv_in
+        gathers (gh_patch_im2col_u8hwc, gh_im2col3x3_c3_u8hwc), bit-identical to the fp32 path; fp32 [B,3,H,W] batches
+        in [0,1] pass through as before."""
         t = t.to(device, non_blocking=True)
         if t.dtype == torch.uint8 and t.dim() == 4 and t.shape[-1] == 3:
-            from . import kernels as K
-            return K.u8hwc_to_f32chw(t)
+            return t.contiguous()
         return t.float()
 
     if mode == "image":

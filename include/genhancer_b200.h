@@ -325,10 +325,19 @@ int gh_conv2d_nhwc(const gh_conv_args* args, void* stream);
  * Feeds gh_gemm_bf16 with the flattened Conv2d weight: HF CLIPVisionEmbeddings, modeling_clip.py:147-153,208. */
 int gh_patch_im2col(const float* img, void* out_bf16, int32_t B, int32_t S, int32_t patch, int64_t ld,
                     const float* mean3, const float* std3, void* stream);
+/* The same gather straight from the DECODED image: img_u8 uint8 HWC [B,S,S,3]; every value becomes u8 / 255 (IEEE
+ * division = torchvision ToTensor, image_datasets/dataset_cc3m.py:107-113) before (x-mean)/std, so the result is
+ * bit-identical to gh_u8hwc_to_f32chw + gh_patch_im2col while the batch is read at 1 byte per value and no fp32 copy
+ * of it exists. */
+int gh_patch_im2col_u8hwc(const void* img_u8, void* out_bf16, int32_t B, int32_t S, int32_t patch, int64_t ld,
+                          const float* mean3, const float* std3, void* stream);
 /* 3x3/pad-1 im2col of a 3-channel image for the AE conv_in (autoencoder.py:126): -> bf16 [B*H*W, 32],
  * k = (kh*3+kw)*3 + c, columns 27..31 zero; (x-mean)/std fused (NORMALIZE_VAE, train_SigLIP_stage1.py:59). */
 int gh_im2col3x3_c3(const float* img, void* out_bf16, int32_t B, int32_t H, int32_t W, float mean, float std,
                     void* stream);
+/* uint8 HWC form of the above (see gh_patch_im2col_u8hwc). */
+int gh_im2col3x3_c3_u8hwc(const void* img_u8, void* out_bf16, int32_t B, int32_t H, int32_t W, float mean, float std,
+                          void* stream);
 /* out[b,t,:] = (t < has_cls ? cls : patch[b,t-has_cls,:]) + pos[t,:]   (modeling_clip.py:210-217) */
 int gh_embed_assemble(const void* patch_bf16, const float* cls, const float* pos, void* out_bf16, int32_t B, int32_t T,
                       int32_t D, int32_t has_cls, void* stream);

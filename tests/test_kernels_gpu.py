@@ -106,3 +106,21 @@ def test_conv3x3_resident_weight_kernel_matches_torch(B, H, W, res):
     # borders (zero padding through TMA out-of-bounds fill) and the ragged last patches on their own
     for a, b in zip((y[:, 0], y[:, -1], y[:, :, 0], y[:, :, -1]), (ref[:, 0], ref[:, -1], ref[:, :, 0], ref[:, :, -1])):
         assert (a.float() - b).norm() / b.norm() < 6e-3
+
+
+def test_uint8_hwc_gathers_are_bit_identical_to_the_fp32_path():
+    """f-4: the decoded uint8 HWC batch feeds the patch-embed / conv_in gathers directly (u8 / 255 on the fly):
+    same bits as ToTensor on the device followed by the fp32 gathers, at 1 byte per value."""
+    from genhancer_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(3)
+    u8 = torch.randint(0, 256, (3, 56, 56, 3), device="cuda", generator=g, dtype=torch.uint8)
+    f32 = K.u8hwc_to_f32chw(u8)
+    assert torch.equal(f32, u8.permute(0, 3, 1, 2).float().div(255))
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    a = K.patch_im2col(f32, 14, 592, mean, std)
+    b = K.patch_im2col(u8, 14, 592, mean, std)
+    assert a.shape == b.shape == (3 * 16, 588) and torch.equal(a, b)
+    c = K.im2col3x3_c3(f32, 0.5, 0.5)
+    d = K.im2col3x3_c3(u8, 0.5, 0.5)
+    assert c.shape == d.shape == (3 * 56 * 56, 32) and torch.equal(c, d)
+    assert K.image_bhw(u8) == (3, 56, 56) and K.image_bhw(f32) == (3, 56, 56)

@@ -85,6 +85,21 @@ def test_stage1_step_rng_draws_are_the_references():
     assert torch.equal(parts["x_1"], parts2["x_1"]) and torch.equal(parts["x_t"], parts2["x_t"])
 
 
+def test_step_takes_the_decoded_uint8_batch_and_gives_the_same_loss():
+    """f-4: a uint8 HWC batch through the whole step == the same batch as fp32 CHW in [0, 1], bit for bit."""
+    from genhancer_b200 import kernels as K
+    fx = load_golden("step_small.pt")
+    step, _, _ = build_step(fx["tower_cfg"], fx["flux_cfg"], fx["ae_cfg"], fx["key_shapes"], fx["seed"],
+                            fx["clip_dim"], fx["t5_dim"])
+    u8 = (fx["img"] * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().cuda()
+    draws = dict(ae_noise=fx["ae_noise"].cuda(), t=fx["t"].cuda(), x_0=fx["x_0"].cuda())
+    with torch.no_grad():
+        l_u8, p_u8 = step(u8, return_parts=True, **draws)
+        l_f32, p_f32 = step(K.u8hwc_to_f32chw(u8), return_parts=True, **draws)
+    assert torch.equal(p_u8["x_1"], p_f32["x_1"]) and torch.equal(p_u8["vec"], p_f32["vec"])
+    assert torch.equal(p_u8["pred"], p_f32["pred"]) and l_u8.item() == l_f32.item()
+
+
 def test_cfg1_full_size_step_matches_reference():
     """BASELINE.json configs[0]: OpenAI CLIP ViT-L/14-224 + the lightweight DiT, B=2, the reference ran it in fp32
     on the CPU; the B200 path runs bf16 tensor-core math.  Gates: class-token cosine >= 0.999, loss within 1e-2."""
