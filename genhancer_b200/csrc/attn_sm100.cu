@@ -513,15 +513,20 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
     const int half = threadIdx.x >> 7;  // which 32 of the 64 query columns this thread owns
     const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int64_t stat_base = (static_cast<int64_t>(b) * p.H + h) * p.Lq;
+    // Per-column statistics of a query block, staged in smem as (-lse, delta * scale) so that the inner loop is
+    // p = ex2(fma(s, c, -lse)) ; dS = p * fma(dP, scale, -delta * scale): threads 0-63 own lse, 64-127 delta.  The
+    // global loads of block i + 1 are issued BEFORE the math of block i (they used to sit, dependent, at the top of every
+    // iteration: one exposed L2 round trip per query block with a single CTA per SM to hide it).
+    auto stat_load = [&](int i) -> float {
+      const int ql = i * 64 + (row & 63);
+      if (threadIdx.x >= 128 || i >= nq || ql >= p.Lq) return 0.f;
+      return row < 64 ? -p.lse2[stat_base + ql] : p.delta[stat_base + ql] * p.scale;
+    };
+    float stat_next = stat_load(0);
     for (int i = 0; i < nq; ++i) {
-      // stage lse / delta of this query block (threads 0-63 -> lse, 64-127 -> delta)
       float* st = sStat + (i & 1) * 128;
-      if (threadIdx.x < 128) {
-        const int c = row & 63;
-        const int ql = i * 64 + c;
-        const float v = ql < p.Lq ? (row < 64 ? p.lse2[stat_base + ql] : p.delta[stat_base + ql]) : 0.f;
-        st[row] = v;
-      }
+      if (threadIdx.x < 128) st[row] = stat_next;
+      stat_next = stat_load(i + 1);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&bar_sd[i & 1], (i >> 1) & 1);
       tc_fence_after();
@@ -532,17 +537,33 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
         tmem_ld_32x32(t_lane + (i & 1) * 128 + half * 32, s);
         tmem_ld_32x32(t_lane + (i & 1) * 128 + 64 + half * 32, dp);
         tmem_ld_wait();
+        const float4* nl4 = reinterpret_cast<const float4*>(st + half * 32);        // -lse of my 32 columns (broadcast reads)
+        const float4* ds4 = reinterpret_cast<const float4*>(st + 64 + half * 32);   // delta * scale
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const int cc = half * 32 + c;
-          float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -st[cc]));
-          float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -st[cc + 1]));
-          if (cc >= q_left) p0 = 0.f;
-          if (cc + 1 >= q_left) p1 = 0.f;
-          const float d0 = p0 * (__uint_as_float(dp[c]) - st[64 + cc]) * p.scale;
-          const float d1 = p1 * (__uint_as_float(dp[c + 1]) - st[64 + cc + 1]) * p.scale;
-          pt[c >> 1] = pack_bf16x2(p0, p1);
-          dst[c >> 1] = pack_bf16x2(d0, d1);
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 nl = nl4[c4], dsc = ds4[c4];
+          const int c = c4 * 4;
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, nl.x));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, nl.y));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(s[c + 2]), p.scale_log2, nl.z));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(s[c + 3]), p.scale_log2, nl.w));
+          pt[c4 * 2] = pack_bf16x2(p0, p1);
+          pt[c4 * 2 + 1] = pack_bf16x2(p2, p3);
+          dst[c4 * 2] = pack_bf16x2(p0 * fmaf(__uint_as_float(dp[c]), p.scale, -dsc.x),
+                                    p1 * fmaf(__uint_as_float(dp[c + 1]), p.scale, -dsc.y));
+          dst[c4 * 2 + 1] = pack_bf16x2(p2 * fmaf(__uint_as_float(dp[c + 2]), p.scale, -dsc.z),
+                                        p3 * fmaf(__uint_as_float(dp[c + 3]), p.scale, -dsc.w));
+        }
+        if (q_left < 64) {   // ragged last query block only: columns past Lq contribute nothing
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const int cc = half * 32 + c;
+            if (cc + 1 >= q_left) {
+              const uint32_t keep = cc < q_left ? 0x0000ffffu : 0u;
+              pt[c >> 1] &= keep;
+              dst[c >> 1] &= keep;
+            }
+          }
         }
       }
       if (i > 0) mbar_wait(bar_acc, (i - 1) & 1);  // previous dV/dK MMAs no longer read sPT/sDST
@@ -732,8 +753,8 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int ql = q0 + row;
     const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + ql;
-    const float lse = ql < p.Lq ? p.lse2[stat] : 0.f;
-    const float dl = ql < p.Lq ? p.delta[stat] : 0.f;
+    const float nlse = ql < p.Lq ? -p.lse2[stat] : 0.f;
+    const float ndls = ql < p.Lq ? -p.delta[stat] * p.scale : 0.f;     // -delta * scale: dS = p * fma(dP, scale, -delta * scale)
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&bar_sd[j & 1], (j >> 1) & 1);
       tc_fence_after();
@@ -746,13 +767,17 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
-          const int cc = half * 32 + c;
-          float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse));
-          float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -lse));
-          if (cc >= kv_left) p0 = 0.f;
-          if (cc + 1 >= kv_left) p1 = 0.f;
-          ds[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dl) * p.scale,
-                                   p1 * (__uint_as_float(dp[c + 1]) - dl) * p.scale);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, nlse));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, nlse));
+          ds[c >> 1] = pack_bf16x2(p0 * fmaf(__uint_as_float(dp[c]), p.scale, ndls),
+                                   p1 * fmaf(__uint_as_float(dp[c + 1]), p.scale, ndls));
+        }
+        if (kv_left < 64) {   // ragged last key block only
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const int cc = half * 32 + c;
+            if (cc + 1 >= kv_left) ds[c >> 1] &= cc < kv_left ? 0x0000ffffu : 0u;
+          }
         }
       }
       if (j > 0) mbar_wait(bar_acc, (j - 1) & 1);
