@@ -115,7 +115,7 @@ def test_uint8_hwc_gathers_are_bit_identical_to_the_fp32_path():
     g = torch.Generator(device="cuda").manual_seed(3)
     u8 = torch.randint(0, 256, (3, 56, 56, 3), device="cuda", generator=g, dtype=torch.uint8)
     f32 = K.u8hwc_to_f32chw(u8)
-    assert torch.equal(f32, u8.permute(0, 3, 1, 2).float().div(255))
+    assert torch.equal(f32.cpu(), u8.cpu().permute(0, 3, 1, 2).float().div(255))   # the CPU ToTensor of the reference's loader
     mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
     a = K.patch_im2col(f32, 14, 592, mean, std)
     b = K.patch_im2col(u8, 14, 592, mean, std)
