@@ -113,6 +113,8 @@ SIGNATURES: dict[str, list] = {
     "gh_conv2d_nhwc": [C.POINTER(ConvArgs), _vp],
     "gh_patch_im2col": [_vp, _vp, _i32, _i32, _i32, _i64, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp],
     "gh_im2col3x3_c3": [_vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp],
+    "gh_patch_embed_fwd": [_vp, _i32, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, C.POINTER(C.c_float),
+                           C.POINTER(C.c_float), _vp],
     "gh_patch_im2col_u8hwc": [_vp, _vp, _i32, _i32, _i32, _i64, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp],
     "gh_im2col3x3_c3_u8hwc": [_vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp],
     "gh_embed_assemble": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],

@@ -26,8 +26,14 @@ from types import SimpleNamespace
 
 import torch
 
+import os
+
 from .. import kernels as K
 from ..kernels import ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, BF16, F32
+
+# patch-embed conv as ONE implicit-GEMM kernel (gh_patch_embed_fwd: the operand tile is gathered from the image into
+# the MMA's shared-memory layout); GH_PATCH_IMPLICIT=0 selects the older gather-to-HBM + plain GEMM pair
+IMPLICIT_PATCH_EMBED = os.environ.get("GH_PATCH_IMPLICIT", "1") != "0"
 
 
 def _alias_f32(t: torch.Tensor) -> torch.Tensor:
@@ -388,8 +394,11 @@ class TowerEngine:
         else:
             img = pixel_values.float().contiguous()
         mean, std = _norm if _norm is not None else (None, None)
-        A = K.patch_im2col(img, c.patch_size, self.patch_ld, mean, std)
-        patch = K.gemm(A, W["patch_w"], bias=W["patch_b"])
+        if IMPLICIT_PATCH_EMBED:   # image bytes -> tokens in one kernel: the im2col matrix never exists in HBM
+            patch = K.patch_embed(img, W["patch_w"], c.patch_size, bias=W["patch_b"], mean=mean, std=std)
+        else:
+            A = K.patch_im2col(img, c.patch_size, self.patch_ld, mean, std)
+            patch = K.gemm(A, W["patch_w"], bias=W["patch_b"])
         x = K.embed_assemble(patch, W["cls"], W["pos"], B, T, D)
         if c.kind == "clip":
             x, _, _ = K.layernorm_fwd(x, weight=W["pre_ln"][0], bias=W["pre_ln"][1], eps=eps, save_stats=False)

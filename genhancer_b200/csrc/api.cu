@@ -99,5 +99,6 @@ extern "C" int gh_init(int device) {
   if (int e = gemm_init()) return e;
   if (int e = attn_init()) return e;
   if (int e = conv_init()) return e;
+  if (int e = patch_embed_init()) return e;
   return GH_OK;
 }

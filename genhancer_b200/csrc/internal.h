@@ -48,5 +48,6 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int gemm_init();
 int attn_init();
 int conv_init();
+int patch_embed_init();
 
 }  // namespace gh

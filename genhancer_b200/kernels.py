@@ -438,6 +438,25 @@ def patch_im2col(img, patch, ld, mean=None, std=None):
     return buf[:, : 3 * patch * patch]
 
 
+def patch_embed(img, w, patch, bias=None, mean=None, std=None):
+    """Patch-embed conv as an implicit GEMM (gh_patch_embed_fwd): img fp32 NCHW [B,3,S,S] in [0,1] or uint8 HWC
+    [B,S,S,3]; w bf16 [D, ld] view of width 3*p*p (pad columns zero); -> bf16 [B*(S/p)^2, D]."""
+    _ensure(img)
+    u8 = is_u8_image(img)
+    assert (u8 or img.dtype == F32) and img.is_contiguous() and w.dtype == BF16 and w.stride(1) == 1
+    B, S, _ = image_bhw(img)
+    G, D = S // patch, w.shape[0]
+    out = torch.empty(B * G * G, D, dtype=BF16, device=img.device)
+    m3 = (C.c_float * 3)(*mean) if mean is not None else None
+    s3 = (C.c_float * 3)(*std) if std is not None else None
+    if bias is not None:
+        assert bias.dtype == F32 and bias.is_contiguous()
+    check(_lib.lib().gh_patch_embed_fwd(img.data_ptr(), int(u8), w.data_ptr(), w.stride(0), _p(bias), out.data_ptr(), D, B, S,
+                                        patch, D, m3, s3, _stream()))
+    _count()
+    return out
+
+
 def im2col3x3_c3(img, mean=0.0, std=1.0):
     """fp32 NCHW [B,3,H,W] or uint8 HWC [B,H,W,3] -> bf16 [B*H*W, 32] (the AE conv_in gather, normalisation fused)."""
     _ensure(img)

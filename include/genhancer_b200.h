@@ -325,6 +325,18 @@ int gh_conv2d_nhwc(const gh_conv_args* args, void* stream);
  * Feeds gh_gemm_bf16 with the flattened Conv2d weight: HF CLIPVisionEmbeddings, modeling_clip.py:147-153,208. */
 int gh_patch_im2col(const float* img, void* out_bf16, int32_t B, int32_t S, int32_t patch, int64_t ld,
                     const float* mean3, const float* std3, void* stream);
+/* Patch-embed convolution as an IMPLICIT GEMM (HF CLIPVisionEmbeddings / SiglipVisionEmbeddings.patch_embedding:
+ * Conv2d(3, D, kernel = stride = patch), modeling_clip.py:147-153,208-209), with ToTensor and transforms.Normalize of the
+ * reference's loader / step (dataset_cc3m.py:107-113, train_SigLIP_stage1.py:54-59) folded into the operand gather:
+ *   out[(b, py, px), n] = sum_{c,i,j} ((pixel[b, c, py*p+i, px*p+j] - mean[c]) / std[c]) * w[n, c*p*p + i*p + j] + bias[n]
+ * img: fp32 NCHW [B,3,S,S] in [0,1] (img_is_u8hwc = 0) or the decoded uint8 HWC [B,S,S,3] batch (1: value / 255 first).
+ * w: bf16 [D, ldw] (ldw >= 3*p*p, multiple of 8, pad columns zero); bias fp32 [D] or NULL; out bf16 [B*(S/p)^2, ldo].
+ * mean3 / std3: HOST pointers (3 floats) or NULL.  The A operand never exists in HBM: producer warps gather each
+ * 128-patch x 64-k tile straight into the swizzled shared-memory layout the tcgen05 MMA reads (a patch row is 56 bytes
+ * of fp32 / 14 of uint8 -- not a legal TMA box or stride -- so the tile cannot be a TMA view). */
+int gh_patch_embed_fwd(const void* img, int32_t img_is_u8hwc, const void* w_bf16, int64_t ldw, const float* bias,
+                       void* out_bf16, int64_t ldo, int32_t B, int32_t S, int32_t patch, int32_t D, const float* mean3,
+                       const float* std3, void* stream);
 /* The same gather straight from the DECODED image: img_u8 uint8 HWC [B,S,S,3]; every value becomes u8 / 255 (IEEE
  * division = torchvision ToTensor, image_datasets/dataset_cc3m.py:107-113) before (x-mean)/std, so the result is
  * bit-identical to gh_u8hwc_to_f32chw + gh_patch_im2col while the batch is read at 1 byte per value and no fp32 copy

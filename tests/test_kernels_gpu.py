@@ -124,3 +124,38 @@ def test_uint8_hwc_gathers_are_bit_identical_to_the_fp32_path():
     d = K.im2col3x3_c3(u8, 0.5, 0.5)
     assert c.shape == d.shape == (3 * 56 * 56, 32) and torch.equal(c, d)
     assert K.image_bhw(u8) == (3, 56, 56) and K.image_bhw(f32) == (3, 56, 56)
+
+
+@pytest.mark.parametrize("B,S,D,bias,u8", [(3, 56, 128, False, False), (2, 224, 1024, False, False), (2, 84, 1152, True, False),
+                                           (5, 42, 200, True, True), (33, 336, 1024, False, True)])
+def test_patch_embed_implicit_gemm_matches_conv2d(B, S, D, bias, u8):
+    """gh_patch_embed_fwd (north_star bullet 1: the patch-embed conv as an implicit GEMM, operand gathered from the image
+    into the MMA's smem layout, ToTensor / Normalize folded in) against torch conv2d on the same bf16-rounded operands,
+    and against the older gather + GEMM pair (same bits up to fp32 accumulation order)."""
+    import torch.nn.functional as F
+    from genhancer_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + S)
+    p = 14
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    if u8:
+        img = torch.randint(0, 256, (B, S, S, 3), device="cuda", generator=g, dtype=torch.uint8)
+        f32 = K.u8hwc_to_f32chw(img)
+    else:
+        img = torch.rand(B, 3, S, S, device="cuda", generator=g)
+        f32 = img
+    kdim, ld = 3 * p * p, (3 * p * p + 7) // 8 * 8
+    w4 = torch.randn(D, 3, p, p, device="cuda", generator=g) * 0.05
+    wk = torch.zeros(D, ld, device="cuda", dtype=torch.bfloat16)
+    wk[:, :kdim] = w4.reshape(D, kdim).to(torch.bfloat16)
+    bv = torch.randn(D, device="cuda", generator=g) if bias else None
+    out = K.patch_embed(img, wk[:, :kdim], p, bias=bv, mean=mean, std=std)
+    G = S // p
+    assert out.shape == (B * G * G, D)
+    # reference: normalise in fp32, round operands to bf16 as the kernels do, conv in fp32
+    m = torch.tensor(mean, device="cuda").view(1, 3, 1, 1)
+    s = torch.tensor(std, device="cuda").view(1, 3, 1, 1)
+    xn = ((f32 - m) * (1.0 / s)).to(torch.bfloat16).float()
+    ref = F.conv2d(xn, wk[:, :kdim].float().view(D, 3, p, p), bv, stride=p).permute(0, 2, 3, 1).reshape(B * G * G, D)
+    assert (out.float() - ref).norm() / ref.norm() < 5e-3
+    old = K.gemm(K.patch_im2col(img, p, ld, mean, std), wk[:, :kdim], bias=bv)
+    assert (out.float() - old.float()).abs().max().item() <= 2e-2 * ref.abs().max().item()
