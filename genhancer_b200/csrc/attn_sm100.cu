@@ -363,6 +363,16 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(SegOut o, SegOut dou
   if (lane == 0) delta[(static_cast<int64_t>(b) * H + h) * L + l] = acc;
 }
 
+// Backward kernels: 16 compute warps (thread = a QUARTER of a score row: 16 columns) + 1 control warp.  With one CTA per
+// SM (TMEM: 2 x (S, dP) + dV + dK = 512 columns) the element-wise part is a chain of TMEM loads, MUFU, shared-memory
+// stores and barrier round trips whose latencies only other warps can hide: the first version had 8 compute warps
+// (half a row each) and ncu showed it latency-bound on everything at once (issue slots 22 % busy, tensor pipe 29 %,
+// no single hot instruction: profiles/r02_kernels_ncu.txt).
+constexpr int ATT_BWD_SPLIT = 4;                       // threads per row
+constexpr int ATT_BWD_CPT = 64 / ATT_BWD_SPLIT;        // columns per thread
+constexpr int ATT_BWD_CW = 4 * ATT_BWD_SPLIT;          // compute warps (also the index of the control warp)
+constexpr int ATT_BWD_THREADS = 32 * (ATT_BWD_CW + 1);
+
 template <int D>
 struct AttnBwdKVCfg {
   static constexpr int KV_BYTES = 128 * D * 2;  // K_j or V_j (resident)
@@ -382,7 +392,7 @@ struct AttnBwdKVCfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                      const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                      const AttnBwdParams p) {
@@ -411,13 +421,13 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
   const int h = blockIdx.y, b = blockIdx.z;
   const int nq = (p.Lq + 63) / 64;
 
-  // warps 0..7: compute (warp w and w + 4 share TMEM lane quadrant w % 4; each thread owns HALF of its row's 64
-  // columns -- two warps per scheduler instead of one: the element-wise part was latency-bound); warp 8: control
-  if (warp == 8 && lane == 0) {
+  // warps 0..15: compute (warps w, w + 4, w + 8, w + 12 share TMEM lane quadrant w % 4; each thread owns a QUARTER of
+  // its row's 64 columns); warp 16: control
+  if (warp == ATT_BWD_CW && lane == 0) {
     mbar_init(bar_kv, 1);
     for (int i = 0; i < NQ; ++i) mbar_init(&bar_qd[i], 1);
     mbar_init(&bar_sd[0], 1); mbar_init(&bar_sd[1], 1);
-    mbar_init(bar_pd, 8);
+    mbar_init(bar_pd, ATT_BWD_CW);
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
@@ -427,7 +437,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
-  if (warp == 8) {
+  if (warp == ATT_BWD_CW) {
     {  // control warp: see flash_fwd_kernel (all lanes run the flow, one elected lane issues)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
       const uint32_t idesc_a = umma_idesc_bf16(128, p.dvalid, false, true);   // accumulators: N = the lanes that hold data
@@ -510,37 +520,41 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
     __syncwarp();
   } else {
     const int row = threadIdx.x & 127;  // key row within the block == TMEM lane
-    const int half = threadIdx.x >> 7;  // which 32 of the 64 query columns this thread owns
+    const int part = threadIdx.x >> 7;  // which 16 of the 64 query columns this thread owns
     const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int64_t stat_base = (static_cast<int64_t>(b) * p.H + h) * p.Lq;
     // Per-column statistics of a query block, staged in smem as (-lse, delta * scale) so that the inner loop is
     // p = ex2(fma(s, c, -lse)) ; dS = p * fma(dP, scale, -delta * scale): threads 0-63 own lse, 64-127 delta.  The
     // global loads of block i + 1 are issued BEFORE the math of block i (they used to sit, dependent, at the top of every
     // iteration: one exposed L2 round trip per query block with a single CTA per SM to hide it).
+    // (the loaded value is kept RAW in a register and only negated / scaled when it is stored one iteration later: a
+    // thread stalls at the first USE of a load, so doing the arithmetic at load time put the L2 round trip back at the
+    // top of every iteration -- 3 % of all stall samples on that one FMUL, plus the 256-thread barrier behind it)
     auto stat_load = [&](int i) -> float {
       const int ql = i * 64 + (row & 63);
       if (threadIdx.x >= 128 || i >= nq || ql >= p.Lq) return 0.f;
-      return row < 64 ? -p.lse2[stat_base + ql] : p.delta[stat_base + ql] * p.scale;
+      return row < 64 ? p.lse2[stat_base + ql] : p.delta[stat_base + ql];
     };
-    float stat_next = stat_load(0);
+    float stat_raw = stat_load(0);
     for (int i = 0; i < nq; ++i) {
       float* st = sStat + (i & 1) * 128;
-      if (threadIdx.x < 128) st[row] = stat_next;
-      stat_next = stat_load(i + 1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x < 128) st[row] = row < 64 ? -stat_raw : stat_raw * p.scale;
+      stat_raw = stat_load(i + 1);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * ATT_BWD_CW) : "memory");
       mbar_wait(&bar_sd[i & 1], (i >> 1) & 1);
       tc_fence_after();
       const int q_left = p.Lq - i * 64;
-      uint32_t pt[16], dst[16];
+      constexpr int CPT = ATT_BWD_CPT;
+      uint32_t pt[CPT / 2], dst[CPT / 2];
       {
-        uint32_t s[32], dp[32];
-        tmem_ld_32x32(t_lane + (i & 1) * 128 + half * 32, s);
-        tmem_ld_32x32(t_lane + (i & 1) * 128 + 64 + half * 32, dp);
+        uint32_t s[CPT], dp[CPT];
+        tmem_ld_32x16(t_lane + (i & 1) * 128 + part * CPT, s);
+        tmem_ld_32x16(t_lane + (i & 1) * 128 + 64 + part * CPT, dp);
         tmem_ld_wait();
-        const float4* nl4 = reinterpret_cast<const float4*>(st + half * 32);        // -lse of my 32 columns (broadcast reads)
-        const float4* ds4 = reinterpret_cast<const float4*>(st + 64 + half * 32);   // delta * scale
+        const float4* nl4 = reinterpret_cast<const float4*>(st + part * CPT);        // -lse of my columns (broadcast reads)
+        const float4* ds4 = reinterpret_cast<const float4*>(st + 64 + part * CPT);   // delta * scale
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
+        for (int c4 = 0; c4 < CPT / 4; ++c4) {
           const float4 nl = nl4[c4], dsc = ds4[c4];
           const int c = c4 * 4;
           const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, nl.x));
@@ -556,8 +570,8 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
         }
         if (q_left < 64) {   // ragged last query block only: columns past Lq contribute nothing
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const int cc = half * 32 + c;
+          for (int c = 0; c < CPT; c += 2) {
+            const int cc = part * CPT + c;
             if (cc + 1 >= q_left) {
               const uint32_t keep = cc < q_left ? 0x0000ffffu : 0u;
               pt[c >> 1] &= keep;
@@ -568,9 +582,9 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
       }
       if (i > 0) mbar_wait(bar_acc, (i - 1) & 1);  // previous dV/dK MMAs no longer read sPT/sDST
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        st_sw128(sPT, row, half * 4 + c, make_uint4(pt[4 * c], pt[4 * c + 1], pt[4 * c + 2], pt[4 * c + 3]));
-        st_sw128(sDST, row, half * 4 + c, make_uint4(dst[4 * c], dst[4 * c + 1], dst[4 * c + 2], dst[4 * c + 3]));
+      for (int c = 0; c < CPT / 8; ++c) {
+        st_sw128(sPT, row, part * (CPT / 8) + c, make_uint4(pt[4 * c], pt[4 * c + 1], pt[4 * c + 2], pt[4 * c + 3]));
+        st_sw128(sDST, row, part * (CPT / 8) + c, make_uint4(dst[4 * c], dst[4 * c + 1], dst[4 * c + 2], dst[4 * c + 3]));
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -585,9 +599,9 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
       bf16* dstp = which ? p.dk + b * p.dk_bs + h * p.dk_hs + static_cast<int64_t>(kl) * p.dk_rs
                          : p.dv + b * p.dv_bs + h * p.dv_hs + static_cast<int64_t>(kl) * p.dv_rs;
 #pragma unroll
-      for (int c = half; c < D / 32; c += 2) {   // the two threads of a row take alternate 32-column chunks
+      for (int c = part; c < D / 32; c += ATT_BWD_SPLIT) {   // the threads of a row take alternate 32-column chunks
         uint32_t o[32];
-        if (c * 32 < p.dvalid) {                     // (warp-uniform: half is per warp)
+        if (c * 32 < p.dvalid) {                     // (warp-uniform: part is per warp)
           tmem_ld_32x32(t_lane + (which ? Cfg::TM_DK : Cfg::TM_DV) + c * 32, o);
           tmem_ld_wait();
         }
@@ -629,7 +643,7 @@ struct AttnBwdQCfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                     const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                     const AttnBwdParams p) {
@@ -656,13 +670,13 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int h = blockIdx.y, b = blockIdx.z;
   const int nkv = (p.Lk + 63) / 64;
 
-  // warps 0..7: compute (warp w and w + 4 share TMEM lane quadrant w % 4; each thread owns HALF of its row's 64
-  // columns -- two warps per scheduler instead of one: the element-wise part was latency-bound); warp 8: control
-  if (warp == 8 && lane == 0) {
+  // warps 0..15: compute (warps w, w + 4, w + 8, w + 12 share TMEM lane quadrant w % 4; each thread owns a QUARTER of
+  // its row's 64 columns); warp 16: control
+  if (warp == ATT_BWD_CW && lane == 0) {
     mbar_init(bar_q, 1);
     for (int i = 0; i < NK; ++i) mbar_init(&bar_kv[i], 1);
     mbar_init(&bar_sd[0], 1); mbar_init(&bar_sd[1], 1);
-    mbar_init(bar_pd, 8);
+    mbar_init(bar_pd, ATT_BWD_CW);
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
@@ -672,7 +686,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
-  if (warp == 8) {
+  if (warp == ATT_BWD_CW) {
     {  // control warp: see flash_fwd_kernel (all lanes run the flow, one elected lane issues)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
       const uint32_t idesc_a = umma_idesc_bf16(128, p.dvalid, false, true);   // accumulators: N = the lanes that hold data
@@ -749,7 +763,8 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     __syncwarp();
   } else {
     const int row = threadIdx.x & 127;
-    const int half = threadIdx.x >> 7;  // which 32 of the 64 key columns this thread owns
+    const int part = threadIdx.x >> 7;  // which 16 of the 64 key columns this thread owns
+    constexpr int CPT = ATT_BWD_CPT;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int ql = q0 + row;
     const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + ql;
@@ -759,14 +774,14 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_wait(&bar_sd[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const int kv_left = p.Lk - j * 64;
-      uint32_t ds[16];
+      uint32_t ds[CPT / 2];
       {
-        uint32_t s[32], dp[32];
-        tmem_ld_32x32(t_lane + (j & 1) * 128 + half * 32, s);
-        tmem_ld_32x32(t_lane + (j & 1) * 128 + 64 + half * 32, dp);
+        uint32_t s[CPT], dp[CPT];
+        tmem_ld_32x16(t_lane + (j & 1) * 128 + part * CPT, s);
+        tmem_ld_32x16(t_lane + (j & 1) * 128 + 64 + part * CPT, dp);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
+        for (int c = 0; c < CPT; c += 2) {
           const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, nlse));
           const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, nlse));
           ds[c >> 1] = pack_bf16x2(p0 * fmaf(__uint_as_float(dp[c]), p.scale, ndls),
@@ -774,16 +789,16 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         if (kv_left < 64) {   // ragged last key block only
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const int cc = half * 32 + c;
+          for (int c = 0; c < CPT; c += 2) {
+            const int cc = part * CPT + c;
             if (cc + 1 >= kv_left) ds[c >> 1] &= cc < kv_left ? 0x0000ffffu : 0u;
           }
         }
       }
       if (j > 0) mbar_wait(bar_acc, (j - 1) & 1);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        st_sw128(sDS, row, half * 4 + c, make_uint4(ds[4 * c], ds[4 * c + 1], ds[4 * c + 2], ds[4 * c + 3]));
+      for (int c = 0; c < CPT / 8; ++c)
+        st_sw128(sDS, row, part * (CPT / 8) + c, make_uint4(ds[4 * c], ds[4 * c + 1], ds[4 * c + 2], ds[4 * c + 3]));
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -793,7 +808,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tc_fence_after();
     bf16* dstp = p.dq + b * p.dq_bs + h * p.dq_hs + static_cast<int64_t>(ql) * p.dq_rs;
 #pragma unroll
-    for (int c = half; c < D / 32; c += 2) {
+    for (int c = part; c < D / 32; c += ATT_BWD_SPLIT) {
       uint32_t o[32];
       if (c * 32 < p.dvalid) {
         tmem_ld_32x32(t_lane + Cfg::TM_DQ + c * 32, o);
@@ -954,9 +969,9 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
     if (int e = make_qkv_map(&mdo, &dot, B, H, Lq, D, 64)) return e;
     dim3 grid((Lk + 127) / 128, H, B);
     if (D == 64)
-      flash_bwd_dkv_kernel<64><<<grid, 288, AttnBwdKVCfg<64>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, p);
+      flash_bwd_dkv_kernel<64><<<grid, ATT_BWD_THREADS, AttnBwdKVCfg<64>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, p);
     else
-      flash_bwd_dkv_kernel<128><<<grid, 288, AttnBwdKVCfg<128>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, p);
+      flash_bwd_dkv_kernel<128><<<grid, ATT_BWD_THREADS, AttnBwdKVCfg<128>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, p);
     GH_CHECK_CUDA(cudaGetLastError());
   }
   {
@@ -967,9 +982,9 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
     if (int e = make_qkv_map(&mdo, &dot, B, H, Lq, D, 128)) return e;
     dim3 grid((Lq + 127) / 128, H, B);
     if (D == 64)
-      flash_bwd_dq_kernel<64><<<grid, 288, AttnBwdQCfg<64>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, p);
+      flash_bwd_dq_kernel<64><<<grid, ATT_BWD_THREADS, AttnBwdQCfg<64>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, p);
     else
-      flash_bwd_dq_kernel<128><<<grid, 288, AttnBwdQCfg<128>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, p);
+      flash_bwd_dq_kernel<128><<<grid, ATT_BWD_THREADS, AttnBwdQCfg<128>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, p);
     GH_CHECK_CUDA(cudaGetLastError());
   }
   return GH_OK;

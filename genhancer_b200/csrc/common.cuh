@@ -133,6 +133,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
+// L2 prefetch of a tensor box (no shared memory, no barrier): turns the DRAM latency of a later cp.async.bulk.tensor of
+// the same box into an L2 hit, for pipelines whose smem budget cannot hold enough stages to cover DRAM latency.
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // TMA store (smem tile -> global, clipped at the tensor's bounds) and its bulk-group bookkeeping
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

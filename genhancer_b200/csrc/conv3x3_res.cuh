@@ -114,9 +114,28 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
+    // Three 18 KB stages hold ~2300 MMA cycles of input -- enough to cover an L2 hit, not a DRAM miss (the first version
+    // ran the tensor pipe at 56 %: ncu profiles/r02_kernels_ncu.txt).  The weights leave no room for a fourth stage, so
+    // the input of the tile AFTER the next one is pulled into L2 while this tile is loaded: the two outer column
+    // shifts (kw = 0, 2) of each channel chunk cover every pixel the three shifts read.
+    auto prefetch_tile = [&](int t) {
+      if (t >= num_tiles || (p.dbg & 2)) return;     // (dbg bit 1: A/B switch GH_CONV_PREFETCH=0)
+      int cb, h0, w0;
+      patch_of(t, cb, h0, w0);
+      if (elect_one()) {
+#pragma unroll
+        for (int chunk = 0; chunk < Cfg::CHUNKS; ++chunk) {
+          tma_prefetch_l2_4d(&tmap_x, chunk * 64, w0 - 1, h0 - 1, cb);
+          tma_prefetch_l2_4d(&tmap_x, chunk * 64, w0 + 1, h0 - 1, cb);
+        }
+      }
+      __syncwarp();
+    };
+    prefetch_tile(worker + num_workers);
     for (int t = worker; t < num_tiles; t += num_workers) {
       int cb, h0, w0;
       patch_of(t, cb, h0, w0);
+      prefetch_tile(t + 2 * num_workers);
       for (int s = 0; s < Cfg::CHUNKS * 3; ++s) {
         const int chunk = s / 3, kw = s - chunk * 3;
         mbar_wait(&empty_bar[stage], phase ^ 1u);

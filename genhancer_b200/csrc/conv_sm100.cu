@@ -72,6 +72,8 @@ static int conv3x3_res_try(const gh_conv_args* a, cudaStream_t s) {
       a->Ho != a->H || a->Wo != a->W || a->act != 0 || a->y_dtype != GH_BF16 || (a->residual && a->res_dtype != GH_BF16))
     return 1;
   GemmParams p{};
+  static const int prefetch = [] { const char* e = getenv("GH_CONV_PREFETCH"); return e ? atoi(e) : 1; }();
+  p.dbg = prefetch ? 0 : 2;
   p.cv.B = a->B; p.cv.Ho = a->Ho; p.cv.Wo = a->Wo; p.cv.TW = Cfg::TW; p.cv.TH = Cfg::TH;
   p.cv.tiles_w = (a->Wo + Cfg::TW - 1) / Cfg::TW;
   p.cv.tiles_h = (a->Ho + Cfg::TH - 1) / Cfg::TH;
