@@ -74,6 +74,49 @@ struct AttnFwdCfg {
   static constexpr int CTAS_PER_SM = LEAN64 ? 3 : 2;
 };
 
+
+// ----------------------------------------------------------------------------------------------------------
+// MMA issue, cheap.  A descriptor differs from its neighbours only in the 14-bit start-address field of its LOW word,
+// so a k-loop is "low word + compile-time constant" per operand.  The first version rebuilt every descriptor from the
+// byte address (shift, two masks, or) and, with a per-k-step `if` for the valid-lane count, the compiler could not
+// group the MMAs: 14 uniform-datapath instructions + a branch sat between consecutive UTCHMMAs, ~100 cycles each, and
+// the dK/dV control warp spent ~1900 of the ~2900 cycles of a query block ISSUING its 24 MMAs (in-kernel counters,
+// tools/attn_prof.py) while the tensor pipe's math was 1024 -- the kernels were bound by one warp's instruction
+// stream.  Here every group is fully unrolled for its k-step count (a switch outside the group, no branch inside).
+//   A_CH / B_CH : byte distance between 64-wide chunks of the reduction dim (K-major operands wider than 64)
+//   A_ST / B_ST : byte step per 16-deep k-step inside a chunk (32 K-major, 2048 MN-major)
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t desc_join(uint32_t hi, uint32_t lo) { return (static_cast<uint64_t>(hi) << 32) | lo; }
+
+template <int KS, int A_CH, int A_ST, int B_CH, int B_ST>
+__device__ __forceinline__ void mma_group(uint32_t tmem_d, uint64_t a_base, uint32_t a_addr, uint64_t b_base, uint32_t b_addr,
+                                          uint32_t idesc, uint32_t acc_first) {
+  const uint32_t a_hi = static_cast<uint32_t>(a_base >> 32), b_hi = static_cast<uint32_t>(b_base >> 32);
+  const uint32_t a_lo = static_cast<uint32_t>(a_base) | ((a_addr >> 4) & 0x3FFFu);
+  const uint32_t b_lo = static_cast<uint32_t>(b_base) | ((b_addr >> 4) & 0x3FFFu);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const uint32_t ao = static_cast<uint32_t>(((ks >> 2) * A_CH + (ks & 3) * A_ST) >> 4);
+    const uint32_t bo = static_cast<uint32_t>(((ks >> 2) * B_CH + (ks & 3) * B_ST) >> 4);
+    umma_ss(tmem_d, desc_join(a_hi, a_lo + ao), desc_join(b_hi, b_lo + bo), idesc, ks == 0 ? acc_first : 1u);
+  }
+}
+// reduction over the head dim: ksteps = (valid lanes) / 16, one of {D/16, ...}; unrolled per count
+template <int D, int A_CH, int B_CH>
+__device__ __forceinline__ void mma_over_head_dim(int ksteps, uint32_t tmem_d, uint64_t kdesc, uint32_t a_addr, uint32_t b_addr,
+                                                  uint32_t idesc) {
+  switch (ksteps) {
+    case 1: mma_group<1, A_CH, 32, B_CH, 32>(tmem_d, kdesc, a_addr, kdesc, b_addr, idesc, 0u); break;
+    case 2: mma_group<2, A_CH, 32, B_CH, 32>(tmem_d, kdesc, a_addr, kdesc, b_addr, idesc, 0u); break;
+    case 3: mma_group<3, A_CH, 32, B_CH, 32>(tmem_d, kdesc, a_addr, kdesc, b_addr, idesc, 0u); break;
+    case 4: mma_group<4, A_CH, 32, B_CH, 32>(tmem_d, kdesc, a_addr, kdesc, b_addr, idesc, 0u); break;
+    case 5: if (D > 64) mma_group<5, A_CH, 32, B_CH, 32>(tmem_d, kdesc, a_addr, kdesc, b_addr, idesc, 0u); break;
+    case 6: if (D > 64) mma_group<6, A_CH, 32, B_CH, 32>(tmem_d, kdesc, a_addr, kdesc, b_addr, idesc, 0u); break;
+    case 7: if (D > 64) mma_group<7, A_CH, 32, B_CH, 32>(tmem_d, kdesc, a_addr, kdesc, b_addr, idesc, 0u); break;
+    default: if (D > 64) mma_group<8, A_CH, 32, B_CH, 32>(tmem_d, kdesc, a_addr, kdesc, b_addr, idesc, 0u); break;
+  }
+}
+
 // write 8 bf16 (16 B) of row r, logical 16-byte chunk c, into a SWIZZLE_128B K-major tile (128 B rows)
 __device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int c, uint4 v) {
   *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v;
@@ -149,13 +192,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       auto issue_s = [&](int j) {
         if (elect_one()) {
           const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + (j & 1) * Cfg::K_BYTES);
-  #pragma unroll
-          for (int c = 0; c < DC; ++c)
-  #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (c * 4 + k < ksteps)
-                umma_ss(tmem + Cfg::TM_S + (Cfg::S_BUFS == 2 ? (j & 1) * ATT_BKV : 0), umma_desc_at(kdesc, aQ + c * 16384 + k * 32),
-                        umma_desc_at(kdesc, aK + c * 8192 + k * 32), idesc_s, (c | k) != 0 ? 1u : 0u);
+          mma_over_head_dim<D, 16384, 8192>(ksteps, tmem + Cfg::TM_S + (Cfg::S_BUFS == 2 ? (j & 1) * ATT_BKV : 0), kdesc, aQ, aK,
+                                            idesc_s);
           umma_commit(&bar_s[j & 1]);
         }
       };
@@ -189,10 +227,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tc_fence_after();
         if (elect_one()) {
           const uint32_t aP = smem_u32(sP), aV = smem_u32(sV);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tmem + Cfg::TM_O, umma_desc_at(kdesc, aP + k * 32), umma_desc_at(vdesc, aV + k * 2048), idesc_o,
-                    (j | k) != 0 ? 1u : 0u);
+          mma_group<4, 0, 32, 0, 2048>(tmem + Cfg::TM_O, kdesc, aP, vdesc, aV, idesc_o, j != 0 ? 1u : 0u);
           umma_commit(bar_o);
         }
         if (j + 2 < nkv) load_k(j + 2);  // K buffer j&1 is free: S_j completed before softmax_j started
@@ -328,6 +363,11 @@ struct AttnBwdParams {
   int B, H, Lq, Lk;
   float scale, scale_log2;
   int dvalid;          // valid leading lanes of the head dim (see AttnFwdParams)
+  // bring-up aid (gh_debug_attn_prof): cycle counters of CTA (0,0,0) of the dK/dV kernel, NULL in production.
+  //   compute warp 0 / lane 0, summed over the query blocks: [0] waiting for S/dP  [1] bar.sync + TMEM loads  [2] math
+  //   [3] waiting for the previous dV/dK MMAs  [4] smem stores + fence + arrive  [5] whole loop  [6] epilogue
+  //   control warp: [8] waiting for Q/dO tiles  [9] waiting for P^T/dS^T  [10] whole loop  [11] K/V load wait
+  long long* prof;
   const float* lse2;   // [B,H,Lq]
   const float* delta;  // [B,H,Lq]
   bf16 *dq, *dk, *dv;  // element [b,h,l,:] at ptr + b*bs + h*hs + l*rs
@@ -461,20 +501,8 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
           const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
           const uint32_t aQ = smem_u32(sQ + s * Cfg::QD_BYTES), aD = smem_u32(sDO + s * Cfg::QD_BYTES);
           const uint32_t tS = tmem + (i & 1) * 128, tP = tS + 64;
-  #pragma unroll
-          for (int c = 0; c < DC; ++c)
-  #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (c * 4 + k < ksteps)
-                umma_ss(tS, umma_desc_at(kdesc, aK + c * 16384 + k * 32), umma_desc_at(kdesc, aQ + c * 8192 + k * 32),
-                        idesc_s, (c | k) != 0 ? 1u : 0u);
-  #pragma unroll
-          for (int c = 0; c < DC; ++c)
-  #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (c * 4 + k < ksteps)
-                umma_ss(tP, umma_desc_at(kdesc, aV + c * 16384 + k * 32), umma_desc_at(kdesc, aD + c * 8192 + k * 32),
-                        idesc_s, (c | k) != 0 ? 1u : 0u);
+          mma_over_head_dim<D, 16384, 8192>(ksteps, tS, kdesc, aK, aQ, idesc_s);
+          mma_over_head_dim<D, 16384, 8192>(ksteps, tP, kdesc, aV, aD, idesc_s);
           umma_commit(&bar_sd[i & 1]);
         }
       };
@@ -486,35 +514,40 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
           tma_load_4d(sV + c * 16384, &tm_v, bar_kv, c * 64, k0, h, b);
         }
       }
+      const bool prof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      long long w_qd = 0, w_pd = 0, t_kv = 0;
+      const long long c_begin = prof ? clock64() : 0;
       load_qd(0);
       if (nq > 1) load_qd(1);
       mbar_wait(bar_kv, 0);
       mbar_wait(&bar_qd[0], 0);
+      if (prof) t_kv = clock64() - c_begin;
       tc_fence_after();
       issue_sd(0);
       for (int i = 0; i < nq; ++i) {
         if (i + 1 < nq) {
+          const long long t0 = prof ? clock64() : 0;
           mbar_wait(&bar_qd[(i + 1) % NQ], ((i + 1) / NQ) & 1);
+          if (prof) w_qd += clock64() - t0;
           tc_fence_after();
           issue_sd(i + 1);
         }
+        const long long t1 = prof ? clock64() : 0;
         mbar_wait(bar_pd, i & 1);  // P^T_i, dS^T_i in smem; implies acc MMAs of i-1 have retired
+        if (prof) w_pd += clock64() - t1;
         tc_fence_after();
         if (i + 2 < nq) load_qd(i + 2);  // ring slot (i+2)%3 == (i-1)%3 is free
         if (elect_one()) {
           const int s = i % NQ;
           const uint32_t aPT = smem_u32(sPT), aDST = smem_u32(sDST);
           const uint32_t aQ = smem_u32(sQ + s * Cfg::QD_BYTES), aD = smem_u32(sDO + s * Cfg::QD_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tmem + Cfg::TM_DV, umma_desc_at(kdesc, aPT + k * 32), umma_desc_at(mdesc, aD + k * 2048), idesc_a,
-                    (i | k) != 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tmem + Cfg::TM_DK, umma_desc_at(kdesc, aDST + k * 32), umma_desc_at(mdesc, aQ + k * 2048), idesc_a,
-                    (i | k) != 0 ? 1u : 0u);
+          mma_group<4, 0, 32, 0, 2048>(tmem + Cfg::TM_DV, kdesc, aPT, mdesc, aD, idesc_a, i != 0 ? 1u : 0u);
+          mma_group<4, 0, 32, 0, 2048>(tmem + Cfg::TM_DK, kdesc, aDST, mdesc, aQ, idesc_a, i != 0 ? 1u : 0u);
           umma_commit(bar_acc);
         }
+      }
+      if (prof && lane == 0) {
+        p.prof[8] = w_qd; p.prof[9] = w_pd; p.prof[10] = clock64() - c_begin; p.prof[11] = t_kv;
       }
     }
     __syncwarp();
@@ -536,12 +569,18 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
       return row < 64 ? p.lse2[stat_base + ql] : p.delta[stat_base + ql];
     };
     float stat_raw = stat_load(0);
+    const bool prof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+    long long pw_s = 0, pw_ld = 0, pw_math = 0, pw_acc = 0, pw_st = 0;
+    const long long p_begin = prof ? clock64() : 0;
     for (int i = 0; i < nq; ++i) {
       float* st = sStat + (i & 1) * 128;
       if (threadIdx.x < 128) st[row] = row < 64 ? -stat_raw : stat_raw * p.scale;
       stat_raw = stat_load(i + 1);
+      long long tp0 = prof ? clock64() : 0;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * ATT_BWD_CW) : "memory");
+      long long tp1 = prof ? clock64() : 0;
       mbar_wait(&bar_sd[i & 1], (i >> 1) & 1);
+      if (prof) { pw_s += clock64() - tp1; pw_ld += tp1 - tp0; tp0 = clock64(); }
       tc_fence_after();
       const int q_left = p.Lq - i * 64;
       constexpr int CPT = ATT_BWD_CPT;
@@ -580,7 +619,9 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
           }
         }
       }
+      if (prof) { tp1 = clock64(); pw_math += tp1 - tp0; }
       if (i > 0) mbar_wait(bar_acc, (i - 1) & 1);  // previous dV/dK MMAs no longer read sPT/sDST
+      if (prof) { tp0 = clock64(); pw_acc += tp0 - tp1; }
 #pragma unroll
       for (int c = 0; c < CPT / 8; ++c) {
         st_sw128(sPT, row, part * (CPT / 8) + c, make_uint4(pt[4 * c], pt[4 * c + 1], pt[4 * c + 2], pt[4 * c + 3]));
@@ -590,7 +631,9 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pd);
+      if (prof) pw_st += clock64() - tp0;
     }
+    const long long p_loop = prof ? clock64() - p_begin : 0;
     mbar_wait(bar_acc, (nq - 1) & 1);
     tc_fence_after();
     const int kl = k0 + row;
@@ -619,6 +662,10 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
           }
         }
       }
+    }
+    if (prof) {
+      p.prof[0] = pw_s; p.prof[1] = pw_ld; p.prof[2] = pw_math; p.prof[3] = pw_acc; p.prof[4] = pw_st; p.prof[5] = p_loop;
+      p.prof[6] = clock64() - p_begin - p_loop; p.prof[7] = nq;
     }
   }
   tc_fence_before();
@@ -710,20 +757,8 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const uint32_t aQ = smem_u32(sQ), aD = smem_u32(sDO);
           const uint32_t aK = smem_u32(sK + s * Cfg::KV_BYTES), aV = smem_u32(sV + s * Cfg::KV_BYTES);
           const uint32_t tS = tmem + (j & 1) * 128, tP = tS + 64;
-  #pragma unroll
-          for (int c = 0; c < DC; ++c)
-  #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (c * 4 + k < ksteps)
-                umma_ss(tS, umma_desc_at(kdesc, aQ + c * 16384 + k * 32), umma_desc_at(kdesc, aK + c * 8192 + k * 32),
-                        idesc_s, (c | k) != 0 ? 1u : 0u);
-  #pragma unroll
-          for (int c = 0; c < DC; ++c)
-  #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (c * 4 + k < ksteps)
-                umma_ss(tP, umma_desc_at(kdesc, aD + c * 16384 + k * 32), umma_desc_at(kdesc, aV + c * 8192 + k * 32),
-                        idesc_s, (c | k) != 0 ? 1u : 0u);
+          mma_over_head_dim<D, 16384, 8192>(ksteps, tS, kdesc, aQ, aK, idesc_s);
+          mma_over_head_dim<D, 16384, 8192>(ksteps, tP, kdesc, aD, aV, idesc_s);
           umma_commit(&bar_sd[j & 1]);
         }
       };
@@ -752,10 +787,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (j + 2 < nkv) load_kv(j + 2);
         if (elect_one()) {
           const uint32_t aDS = smem_u32(sDS), aK = smem_u32(sK + (j % NK) * Cfg::KV_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tmem + Cfg::TM_DQ, umma_desc_at(kdesc, aDS + k * 32), umma_desc_at(mdesc, aK + k * 2048), idesc_a,
-                    (j | k) != 0 ? 1u : 0u);
+          mma_group<4, 0, 32, 0, 2048>(tmem + Cfg::TM_DQ, kdesc, aDS, mdesc, aK, idesc_a, j != 0 ? 1u : 0u);
           umma_commit(bar_acc);
         }
       }
@@ -912,6 +944,12 @@ extern "C" int64_t gh_flash_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32
   return which == 0 ? rows * D * 2 : rows * 4;
 }
 
+static long long* g_attn_prof = nullptr;
+extern "C" int gh_debug_attn_prof(void* device_buf) {
+  g_attn_prof = static_cast<long long*>(device_buf);
+  return GH_OK;
+}
+
 static void seg_from(const gh_attn_out* o, SegOut* s) {
   s->p0 = static_cast<bf16*>(o->seg0); s->bs0 = o->seg0_batch_stride; s->rs0 = o->seg0_row_stride;
   s->p1 = static_cast<bf16*>(o->seg1); s->bs1 = o->seg1_batch_stride; s->rs1 = o->seg1_row_stride;
@@ -957,6 +995,7 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.dvalid = d_valid;
+  p.prof = g_attn_prof;
   p.lse2 = lse2; p.delta = ws_delta;
   p.dq = static_cast<bf16*>(const_cast<void*>(dq->ptr)); p.dq_bs = dq->batch_stride; p.dq_hs = dq->head_stride; p.dq_rs = dq->row_stride;
   p.dk = static_cast<bf16*>(const_cast<void*>(dk->ptr)); p.dk_bs = dk->batch_stride; p.dk_hs = dk->head_stride; p.dk_rs = dk->row_stride;

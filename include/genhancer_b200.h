@@ -295,6 +295,9 @@ int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh
                       const gh_attn_out* d_o, const float* lse2, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
                       int32_t D, int32_t d_valid, float scale, const gh_attn_tensor* dq, const gh_attn_tensor* dk,
                       const gh_attn_tensor* dv, void* ws_do_headmajor, float* ws_delta, void* stream);
+/* Bring-up aid (like gh_debug_gemm_prof): a device buffer of 16 int64 that CTA (0,0,0) of the dK/dV kernel fills with
+ * cycle counters of its pipeline phases; NULL (the default) switches it off.  Process-global, not for production. */
+int gh_debug_attn_prof(void* device_buf);
 /* bytes of the two workspaces of gh_flash_attn_bwd: [0] = ws_do_headmajor, [1] = ws_delta */
 int64_t gh_flash_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t Lq, int32_t D, int32_t which);
 
