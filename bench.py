@@ -399,10 +399,17 @@ def run_ours(args):
     # under the frozen AE / tower forward of step n+1.  Per timed step: one forward, one backward, one complete
     # exchange, one optimizer update.
     pipe = None
+    GA = max(1, args.grad_accum)
+    if GA > 1 and args.no_graph:
+        raise SystemExit("--grad-accum > 1 is measured through the step graph (drop --no-graph)")
     if not args.no_graph:
         from genhancer_b200.graph import PipelinedTrainStep
-        pipe = PipelinedTrainStep(w.step, w.prep(dev_batches[0]), opt, reducer)
-        train_step = lambda x: pipe(*w.prep(x))          # noqa: E731
+        pipe = PipelinedTrainStep(w.step, w.prep(dev_batches[0]), opt, reducer, grad_accum=GA)
+
+        def train_step(x):           # one OPTIMIZER step = GA micro-batches (the reference's YAMLs use GA = 2: the gradient
+            for _ in range(GA):      # exchange and the update run once per GA micro-steps, train_SigLIP_stage1.py:238-275)
+                loss = pipe(*w.prep(x))
+            return loss
         flush = pipe.flush
     else:
         train_step = lambda x: eager_pipelined(*w.prep(x))   # noqa: E731
@@ -415,7 +422,7 @@ def run_ours(args):
     ms_value = timed(lambda i: train_step(dev_batches[i % pool]), args.steps)
     host_enqueue_ms = host["enqueue_ms"] / args.steps
     clocks.stop()
-    launches = K.LAUNCHES - n0 + ((pipe.replays - r0) * next(iter(pipe.launches_per_replay.values())) if pipe else 0)
+    launches = K.LAUNCHES - n0 + ((pipe.replays - r0) * max(pipe.launches_per_replay.values()) if pipe else 0)
 
     # ---- end-to-end arm: pinned host batch -> H2D -> step -> loss read back, every step ------------------------
     # Input pipeline of the public API as a user would drive it: the pinned batch of step i+1 is copied on a copy
@@ -439,7 +446,19 @@ def run_ours(args):
                 dst.copy_(src, non_blocking=True)
             ready[k].record(copy_stream)
 
+    def e2e_step_ga(i):
+        """GA > 1: every micro-batch is its own H2D copy (same stream, no overlap), one loss read per optimizer step."""
+        for m in range(GA):
+            for dst, src in zip(staged[0], host_batches[(i * GA + m) % pool]):
+                dst.copy_(src, non_blocking=True)
+            loss = pipe(*w.prep(staged[0]))
+        loss_host[0].copy_(loss.detach().float().reshape(()), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        last["loss"] = float(loss_host[0])
+
     def e2e_step(i):
+        if GA > 1:
+            return e2e_step_ga(i)
         k = i % 2
         if i == 0:
             stage(0)
@@ -494,22 +513,24 @@ def run_ours(args):
     _overlap, _engine.GradSink.overlap_wgrad = _engine.GradSink.overlap_wgrad, False
     _overlap_ae, _ts.OVERLAP_AE = _ts.OVERLAP_AE, False
     _overlap_cond, _engine.OVERLAP_COND = getattr(_engine, "OVERLAP_COND", False), False
-    eager_step(dev_batches[0])
     timer = GemmTimer()
-    K.GEMM_TIMER = timer
-    n_roof = min(args.steps, 3)
-    ms_roof = timed(lambda i: eager_step(dev_batches[i % pool]), n_roof)
-    K.GEMM_TIMER = None
+    n_roof = 0 if args.no_roofline else min(args.steps, 3)
+    ms_roof = 0.0
+    if n_roof:
+        eager_step(dev_batches[0])
+        K.GEMM_TIMER = timer
+        ms_roof = timed(lambda i: eager_step(dev_batches[i % pool]), n_roof)
+        K.GEMM_TIMER = None
     _engine.GradSink.overlap_wgrad = _overlap
     _ts.OVERLAP_AE = _overlap_ae
     _engine.OVERLAP_COND = _overlap_cond
     gemm_flops, gemm_ms, gemm_n = timer.summary()
     if rank == 0 and args.dump_shapes:
         os.makedirs(os.path.dirname(os.path.abspath(args.dump_shapes)), exist_ok=True)
-        json.dump({"steps": n_roof, "ms_step": ms_roof / n_roof, "rows": timer.by_shape()},
+        json.dump({"steps": n_roof, "ms_step": ms_roof / max(n_roof, 1), "rows": timer.by_shape()},
                   open(args.dump_shapes, "w"), indent=1)
 
-    samples = w.samples * world * args.steps
+    samples = w.samples * world * args.steps * GA
     value = samples / (ms_value / 1e3)
     e2e = samples / (ms_e2e / 1e3)
     peak_sust, peak_burst, prov = peaks()
@@ -525,7 +546,8 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": round(ms_value / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{cfg['what']}, batch {B}/GPU ({w.samples} samples per step and GPU), random-init weights",
-                   "name": args.config, "global_batch": w.samples * world, "image_size": S, "parallelism": f"dp{world}",
+                   "name": args.config, "global_batch": w.samples * world * GA, "gradient_accumulation_steps": GA,
+                   "image_size": S, "parallelism": f"dp{world}",
                    "execution": ("forward + backward" + (" + overlapped NCCL gradient all-reduce" if world > 1 else "")
                                  + " + clip/AdamW update replayed as ONE CUDA graph per step (the update of step n on a "
                                    "forked branch under the frozen forward of step n+1)") if pipe else "eager launches",
@@ -534,7 +556,7 @@ def run_ours(args):
         "mfu": {"flops_per_sample": flops,
                 "of_measured_sustained": round(value * flops / world / (peak_sust * 1e12), 4),
                 "of_nominal_2250": round(value * flops / world / 2250e12, 4), "peak_source": prov},
-        "e2e": {"value": round(e2e, 2), "unit": cfg["unit"], "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+        "e2e": {"value": round(e2e, 2), "unit": cfg["unit"], "h2d_bytes_per_step": h2d_bytes * GA, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last.get("loss")},
         "parity_rel": parity.get("parity_rel") if parity else None,
         "parity": parity,
@@ -549,8 +571,8 @@ def run_ours(args):
                                                              "tensor_pipe_active_pct", "sm_clock_ghz_during_capture")},
                      "launches_timed": gemm_n, "peak_source": prov,
                      "share_of_step": round(gemm_ms / ms_roof, 4) if ms_roof > 0 else None,
-                     "measured_in": f"eager single-stream pass of {n_roof} steps, {round(ms_roof / n_roof, 3)} ms/step (CUDA "
-                                    "events cannot be recorded inside the graphed step)" if pipe else "the timed steps"},
+                     "measured_in": (f"eager single-stream pass of {n_roof} steps, {round(ms_roof / max(n_roof, 1), 3)} ms/step (CUDA "
+                                     "events cannot be recorded inside the graphed step)" if n_roof else "skipped (--no-roofline)")},
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
         "cuda_graph": bool(pipe),
     }
@@ -777,10 +799,13 @@ def main():
     ap.add_argument("--config", default="img336_stage1", choices=sorted(CONFIGS),
                     help="which BASELINE.json configuration (default: configs[1], the one the headline metric is quoted on)")
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (BASELINE configs: 32)")
+    ap.add_argument("--grad-accum", type=int, default=1,
+                    help="micro-batches per optimizer step (SURVEY.md 8d cfg 3 asks for GA = 1 and the reference's GA = 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true",
                     help="skip the stock-PyTorch-on-this-GPU runs of the oracle port (SURVEY.md 8d, optional baseline)")
     ap.add_argument("--no-parity", action="store_true", help="skip the one-step comparison with the oracle port on this GPU")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the eager per-launch GEMM timing pass (multi-GPU sweeps)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
     ap.add_argument("--dump-shapes", default="", help="write the per-shape GEMM/conv timing table (JSON) here")
     ap.add_argument("--cpu-budget", type=float, default=45.0)
