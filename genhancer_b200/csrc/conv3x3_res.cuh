@@ -42,6 +42,68 @@ struct Conv3x3ResCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
+// Epilogue of one warp for one 128-channel tile: bf16 out = acc + bias [+ bf16 residual].  Same arithmetic and staging
+// as lean_tile (umma_gemm.cuh), but the residual of the WHOLE tile (2 rows x 4 slices x 16 B per lane) is requested
+// by the caller BEFORE it waits for the accumulator: the residual streams from HBM (925 MB per launch), and with the
+// one-slice-ahead prefetch of lean_tile 29 % of all warp-stall samples of this kernel sat on the first use of those
+// loads (ncu source page, profiles/r02_kernels_ncu.txt) -- four exposed DRAM round trips per tile and warp, which held
+// the tensor pipe at 56 %.
+template <bool HAS_RES>
+__device__ __forceinline__ void conv_res_tile(const EpilogueParams& ep, float* __restrict__ st, const float* __restrict__ bias_s,
+                                              uint32_t t_row, int half, int lane, int sub_row, int col8,
+                                              const int (&rows)[2], uint32_t rowmask, const uint4 (&res)[4][2]) {
+  constexpr int BN = Conv3x3ResCfg::BN;
+  constexpr int LD = GemmCfg<BN>::EPI_LD;
+  constexpr int NJ = BN / 32;
+  const bool ok0 = rowmask & 1u, ok1 = (rowmask >> 1) & 1u;
+  __nv_bfloat16* d0 = static_cast<__nv_bfloat16*>(ep.d) + static_cast<int64_t>(rows[0]) * ep.ldd + col8 + half * 16;
+  __nv_bfloat16* d1 = static_cast<__nv_bfloat16*>(ep.d) + static_cast<int64_t>(rows[1]) * ep.ldd + col8 + half * 16;
+  const float* sp0 = st + sub_row * LD + col8;
+  const float* sp1 = sp0 + 16 * LD;
+  float4* dst = reinterpret_cast<float4*>(st + lane * LD);
+  uint32_t treg[16];
+  tmem_ld_32x16(t_row + half * 16, treg);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      dst[q] = make_float4(__uint_as_float(treg[4 * q]), __uint_as_float(treg[4 * q + 1]),
+                           __uint_as_float(treg[4 * q + 2]), __uint_as_float(treg[4 * q + 3]));
+    __syncwarp();
+    if (j + 1 < NJ) tmem_ld_32x16(t_row + half * 16 + (j + 1) * 32, treg);
+    const float4 bb0 = *reinterpret_cast<const float4*>(bias_s + j * 16 + col8);
+    const float4 bb1 = *reinterpret_cast<const float4*>(bias_s + j * 16 + col8 + 4);
+    const float4 a0 = *reinterpret_cast<const float4*>(sp0), a1 = *reinterpret_cast<const float4*>(sp0 + 4);
+    const float4 c0 = *reinterpret_cast<const float4*>(sp1), c1 = *reinterpret_cast<const float4*>(sp1 + 4);
+    float v0[8] = {a0.x + bb0.x, a0.y + bb0.y, a0.z + bb0.z, a0.w + bb0.w, a1.x + bb1.x, a1.y + bb1.y, a1.z + bb1.z, a1.w + bb1.w};
+    float v1[8] = {c0.x + bb0.x, c0.y + bb0.y, c0.z + bb0.z, c0.w + bb0.w, c1.x + bb1.x, c1.y + bb1.y, c1.z + bb1.z, c1.w + bb1.w};
+    if (HAS_RES) {
+      float r[8];
+      unpack8(res[j][0], r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v0[k] += r[k];
+      unpack8(res[j][1], r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v1[k] += r[k];
+    }
+    if (ok0) {
+      uint4 o;
+      o.x = pack_bf16x2(v0[0], v0[1]); o.y = pack_bf16x2(v0[2], v0[3]);
+      o.z = pack_bf16x2(v0[4], v0[5]); o.w = pack_bf16x2(v0[6], v0[7]);
+      *reinterpret_cast<uint4*>(d0 + j * 32) = o;
+    }
+    if (ok1) {
+      uint4 o;
+      o.x = pack_bf16x2(v1[0], v1[1]); o.y = pack_bf16x2(v1[2], v1[3]);
+      o.z = pack_bf16x2(v1[4], v1[5]); o.w = pack_bf16x2(v1[6], v1[7]);
+      *reinterpret_cast<uint4*>(d1 + j * 32) = o;
+    }
+    __syncwarp();
+    if (j + 1 < NJ) tmem_ld_wait();
+  }
+}
+
 __global__ void __launch_bounds__(Conv3x3ResCfg::THREADS, 1)
 conv3x3_res_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const GemmParams p) {
@@ -231,10 +293,22 @@ conv3x3_res_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         rowmask |= static_cast<uint32_t>(ok) << it;
       }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      // the residual of the whole tile is requested now, a tile's worth of MMAs before it is used
+      uint4 res[4][2];
+      if (ep.residual) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(ep.residual) + static_cast<int64_t>(rows[it]) * ep.ld_res +
+                                    col8 + half * 16;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            res[j][it] = (rowmask >> it) & 1u ? __ldg(reinterpret_cast<const uint4*>(rp + j * 32)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      if (ep.residual) lean_tile<BN, ACT_NONE, true>(ep, st, bias_s, t_row, half, lane, sub_row, col8, 0, rows, rowmask);
-      else lean_tile<BN, ACT_NONE, false>(ep, st, bias_s, t_row, half, lane, sub_row, col8, 0, rows, rowmask);
+      if (ep.residual) conv_res_tile<true>(ep, st, bias_s, t_row, half, lane, sub_row, col8, rows, rowmask, res);
+      else conv_res_tile<false>(ep, st, bias_s, t_row, half, lane, sub_row, col8, rows, rowmask, res);
       tc_fence_before();
       if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader[acc]);
       acc ^= 1;

@@ -356,9 +356,26 @@ __device__ __forceinline__ void lean_tile(const EpilogueParams& ep, float* __res
 // ----------------------------------------------------------------------------------------------------------
 // RM = 0: no second tile; 1: + bf16 residual; 2: act_grad -- the tile is aux_in (the saved pre-activation) and the
 // result is (alpha*acc + bias) * ACT'(aux_in): the dgrad through a GELU / QuickGELU MLP (fc1's dY) on the lean path.
+// Request the second tile (residual / saved pre-activation) of 64-column group `g` into staging buffer `b`.  The bulk
+// store that last read that buffer must be done with it: `pending_ok` = how many of this thread's committed store groups
+// may still be reading (1 when the most recent store used the OTHER buffer, 0 when it used this one).
+template <int PENDING_OK>
+__device__ __forceinline__ void lean_res_request(const CUtensorMap* tmap_r, uint8_t* stg, uint64_t* res_bar2, int b, int gn, int row0) {
+  if (elect_one()) {
+    bulk_wait_group_read<PENDING_OK>();
+    mbar_arrive_expect_tx(&res_bar2[b], 4096u);
+    tma_load_2d(stg + b * 4096, tmap_r, &res_bar2[b], gn, row0);
+  }
+  __syncwarp();
+}
+
+// RM != 0: the second tile of a group is requested BEFORE the group is worked on -- the first group of an output tile by
+// the caller, ahead of its wait for the accumulator (a whole mainloop of cover), every later group at the start of the
+// group before it -- so its L2 / DRAM latency is off the epilogue's critical path (it used to be requested at the top
+// of its own group and waited for ~100 instructions later: with K = 1024 the epilogue paces the kernel).
 template <int BN, int ACT, int RM>
 __device__ __forceinline__ void lean_tile_tma(const EpilogueParams& ep, const CUtensorMap* tmap_d, const CUtensorMap* tmap_r,
-                                              uint8_t* stg, uint64_t* res_bar, uint32_t& res_phase, int& buf,
+                                              uint8_t* stg, uint64_t* res_bar2, uint32_t& res_phase, int& buf,
                                               uint32_t t_row, int half, int lane, int row0, int n0, int N,
                                               const float4 (&breg)[(BN + 255) / 256]) {
   constexpr int NG = BN / 64;
@@ -370,14 +387,13 @@ __device__ __forceinline__ void lean_tile_tma(const EpilogueParams& ep, const CU
     if (gn >= N) break;
     uint8_t* tile = stg + buf * 4096;
     uint8_t* rowp = tile + lane * 128;
-    // the bulk store that last read this buffer must be done with it (one other group may still be in flight)
-    if (elect_one()) bulk_wait_group_read<1>();
-    __syncwarp();
     if (RM != 0) {
-      if (elect_one()) {
-        mbar_arrive_expect_tx(res_bar, 4096u);
-        tma_load_2d(tile, tmap_r, res_bar, gn, row0);
-      }
+      // next group's second tile -> the other buffer (last read by the store committed just before this group)
+      if (g + 2 < NG && gn + 128 < N) lean_res_request<0>(tmap_r, stg, res_bar2, buf ^ 1, gn + 128, row0);
+    } else {
+      // the bulk store that last read this buffer must be done with it (one other group may still be in flight)
+      if (elect_one()) bulk_wait_group_read<1>();
+      __syncwarp();
     }
     uint32_t treg[16];
     tmem_ld_32x16(t_row + g * 64, treg);
@@ -413,8 +429,8 @@ __device__ __forceinline__ void lean_tile_tma(const EpilogueParams& ep, const CU
       uint4* p1 = reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ sw) << 4));
       if (RM != 0) {
         if (c == 0) {
-          mbar_wait(res_bar, res_phase);
-          res_phase ^= 1u;
+          mbar_wait(&res_bar2[buf], (res_phase >> buf) & 1u);
+          res_phase ^= 1u << buf;
         }
         float r[8];
         unpack8(*p0, r);
@@ -478,12 +494,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
-  uint64_t* res_bars = bars + 2 * STAGES + 4;   // [EPI_WARPS] residual tiles of the TMA epilogue
-  uint64_t* tq_full = bars + 2 * STAGES + 4 + Cfg::EPI_WARPS;   // [2] dynamic tile queue: entry published
+  uint64_t* res_bars = bars + 2 * STAGES + 4;   // [2 * EPI_WARPS] residual tiles of the TMA epilogue (one per staging buffer)
+  uint64_t* tq_full = bars + 2 * STAGES + 4 + 2 * Cfg::EPI_WARPS;   // [2] dynamic tile queue: entry published
   uint64_t* tq_empty = tq_full + 2;                             // [2] entry read by every consumer warp (leader's copy)
   int* tile_q = reinterpret_cast<int*>(tq_empty + 2);           // [2] tile index or -1 (no more tiles)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tile_q + 2);
-  static_assert((2 * STAGES + 4 + Cfg::EPI_WARPS + 4) * 8 + 8 + 4 <= Cfg::BAR_BYTES, "barrier block too small");
+  static_assert((2 * STAGES + 4 + 2 * Cfg::EPI_WARPS + 4) * 8 + 8 + 4 <= Cfg::BAR_BYTES, "barrier block too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -510,7 +526,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], Cfg::EPI_WARPS * (CTA2 ? 2 : 1));  // one arrive per epilogue warp (of both CTAs)
     mbar_init(&tempty_bar[1], Cfg::EPI_WARPS * (CTA2 ? 2 : 1));
-    for (int w = 0; w < Cfg::EPI_WARPS; ++w) mbar_init(&res_bars[w], 1);
+    for (int w = 0; w < 2 * Cfg::EPI_WARPS; ++w) mbar_init(&res_bars[w], 1);
     // consumers of a tile-queue entry: producer + issuer + epilogue warps of the leader, producer + epilogue warps of the peer
     mbar_init(&tq_full[0], 1);
     mbar_init(&tq_full[1], 1);
@@ -830,6 +846,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           breg[sidx] = bv;
         }
+        const int row0 = m_blk * 128 + quad * 32;
+        // second tile (residual / pre-activation) of this warp's FIRST group: requested before the accumulator is ready;
+        // the buffer it lands in was last read by the store before the most recent one (at most one may still be reading)
+        if ((ep.residual || ep.act_grad) && row0 < p.M && half < BN / 64 && n0 + half * 64 < p.N)   // (iff the loop below runs)
+          lean_res_request<1>(&tmap_r, stg, &res_bars[2 * ew], stg_buf, n0 + half * 64, row0);
         if (p.prof) {
           const long long t0 = clock64();
           mbar_wait(&tfull_bar[acc], acc_phase);
@@ -839,9 +860,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         tc_fence_after();
         const long long t_lean0 = p.prof ? clock64() : 0;
-        const int row0 = m_blk * 128 + quad * 32;
 #define GH_LEANT(A, R) \
-  lean_tile_tma<BN, A, R>(ep, &tmap_d, &tmap_r, stg, &res_bars[ew], res_phase, stg_buf, t_row, half, lane, row0, n0, p.N, breg)
+  lean_tile_tma<BN, A, R>(ep, &tmap_d, &tmap_r, stg, &res_bars[2 * ew], res_phase, stg_buf, t_row, half, lane, row0, n0, p.N, breg)
         if (row0 < p.M) {
           if (ep.act_grad) {   // (the host only routes GELU-tanh and QuickGELU here: the DiT's and the ViT's MLPs)
             if (ep.act == ACT_GELU_TANH) GH_LEANT(ACT_GELU_TANH, 2);
