@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("a2", C.c_void_p), ("lda2", C.c_int64), ("b2", C.c_void_p), ("ldb2", C.c_int64), ("K2", C.c_int32),
         ("k_splits", C.c_int32),
         ("batch", C.c_int32), ("a_batch_rows", C.c_int64), ("b_batch_rows", C.c_int64), ("d_batch_rows", C.c_int64),
+        ("dynamic_tiles", C.c_int32),
     ]
 
 
@@ -83,8 +84,6 @@ SIGNATURES: dict[str, list] = {
     "gh_last_error": [],
     "gh_version": [],
     "gh_init": [C.c_int],
-    "gh_set_sm_budget": [C.c_int],
-    "gh_set_tile_scheduler": [C.c_int],
     "gh_gemm_bf16": [C.POINTER(GemmArgs), _vp],
     "gh_debug_gemm_prof": [_vp],
     "gh_fm_interp_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _vp],

@@ -34,7 +34,7 @@ PFN_encodeTiled get_encode_tiled() {
   return g_encode;
 }
 
-static int g_sm_budget = 0;   // gh_set_sm_budget: SMs the persistent grids may fill (0 = all)
+static int g_sm_budget = 0;   // GH_SM_BUDGET in the environment (an experiment knob, DESIGN.md section 6: negative result)
 
 int num_sms() {
   if (g_num_sms == 0) {
@@ -81,11 +81,6 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 extern "C" const char* gh_last_error(void) { return gh::g_last_error.c_str(); }
 extern "C" int gh_version(void) { return 100; }
-
-extern "C" int gh_set_sm_budget(int sms) {
-  gh::g_sm_budget = sms > 0 ? sms : 0;
-  return GH_OK;
-}
 
 extern "C" int gh_init(int device) {
   using namespace gh;

@@ -7,11 +7,11 @@
 
 namespace gh {
 
-// dynamic tile schedule (gh_set_tile_scheduler): a pool of {next tile, workers done} counter pairs, one per launch in
+// dynamic tile schedule (gh_gemm_args::dynamic_tiles): a pool of {next tile, workers done} counter pairs, one per launch in
 // rotation, so launches on different streams never share a pair; a kernel hands its pair back zeroed
 static constexpr unsigned TILE_CTR_SLOTS = 1024;
 static int* g_tile_ctrs = nullptr;
-static int g_tile_dynamic = 0;
+static int g_tile_dynamic = 0;   // GH_TILE_SCHEDULER=1 in the environment: every launch dynamic (A/B runs)
 static std::atomic<unsigned> g_tile_ctr_next{0};
 
 template <int BN, bool A_MN, bool B_MN>
@@ -187,7 +187,7 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
   p.num_m_blocks = (a->M + 127) / 128;
   p.num_n_blocks = (a->N + bn - 1) / bn;
   p.num_k_blocks = (a->K + 63) / 64;
-  p.tile_ctr = (g_tile_dynamic && g_tile_ctrs) ? g_tile_ctrs + 2 * (g_tile_ctr_next.fetch_add(1) % TILE_CTR_SLOTS) : nullptr;
+  p.tile_ctr = ((a->dynamic_tiles || g_tile_dynamic) && g_tile_ctrs) ? g_tile_ctrs + 2 * (g_tile_ctr_next.fetch_add(1) % TILE_CTR_SLOTS) : nullptr;
   p.batch = batch;
   p.a_boff = static_cast<int>(a->a_batch_rows); p.b_boff = static_cast<int>(a->b_batch_rows);
   p.d_brows = static_cast<int>(a->d_batch_rows);
@@ -274,11 +274,6 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
     case 128: return dispatch_major<128>(tc.pair, amn, bmn, tm, p, s);
     default: return dispatch_major<64>(false, amn, bmn, tm, p, s);
   }
-}
-
-extern "C" int gh_set_tile_scheduler(int dynamic) {
-  gh::g_tile_dynamic = dynamic != 0;
-  return GH_OK;
 }
 
 extern "C" int gh_debug_gemm_prof(void* device_buf) {

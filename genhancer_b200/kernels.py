@@ -14,6 +14,9 @@ from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, ACT_SI
                    check)
 
 LAUNCHES = 0
+# Host-side launch policy (NOT library state): parallel.GradReducer sets it while gradient buckets are in flight, every
+# GEMM launched meanwhile asks for the dynamic tile schedule through gh_gemm_args::dynamic_tiles.
+DYNAMIC_TILES = False
 GEMM_TIMER = None  # bench.py: callable(flops) -> (start_event, stop_event) recorded around every tcgen05 GEMM/conv launch
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -107,6 +110,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         g.residual, g.ld_res, g.res_dtype = residual.data_ptr(), residual.stride(0), _dt(residual)
     if batch > 1:
         g.batch, g.a_batch_rows, g.b_batch_rows, g.d_batch_rows = batch, a_rows, b_rows, M
+    g.dynamic_tiles = int(DYNAMIC_TILES)
     g.k_splits = k_splits   # != 0: out (fp32, zeroed or to be accumulated into by the caller) += A @ B^T, split over K
     K2 = 0
     if a2 is not None:

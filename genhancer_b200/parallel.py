@@ -29,7 +29,7 @@ class GradReducer:
         self.bucket_cap_bytes = bucket_cap_bytes
         self.enabled = True          # False on gradient-accumulation micro-steps that do not synchronise
         # While buckets are in flight NCCL's kernels hold some SMs: the persistent GEMM grids switch to the dynamic
-        # tile schedule (gh_set_tile_scheduler) from the first bucket until wait(), so CTAs that start late find the
+        # tile schedule (gh_gemm_args::dynamic_tiles, a per-launch field) from the first bucket until wait(), so CTAs that start late find the
         # tile queue drained instead of owing a full static share (CUDA tensors only; the CPU tests run on gloo).
         self.dynamic_tiles = bool(groups) and groups[0].flat_g.is_cuda
         self._dyn_on = False
@@ -104,8 +104,8 @@ class GradReducer:
             self._set_dynamic(False)
 
     def _set_dynamic(self, on: bool) -> None:
-        from . import _lib
-        _lib.check(_lib.lib().gh_set_tile_scheduler(int(on)))
+        from . import kernels as K
+        K.DYNAMIC_TILES = bool(on)      # launch policy of the host wrapper; the library itself holds no such state
         self._dyn_on = on
 
     def finish(self) -> None:

@@ -40,19 +40,6 @@ const char* gh_last_error(void);
 int gh_version(void);
 /* Resolve the driver entry points, raise the kernels' dynamic-smem limits on `device`. */
 int gh_init(int device);
-/* How many SMs the persistent kernels (one CTA or CTA pair per SM) may fill; 0 = all (the default).  An experiment
- * knob: leaving a few SMs to the concurrent NCCL all-reduce kernels was measured to be WORSE than full grids (132 SMs:
- * +4 ms per step on 2 and 8 GPUs); what data-parallel training uses instead is the dynamic tile
- * schedule below.  (accelerate / DeepSpeed have no analogue: their GEMMs are not persistent.) */
-int gh_set_sm_budget(int sms);
-/* Tile schedule of the persistent tcgen05 GEMM grids launched from now on: 0 = static (tile = worker + i * #workers,
- * the default: no atomics, no start-up latency), 1 = dynamic (each CTA / CTA pair pulls its next tile from a global
- * counter through a 2-deep queue in shared memory).  Data-parallel training switches to dynamic for the backward,
- * during which NCCL's all-reduce kernels hold some SMs: CTAs of a persistent grid that start a wave late then find the
- * queue drained instead of owing a full static share of the tiles (which doubled the GEMM's duration).  Results are
- * identical (each tile is computed by exactly one worker; only the assignment changes). */
-int gh_set_tile_scheduler(int dynamic);
-
 /* --------------------------------------------------------------------------
  * gh_gemm_bf16 -- tcgen05/TMEM GEMM fed by TMA, fused epilogue.
  *   acc[m,n] = alpha * sum_k A(m,k) * B(n,k)                    (bf16 x bf16 -> fp32)
@@ -124,6 +111,14 @@ typedef struct {
    * No second operand pair, split-K or gate.  batch <= 1: plain GEMM. */
   int32_t batch;
   int64_t a_batch_rows, b_batch_rows, d_batch_rows;
+  /* Tile schedule of THIS launch's persistent grid: 0 = static (tile = worker + i * #workers: no atomics, no start-up
+   * latency), 1 = dynamic (each CTA / CTA pair pulls its next tile from a global counter through a 2-deep queue in
+   * shared memory).  Data-parallel training asks for dynamic while gradient buckets are in flight: NCCL's all-reduce
+   * kernels hold some SMs, and CTAs of a persistent grid that start a wave late then find the queue drained instead of
+   * owing a full static share of the tiles (which doubled the GEMM's duration).  Results are
+   * identical (each tile is computed by exactly one worker).  A per-call field, not library state: the policy lives in
+   * the host (parallel.GradReducer), the library stays re-entrant across streams. */
+  int32_t dynamic_tiles;
 } gh_gemm_args;
 int gh_gemm_bf16(const gh_gemm_args* args, void* stream);
 /* Bring-up aid: when device_buf (int64 [8 * #SMs]) is non-NULL, every following gh_gemm_bf16 launch writes per-CTA

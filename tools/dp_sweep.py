@@ -24,7 +24,7 @@ import bench  # noqa: E402
 
 
 def main():
-    from genhancer_b200 import _lib, optim
+    from genhancer_b200 import _lib, kernels as K, optim
     from genhancer_b200.parallel import GradReducer, broadcast_parameters
 
     world, rank, local = (int(os.environ[k]) for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"))
@@ -58,9 +58,9 @@ def main():
         reducer = GradReducer(groups, engine_modules=[dit], process_group=pg, bucket_cap_bytes=bucket_mb << 20)
         reducer.enabled = comm
         reducer.dynamic_tiles = dyn == 1      # 1: dynamic tile schedule while buckets are in flight; 2: always; 0: never
-        L.gh_set_tile_scheduler(1 if dyn == 2 else 0)
+        K.DYNAMIC_TILES = dyn == 2
         gscale = 1.0 / world
-        L.gh_set_sm_budget(budget)
+        os.environ["GH_SM_BUDGET"] = str(budget)   # (read once per process: the sweep over budgets needs fresh processes)
         pend = {"n": 0}
 
         def flush():
@@ -111,8 +111,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         lo = torch.tensor([mine], device=dev)
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        L.gh_set_sm_budget(0)
-        L.gh_set_tile_scheduler(0)
+        K.DYNAMIC_TILES = False
         dit._on_grads_ready = None
         if graph:           # a graph keeps its own ~35 GB activation pool: release it before the next configuration
             graphs.remove(gm)

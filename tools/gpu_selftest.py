@@ -298,9 +298,8 @@ def main():
     if "batched" in which:
         batched_cases()
     if "dyn" in which:
-        # dynamic tile schedule (gh_set_tile_scheduler): same results, counters hand themselves back zeroed (repeat)
-        from genhancer_b200 import _lib
-        _lib.lib().gh_set_tile_scheduler(1)
+        # dynamic tile schedule (gh_gemm_args::dynamic_tiles): same results, counters hand themselves back zeroed (repeat)
+        K.DYNAMIC_TILES = True
         try:
             for rep in range(3):
                 gemm_case(3000, 3072, 1024)                          # CTA pairs, several tiles per pair
@@ -311,7 +310,7 @@ def main():
                 gemm_case(300, 512, 256, bias=True, gate=100, residual=True)
             batched_cases()
         finally:
-            _lib.lib().gh_set_tile_scheduler(0)
+            K.DYNAMIC_TILES = False
         gemm_case(3000, 3072, 1024)
     if "time" in which:
         time_gemm(4096, 4096, 4096)
