@@ -44,9 +44,15 @@ def test_flux_forward_backward_matches_reference(name):
     assert cosine(txt.grad, fx["d_txt"]) > min(0.99, floor["d_txt"] - 0.01)
     assert cosine(y.grad, fx["d_y"]) > min(0.99, floor["d_y"] - 0.01)
     params = dict(dit.named_parameters())
+    below = {}
     for k, g in fx["grads"].items():
         assert params[k].grad is not None, k
-        assert cosine(params[k].grad, g) > min(0.99, floor[k] - 0.01), (k, cosine(params[k].grad, g), floor[k])
+        c = cosine(params[k].grad, g)
+        if c < 0.99 or floor[k] < 0.99:
+            below[k] = (round(c, 4), round(float(floor[k]), 4))
+        assert c > min(0.99, floor[k] - 0.01), (k, c, floor[k])
+    # evidence for the gate: every tensor where we OR the reference's own bf16 run sit below 0.99 against the fp32 gradients
+    print(f"GRADCOS {name}: {len(fx['grads'])} tensors, (ours, reference-bf16 floor) where either is < 0.99: {below}")
 
 
 def test_flux_error_behaviour():

@@ -8,6 +8,9 @@ from conftest import cosine, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
+# per-tensor gradient cosine >= 0.99 against the reference's fp32 gradients (the printed values are the
+# evidence: `pytest -s -k ...` shows them)
+GRAD_COS = 0.99
 OPENAI_MEAN = (0.48145466, 0.4578275, 0.40821073)
 OPENAI_STD = (0.26862954, 0.26130258, 0.27577711)
 
@@ -60,9 +63,11 @@ def test_stage1_step_small_matches_reference():
     assert abs(loss.item() - fx["loss"].item()) / fx["loss"].item() < 1e-2     # north_star tolerance
     loss.backward()
     P = dict(dit.named_parameters())
-    assert cosine(P["txt_in.weight"].grad, fx["grad_txt_in_weight"]) > 0.98
-    assert cosine(P["final_layer.linear.weight"].grad, fx["grad_final_linear_weight"]) > 0.99
-    assert cosine(wrap.project_t5[3].weight.grad, fx["grad_project_t5_3_weight"]) > 0.98
+    cs = dict(txt_in=cosine(P["txt_in.weight"].grad, fx["grad_txt_in_weight"]),
+              final=cosine(P["final_layer.linear.weight"].grad, fx["grad_final_linear_weight"]),
+              t5=cosine(wrap.project_t5[3].weight.grad, fx["grad_project_t5_3_weight"]))
+    print("GRADCOS step_small", cs)
+    assert min(cs.values()) >= GRAD_COS, cs
 
 
 def test_stage1_step_rng_draws_are_the_references():
@@ -120,8 +125,10 @@ def test_cfg1_full_size_step_matches_reference():
     assert cosine(parts["pred"], fx["pred"]) > 0.995
     loss.backward()
     P = dict(dit.named_parameters())
-    assert cosine(P["final_layer.linear.weight"].grad, fx["grad_final_linear_weight"]) > 0.99
-    assert cosine(P["img_in.weight"].grad, fx["grad_img_in_weight"]) > 0.95
+    cs = dict(final=cosine(P["final_layer.linear.weight"].grad, fx["grad_final_linear_weight"]),
+              img_in=cosine(P["img_in.weight"].grad, fx["grad_img_in_weight"]))
+    print("GRADCOS cfg1_full", cs)
+    assert min(cs.values()) >= GRAD_COS, cs
     gn = wrap.project_t5[1].weight.grad.float().norm().item()
     assert abs(gn - fx["grad_norm_project_t5_1_weight"].item()) / fx["grad_norm_project_t5_1_weight"].item() < 0.1
 
@@ -185,5 +192,7 @@ def test_stage2_step_small_lora_gradients_match_oracle():
     for wkey, (A, B, _) in lo_o.items():
         pair = wrap.model.lora[wkey[:-len(".weight")].replace(".", "/")]
         worst = min(worst, cosine(pair.A.grad, A.grad), cosine(pair.B.grad, B.grad))
-    assert worst >= 0.97, worst
-    assert cosine(dict(wrap.model.named_parameters())[bkey].grad, sd_t[bkey].grad) >= 0.98
+    cb = cosine(dict(wrap.model.named_parameters())[bkey].grad, sd_t[bkey].grad)
+    print("GRADCOS stage2 whole-step worst LoRA", worst, "bias", cb)
+    assert worst >= GRAD_COS, worst
+    assert cb >= GRAD_COS

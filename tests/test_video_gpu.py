@@ -60,9 +60,11 @@ def test_video_step_matches_reference():
     assert rel_err(parts["pred"], fx["pred"]) < 5e-2
     assert abs(loss.item() - fx["loss"].item()) / fx["loss"].item() < 1e-2
     loss.backward()
-    assert cosine(sm.visual_adapter.proj[2].weight.grad, fx["grad_adapter_proj2_weight"]) > 0.98
-    assert cosine(sm.visual_adapter.proj[3].bias.grad, fx["grad_adapter_proj3_bias"]) > 0.98
-    assert cosine(dict(sm.dit.named_parameters())["txt_in.weight"].grad, fx["grad_txt_in_weight"]) > 0.98
+    cs = dict(proj2=cosine(sm.visual_adapter.proj[2].weight.grad, fx["grad_adapter_proj2_weight"]),
+              proj3_bias=cosine(sm.visual_adapter.proj[3].bias.grad, fx["grad_adapter_proj3_bias"]),
+              txt_in=cosine(dict(sm.dit.named_parameters())["txt_in.weight"].grad, fx["grad_txt_in_weight"]))
+    print("GRADCOS video_step_small", cs)
+    assert min(cs.values()) >= 0.99, cs          # per-tensor gradient cosine >= 0.99
 
 
 def test_video_step_argument_checks_and_adapter_keys():
