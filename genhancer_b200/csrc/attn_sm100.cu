@@ -866,6 +866,10 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+}  // namespace gh
+#include "attn_bwd2.cuh"
+namespace gh {
+
 // 4-D map over [b, h, l, d] with arbitrary (16-byte multiple) strides; box = 64 x box_rows x 1 x 1
 static int make_qkv_map(CUtensorMap* m, const gh_attn_tensor* t, int B, int H, int L, int D, int box_rows) {
   const uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(L), static_cast<uint64_t>(H),
@@ -894,6 +898,14 @@ int attn_init() {
                                      AttnBwdQCfg<64>::SMEM_BYTES));
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnBwdQCfg<128>::SMEM_BYTES));
+  GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AttnBwdKV2Cfg<64>::SMEM_BYTES));
+  GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AttnBwdKV2Cfg<128>::SMEM_BYTES));
+  GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dq2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AttnBwdQ2Cfg<64>::SMEM_BYTES));
+  GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dq2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AttnBwdQ2Cfg<128>::SMEM_BYTES));
   return GH_OK;
 }
 
@@ -1000,6 +1012,29 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
   p.dq = static_cast<bf16*>(const_cast<void*>(dq->ptr)); p.dq_bs = dq->batch_stride; p.dq_hs = dq->head_stride; p.dq_rs = dq->row_stride;
   p.dk = static_cast<bf16*>(const_cast<void*>(dk->ptr)); p.dk_bs = dk->batch_stride; p.dk_hs = dk->head_stride; p.dk_rs = dk->row_stride;
   p.dv = static_cast<bf16*>(const_cast<void*>(dv->ptr)); p.dv_bs = dv->batch_stride; p.dv_hs = dv->head_stride; p.dv_rs = dv->row_stride;
+#ifndef GH_ATTN_BWD_V1   // (A/B builds, tools/build_ab.sh: the first form -- 128 x 64 tiles, every operand in shared memory)
+  {
+    CUtensorMap mk_, mv, mq, mdo;   // every tile of the second form is 128 rows x 64 lanes x D / 64 boxes
+    if (int e = make_qkv_map(&mk_, k, B, H, Lk, D, 128)) return e;
+    if (int e = make_qkv_map(&mv, v, B, H, Lk, D, 128)) return e;
+    if (int e = make_qkv_map(&mq, q, B, H, Lq, D, 128)) return e;
+    if (int e = make_qkv_map(&mdo, &dot, B, H, Lq, D, 128)) return e;
+    CUtensorMap mdq, mdk, mdv;      // outputs: bulk tensor stores of [128 rows x 64 lanes] tiles, clipped at the sequence end
+    if (int e = make_qkv_map(&mdq, dq, B, H, Lq, D, 128)) return e;
+    if (int e = make_qkv_map(&mdk, dk, B, H, Lk, D, 128)) return e;
+    if (int e = make_qkv_map(&mdv, dv, B, H, Lk, D, 128)) return e;
+    const dim3 grid_kv((Lk + 127) / 128, H, B), grid_q((Lq + 127) / 128, H, B);
+    if (D == 64) {
+      flash_bwd_dkv2_kernel<64><<<grid_kv, ATT_BWD2_THREADS, AttnBwdKV2Cfg<64>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, mdk, mdv, p);
+      flash_bwd_dq2_kernel<64><<<grid_q, ATT_BWD2_THREADS, AttnBwdQ2Cfg<64>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, mdq, p);
+    } else {
+      flash_bwd_dkv2_kernel<128><<<grid_kv, ATT_BWD2_THREADS, AttnBwdKV2Cfg<128>::SMEM_BYTES, s>>>(mk_, mv, mq, mdo, mdk, mdv, p);
+      flash_bwd_dq2_kernel<128><<<grid_q, ATT_BWD2_THREADS, AttnBwdQ2Cfg<128>::SMEM_BYTES, s>>>(mq, mdo, mk_, mv, mdq, p);
+    }
+    GH_CHECK_CUDA(cudaGetLastError());
+    return GH_OK;
+  }
+#endif
   {
     CUtensorMap mk_, mv, mq, mdo;
     if (int e = make_qkv_map(&mk_, k, B, H, Lk, D, 128)) return e;
