@@ -39,28 +39,31 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 
-// D[tmem] (+)= A[tmem, packed as described above] * B[smem, MN-major, 2048 B per k-step]
-template <int KS>
+// D[tmem] (+)= A[tmem, packed as described above] * B[smem, MN-major, 2048 B per k-step].  SPAN = fp32 columns a compute
+// thread owns (32 in the backward kernels, 64 in the forward): its SPAN / 2 packed columns start at the span's first column.
+template <int KS, int SPAN>
 __device__ __forceinline__ void mma_group_ts(uint32_t tmem_d, uint32_t a_tmem, uint64_t b_base, uint32_t b_addr, uint32_t idesc,
                                              uint32_t acc_first) {
+  constexpr int KPS = SPAN / 16;   // k-steps per span
   const uint32_t b_hi = static_cast<uint32_t>(b_base >> 32);
   const uint32_t b_lo = static_cast<uint32_t>(b_base) | ((b_addr >> 4) & 0x3FFFu);
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks)
-    umma_ts(tmem_d, a_tmem + 32u * (ks >> 1) + 8u * (ks & 1), desc_join(b_hi, b_lo + static_cast<uint32_t>(ks * (2048 >> 4))), idesc,
-            ks == 0 ? acc_first : 1u);
+    umma_ts(tmem_d, a_tmem + static_cast<uint32_t>(SPAN * (ks / KPS) + 8 * (ks % KPS)),
+            desc_join(b_hi, b_lo + static_cast<uint32_t>(ks * (2048 >> 4))), idesc, ks == 0 ? acc_first : 1u);
 }
+template <int SPAN = 32>
 __device__ __forceinline__ void mma_ts_ksteps(int ksteps, uint32_t tmem_d, uint32_t a_tmem, uint64_t b_base, uint32_t b_addr,
                                               uint32_t idesc, uint32_t acc_first) {
   switch (ksteps) {
-    case 1: mma_group_ts<1>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
-    case 2: mma_group_ts<2>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
-    case 3: mma_group_ts<3>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
-    case 4: mma_group_ts<4>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
-    case 5: mma_group_ts<5>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
-    case 6: mma_group_ts<6>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
-    case 7: mma_group_ts<7>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
-    default: mma_group_ts<8>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
+    case 1: mma_group_ts<1, SPAN>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
+    case 2: mma_group_ts<2, SPAN>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
+    case 3: mma_group_ts<3, SPAN>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
+    case 4: mma_group_ts<4, SPAN>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
+    case 5: mma_group_ts<5, SPAN>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
+    case 6: mma_group_ts<6, SPAN>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
+    case 7: mma_group_ts<7, SPAN>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
+    default: mma_group_ts<8, SPAN>(tmem_d, a_tmem, b_base, b_addr, idesc, acc_first); break;
   }
 }
 

@@ -868,6 +868,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
 }  // namespace gh
 #include "attn_bwd2.cuh"
+#include "attn_fwd2.cuh"
 namespace gh {
 
 // 4-D map over [b, h, l, d] with arbitrary (16-byte multiple) strides; box = 64 x box_rows x 1 x 1
@@ -898,6 +899,10 @@ int attn_init() {
                                      AttnBwdQCfg<64>::SMEM_BYTES));
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnBwdQCfg<128>::SMEM_BYTES));
+  GH_CHECK_CUDA(cudaFuncSetAttribute(flash_fwd2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AttnFwd2Cfg<64>::SMEM_BYTES));
+  GH_CHECK_CUDA(cudaFuncSetAttribute(flash_fwd2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AttnFwd2Cfg<128>::SMEM_BYTES));
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnBwdKV2Cfg<64>::SMEM_BYTES));
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -929,10 +934,15 @@ extern "C" int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* 
   GH_REQUIRE(o->seg1_row_stride % 8 == 0 && o->seg1_batch_stride % 8 == 0 && aligned16(o->seg1) &&
                  (o->n_split == 0 || (o->seg0_row_stride % 8 == 0 && o->seg0_batch_stride % 8 == 0 && aligned16(o->seg0))),
              GH_ERR_ALIGN, "gh_flash_attn_fwd: output strides must be multiples of 8 elements");
+#ifdef GH_ATTN_FWD_V2    // (A/B builds, tools/build_ab.sh: attn_fwd2.cuh -- 128-key blocks, P through TMEM; measured no faster)
+  constexpr int kv_box = 128;
+#else
+  constexpr int kv_box = ATT_BKV;
+#endif
   CUtensorMap mq, mk_, mv;
   if (int e = make_qkv_map(&mq, q, B, H, Lq, D, ATT_BQ)) return e;
-  if (int e = make_qkv_map(&mk_, k, B, H, Lk, D, ATT_BKV)) return e;
-  if (int e = make_qkv_map(&mv, v, B, H, Lk, D, ATT_BKV)) return e;
+  if (int e = make_qkv_map(&mk_, k, B, H, Lk, D, kv_box)) return e;
+  if (int e = make_qkv_map(&mv, v, B, H, Lk, D, kv_box)) return e;
   AttnFwdParams p{};
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
@@ -943,10 +953,17 @@ extern "C" int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* 
   p.lse2 = lse2;
   dim3 grid((Lq + ATT_BQ - 1) / ATT_BQ, H, B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+#ifdef GH_ATTN_FWD_V2
+  if (D == 64)
+    flash_fwd2_kernel<64><<<grid, ATT_FWD2_THREADS, AttnFwd2Cfg<64>::SMEM_BYTES, s>>>(mq, mk_, mv, p);
+  else
+    flash_fwd2_kernel<128><<<grid, ATT_FWD2_THREADS, AttnFwd2Cfg<128>::SMEM_BYTES, s>>>(mq, mk_, mv, p);
+#else
   if (D == 64)
     flash_fwd_kernel<64><<<grid, 160, AttnFwdCfg<64>::SMEM_BYTES, s>>>(mq, mk_, mv, p);
   else
     flash_fwd_kernel<128><<<grid, 160, AttnFwdCfg<128>::SMEM_BYTES, s>>>(mq, mk_, mv, p);
+#endif
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
 }
