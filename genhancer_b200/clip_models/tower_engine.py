@@ -64,9 +64,19 @@ class LinGroup:
         self.train_bias = [m.bias is not None and m.bias.requires_grad for m in mods]
         self.w = torch.zeros(self.N, self.K, dtype=BF16, device=dev)
         self.bias = torch.zeros(self.N, dtype=F32, device=dev) if self.has_bias else None
-        self.A = torch.zeros(self.R, self.K, dtype=BF16, device=dev) if self.R else None
+        # Trainable biases of a LoRA-wrapped group: db = colsum(dy) = dy^T 1 rides in the dB = dy^T u GEMM as one more column.
+        # u gets RX extra columns, the first of them a constant one (the u GEMM's "bias" on a zero row of A), so the wgrad
+        # GEMM's output is [dB | db | 0]: no separate pass over dy (it was 145 column-sum launches, 7.4 ms of the SigLIP
+        # stage-2 step).  An MMA with N = 32 costs what N = 16 costs.
+        self.RX = 16 if (self.R and any(self.train_bias)) else 0
+        self.A_ext = torch.zeros(self.R + self.RX, self.K, dtype=BF16, device=dev) if self.R else None
+        self.A = self.A_ext[:self.R] if self.R else None
+        self.u_bias = None
+        if self.RX:
+            self.u_bias = torch.zeros(self.R + self.RX, dtype=F32, device=dev)
+            self.u_bias[self.R] = 1.0
         self.Bm = torch.zeros(self.N, self.R, dtype=BF16, device=dev) if self.R else None
-        self.gA = self.gB = self.gb = None  # fp32 gradient staging, carved out of the engine's flat buffer
+        self.gA = self.gB = self.gb = self.gBx = None  # fp32 gradient staging, carved out of the engine's flat buffer
 
     # ---- slot mapping helpers -----------------------------------------------------------------------------
     def _rg(self):
@@ -101,8 +111,8 @@ class LinGroup:
     def staging_numel(self) -> int:
         n = 0
         if self.R:
-            n += self.R * self.K + self.N * self.R
-        if any(self.train_bias):
+            n += self.R * self.K + self.N * (self.R + self.RX)
+        if any(self.train_bias) and not self.RX:
             n += self.N
         return (n + 63) // 64 * 64
 
@@ -111,9 +121,12 @@ class LinGroup:
         if self.R:
             self.gA = flat[o:o + self.R * self.K].view(self.R, self.K)
             o += self.R * self.K
-            self.gB = flat[o:o + self.N * self.R].view(self.N, self.R)
-            o += self.N * self.R
-        if any(self.train_bias):
+            self.gBx = flat[o:o + self.N * (self.R + self.RX)].view(self.N, self.R + self.RX)   # [dB | db | 0]
+            self.gB = self.gBx[:, :self.R]
+            o += self.N * (self.R + self.RX)
+        if self.RX:
+            self.gb = self.gBx[:, self.R]
+        elif any(self.train_bias):
             self.gb = flat[o:o + self.N]
 
     def fill_scatter(self, tab: K.CopyTable) -> None:
@@ -149,8 +162,8 @@ class LinGroup:
         xd = None
         if drop is not None:
             xd = K.dropout_fwd(x2d.contiguous(), *drop)
-        u = K.gemm(x2d if xd is None else xd, self.A, alpha=self.s)
-        return K.gemm(x2d, self.w, bias=self.bias, a2=u, b2=self.Bm, **epi), (u, xd, drop)
+        ux = K.gemm(x2d if xd is None else xd, self.A_ext, alpha=self.s, bias=self.u_bias)   # [s x A^T | 1 | 0]
+        return K.gemm(x2d, self.w, bias=self.bias, a2=ux[:, :self.R], b2=self.Bm, **epi), (ux, xd, drop)
 
     def bwd(self, dy2d, x2d, saved, need_dx=True, **dx_epi):
         """dx (or None).  Parameter gradients go to the fp32 staging (the engine scatters them once per backward)."""
@@ -171,10 +184,10 @@ class LinGroup:
             # skinny outputs reduced over every token of the batch: split-K, partial products added into the staging
             # (which is all-zero between backward calls, see TowerEngine._scatter_grads)
             K.gemm(du, x2d if xd is None else xd, a_mn=True, b_mn=True, out=self.gA, k_splits=-1)
-            K.gemm(dy2d, u, a_mn=True, b_mn=True, out=self.gB, k_splits=-1)
+            K.gemm(dy2d, u, a_mn=True, b_mn=True, out=self.gBx, k_splits=-1)   # [dB | db | 0]
         elif need_dx:
             dx = K.gemm(dy2d, self.w, b_mn=True, **dx_epi)
-        if self.gb is not None:
+        if self.gb is not None and not self.RX:
             K.colsum(dy2d, self.gb)
         return dx
 

@@ -387,9 +387,14 @@ __device__ __forceinline__ void lean_tile_tma(const EpilogueParams& ep, const CU
     if (gn >= N) break;
     uint8_t* tile = stg + buf * 4096;
     uint8_t* rowp = tile + lane * 128;
-    if (RM != 0) {
+    if (RM == 1 || RM == 2) {
       // next group's second tile -> the other buffer (last read by the store committed just before this group)
       if (g + 2 < NG && gn + 128 < N) lean_res_request<0>(tmap_r, stg, res_bar2, buf ^ 1, gn + 128, row0);
+    } else if (RM == 3) {
+      // RM == 3 (aux_out): BOTH buffers are written below -- the activated tile and the pre-activation tile an MLP's
+      // backward needs -- and leave by two bulk stores; the pair committed for the previous group must be done reading
+      if (elect_one()) bulk_wait_group_read<0>();
+      __syncwarp();
     } else {
       // the bulk store that last read this buffer must be done with it (one other group may still be in flight)
       if (elect_one()) bulk_wait_group_read<1>();
@@ -421,13 +426,23 @@ __device__ __forceinline__ void lean_tile_tma(const EpilogueParams& ep, const CU
         v1[k] = fmaf(__uint_as_float(treg[8 + k]), alpha, b[8 + k]);
       }
       if (c + 1 < 4) tmem_ld_32x16(t_row + g * 64 + (c + 1) * 16, treg);   // next chunk in flight during the math
+      if (RM == 3) {
+        uint8_t* rowa = stg + (buf ^ 1) * 4096 + lane * 128;
+        uint4 o;
+        o.x = pack_bf16x2(v0[0], v0[1]); o.y = pack_bf16x2(v0[2], v0[3]);
+        o.z = pack_bf16x2(v0[4], v0[5]); o.w = pack_bf16x2(v0[6], v0[7]);
+        *reinterpret_cast<uint4*>(rowa + (((2 * c) ^ sw) << 4)) = o;
+        o.x = pack_bf16x2(v1[0], v1[1]); o.y = pack_bf16x2(v1[2], v1[3]);
+        o.z = pack_bf16x2(v1[4], v1[5]); o.w = pack_bf16x2(v1[6], v1[7]);
+        *reinterpret_cast<uint4*>(rowa + (((2 * c + 1) ^ sw) << 4)) = o;
+      }
       if (ACT != ACT_NONE && RM != 2) {
         act_fwd8(ACT, v0);
         act_fwd8(ACT, v1);
       }
       uint4* p0 = reinterpret_cast<uint4*>(rowp + (((2 * c) ^ sw) << 4));
       uint4* p1 = reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ sw) << 4));
-      if (RM != 0) {
+      if (RM == 1 || RM == 2) {
         if (c == 0) {
           mbar_wait(&res_bar2[buf], (res_phase >> buf) & 1u);
           res_phase ^= 1u << buf;
@@ -460,6 +475,7 @@ __device__ __forceinline__ void lean_tile_tma(const EpilogueParams& ep, const CU
     __syncwarp();
     if (elect_one()) {
       tma_store_2d(tmap_d, tile, gn, row0);
+      if (RM == 3) tma_store_2d(tmap_r, stg + (buf ^ 1) * 4096, gn, row0);
       bulk_commit_group();
     }
     buf ^= 1;
@@ -866,6 +882,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (ep.act_grad) {   // (the host only routes GELU-tanh and QuickGELU here: the DiT's and the ViT's MLPs)
             if (ep.act == ACT_GELU_TANH) GH_LEANT(ACT_GELU_TANH, 2);
             else GH_LEANT(ACT_QUICK_GELU, 2);
+          } else if (ep.aux_out) {   // forward of an MLP's fc1: act(pre) AND pre leave through the lean path
+            switch (ep.act) {
+              case ACT_GELU_TANH: GH_LEANT(ACT_GELU_TANH, 3); break;
+              case ACT_QUICK_GELU: GH_LEANT(ACT_QUICK_GELU, 3); break;
+              case ACT_SILU: GH_LEANT(ACT_SILU, 3); break;
+              default: GH_LEANT(ACT_GELU_ERF, 3); break;
+            }
           } else if (ep.residual) {
             switch (ep.act) {
               case ACT_GELU_TANH: GH_LEANT(ACT_GELU_TANH, 1); break;
