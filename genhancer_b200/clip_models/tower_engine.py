@@ -160,6 +160,10 @@ class LinGroup:
         if not self.R:
             return K.gemm(x2d, self.w, bias=self.bias, **epi), None
         xd = None
+        if drop is not None and self.R in (16, 32, 48) and self.K % 8 == 0:
+            # the mask sits between x and A: dropout and the skinny product in ONE pass over x (csrc/lora_fused.cu)
+            xd, ux = K.lora_dropout_fwd(x2d.contiguous(), self.A_ext, self.R, self.s, *drop)
+            return K.gemm(x2d, self.w, bias=self.bias, a2=ux[:, :self.R], b2=self.Bm, **epi), (ux, xd, drop)
         if drop is not None:
             xd = K.dropout_fwd(x2d.contiguous(), *drop)
         ux = K.gemm(x2d if xd is None else xd, self.A_ext, alpha=self.s, bias=self.u_bias)   # [s x A^T | 1 | 0]
@@ -176,7 +180,10 @@ class LinGroup:
                     dx = K.gemm(dy2d, self.w, b_mn=True, a2=du, b2=self.A, **dx_epi)
                 else:  # the mask sits between x and A: dx = dy W + mask * (du A) / (1 - p), then the epilogue math
                     dx = K.gemm(dy2d, self.w, b_mn=True)
-                    K.dropout_bwd_add(K.gemm(du, self.A, b_mn=True), dx, *drop)
+                    if self.R in (16, 32, 48) and self.K % 8 == 0:
+                        K.lora_dropout_bwd(du, self.A, dx, *drop)      # du A never exists in memory
+                    else:
+                        K.dropout_bwd_add(K.gemm(du, self.A, b_mn=True), dx, *drop)
                     if dx_epi.get("act_grad"):
                         dx = K.act_bwd(dx, dx_epi["aux_in"], dx_epi["act"])
                     elif dx_epi:

@@ -1,6 +1,7 @@
 // genhancer_b200 -- HBM-bound flow-matching kernels (128-bit loads, warp-shuffle reductions).
 #include "common.cuh"
 #include "internal.h"
+#include "philox.cuh"
 
 namespace gh {
 
@@ -91,17 +92,6 @@ __global__ void __launch_bounds__(256) batched_copy_kernel(const gh_copy_desc* _
 // Philox-4x32-10 keyed by (seed, call offset): the backward regenerates the mask instead of storing it.
 // Algorithmic bytes / element: fwd 2 + 2, bwd 2 + 2 + 2.
 // ----------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
-  }
-  return c;
-}
 // One thread = 8 consecutive elements (one 16-byte access) = ONE Philox block: each element takes 16 of its 128 random
 // bits (keep iff bits >= p * 2^16: the drop probability is quantised to 1/65536, 0.1 -> 0.100006).  The first version
 // spent a whole Philox block and an 8-byte access per 4 elements and ran at 2.9 TB/s, compute-bound on the ten

@@ -642,6 +642,33 @@ def dropout_bwd_add(t: torch.Tensor, dx: torch.Tensor, p: float, seed: int, offs
     _count()
 
 
+def lora_dropout_fwd(x: torch.Tensor, a_ext: torch.Tensor, r: int, alpha: float, p: float, seed: int, offset: int,
+                     offset_base: torch.Tensor | None = None):
+    """-> (xd, u): xd = dropout(x) [M,K] and u [M, a_ext.shape[0]] with u[:, :r] = alpha * xd @ a_ext[:r]^T and, when a_ext
+    has 16 more rows than r, u[:, r:] = [1, 0, ...] -- one pass over x (gh_lora_dropout_fwd)."""
+    _ensure(x)
+    assert x.dtype == BF16 and x.is_contiguous() and x.dim() == 2 and a_ext.dtype == BF16 and a_ext.is_contiguous()
+    M, Kd = x.shape
+    rw = a_ext.shape[0]
+    xd = torch.empty_like(x)
+    u = torch.empty(M, rw, dtype=BF16, device=x.device)
+    check(_lib.lib().gh_lora_dropout_fwd(x.data_ptr(), xd.data_ptr(), a_ext.data_ptr(), u.data_ptr(), M, Kd, r, rw - r, rw,
+                                         float(alpha), float(p), int(seed), int(offset), _p(offset_base), _stream()))
+    _count()
+    return xd, u
+
+
+def lora_dropout_bwd(du: torch.Tensor, a: torch.Tensor, dx: torch.Tensor, p: float, seed: int, offset: int,
+                     offset_base: torch.Tensor | None = None) -> None:
+    """dx += mask(seed, offset) * (du @ a) / (1 - p), in place; du [M,R] (unit inner stride), a [R,K] contiguous."""
+    _ensure(du)
+    assert du.dtype == BF16 and a.dtype == BF16 and dx.dtype == BF16 and a.is_contiguous() and dx.is_contiguous()
+    assert du.dim() == 2 and du.stride(1) == 1 and dx.dim() == 2 and dx.shape == (du.shape[0], a.shape[1]) and du.shape[1] == a.shape[0]
+    check(_lib.lib().gh_lora_dropout_bwd(du.data_ptr(), a.data_ptr(), dx.data_ptr(), dx.shape[0], dx.shape[1], a.shape[0],
+                                         du.stride(0), float(p), int(seed), int(offset), _p(offset_base), _stream()))
+    _count()
+
+
 class CopyTable:
     """A device-resident table of ``gh_copy_desc`` built once (pointers are stable: parameters and gradients live in
     the flat buffers of ``optim.flatten``); ``run()`` is ONE launch for all of them."""

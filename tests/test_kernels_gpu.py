@@ -37,6 +37,14 @@ def test_norm_rope_attention_kernels(group):
     _run("tools.gpu_selftest2", [group])
 
 
+@pytest.mark.parametrize("shape", [(23328, 1152, 48, 16), (2000, 4304, 16, 16), (1000, 136, 16, 16), (33, 72, 32, 0), (32, 1152, 16, 16)])
+def test_fused_lora_dropout_kernels_match_the_unfused_pair(shape):
+    """gh_lora_dropout_fwd / _bwd (mask applied in registers around a warp-level MMA) against dropout kernel + skinny GEMM:
+    the SAME mask bit for bit, u and dx to bf16 precision, the ones column of the bias-gradient trick."""
+    from tools import lora_fused_check
+    assert lora_fused_check.case(*shape)
+
+
 def test_fm_interp_is_bit_exact_and_loss_matches():
     from genhancer_b200 import kernels as K
     g = torch.Generator(device="cuda").manual_seed(3)

@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/../genhancer_b200/csrc"
 mkdir -p build_ab
-for f in api gemm_sm100 conv_sm100 patch_embed_sm100 attn_sm100 elementwise norm vision optim; do
+for f in api gemm_sm100 conv_sm100 patch_embed_sm100 attn_sm100 elementwise lora_fused norm vision optim; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wall,-Wno-unused-function \
     --expt-relaxed-constexpr "$@" -c $f.cu -o build_ab/$f.o &
 done
