@@ -180,7 +180,15 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
                             a->d_batch_rows >= a->M),
              GH_ERR_UNSUPPORTED, "gh_gemm_bf16: batched mode takes no second operand pair, split-K or gate, and needs "
                                  "d_batch_rows >= M");
-  const TileChoice tc = pick_tile(a->M, a->N, batch);
+  TileChoice tc = pick_tile(a->M, a->N, batch);
+  if (a->k_splits != 0) {
+    // split-K = a skinny output reduced over every token (LoRA wgrads): the kernel streams one big operand once and is
+    // HBM-bound, so the tile that counts is the one with the WIDEST boxes of that operand (longer DRAM bursts, fewer MMA
+    // instructions per byte -- an N = 64 MMA costs what an N = 128 one costs): 256-row pair tiles when the big operand is A
+    // (dB = dY^T u: M = out features), 256-column tiles when it is B (dA = du^T x: N = in features).
+    if (a->M >= 256 && a->N <= 128) tc = TileChoice{128, true};
+    else if (a->M <= 128 && a->N >= 256) tc = TileChoice{256, false};
+  }
   const int bn = tc.bn;
   GemmParams p{};
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -218,8 +226,9 @@ extern "C" int gh_gemm_bf16(const gh_gemm_args* a, void* stream) {
     GH_REQUIRE(a->d_dtype == GH_F32 && a->K2 == 0 && !a->bias && a->act == 0 && !a->act_grad && !a->gate && !a->residual &&
                    !a->aux_out,
                GH_ERR_UNSUPPORTED, "gh_gemm_bf16: split-K adds bare partial products into an fp32 D (no epilogue options)");
-    const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
-    int s = a->k_splits > 0 ? a->k_splits : num_sms() / (tiles_mn > 0 ? tiles_mn : 1);   // < 0: fill the machine
+    const int tiles_mn = (tc.pair ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks) * p.num_n_blocks;
+    const int workers = tc.pair ? num_sms() / 2 : num_sms();
+    int s = a->k_splits > 0 ? a->k_splits : workers / (tiles_mn > 0 ? tiles_mn : 1);   // < 0: fill the machine
     if (s > p.num_k_blocks / 4) s = p.num_k_blocks / 4;                                 // >= 4 k blocks per slice
     if (s > 64) s = 64;
     if (s < 1) s = 1;
