@@ -138,6 +138,8 @@ _inited_devices: set[int] = set()
 
 def _declare(lib):
     for name, argtypes in SIGNATURES.items():
+        if os.environ.get("GH_LIB_PATH") and not hasattr(lib, name):
+            continue   # an A/B build of an OLDER source (same-box comparisons): entry points added since are absent
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = (C.c_char_p if name == "gh_last_error" else C.c_int64 if name.endswith(("_ws_bytes", "_workspace_bytes")) else C.c_int)

@@ -34,6 +34,10 @@ from ..kernels import ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, BF16, F32
 # patch-embed conv as ONE implicit-GEMM kernel (gh_patch_embed_fwd: the operand tile is gathered from the image into
 # the MMA's shared-memory layout); GH_PATCH_IMPLICIT=0 selects the older gather-to-HBM + plain GEMM pair
 IMPLICIT_PATCH_EMBED = os.environ.get("GH_PATCH_IMPLICIT", "1") != "0"
+# A/B switches of the round-2 LoRA work (profiles/r02_same_box_ab.txt): the fused dropout kernels of csrc/lora_fused.cu, and
+# the bias gradient as a ones column of u
+LORA_FUSED = os.environ.get("GH_LORA_FUSED", "1") != "0"
+LORA_ONES_COLUMN = os.environ.get("GH_LORA_ONES", "1") != "0"
 
 
 def _alias_f32(t: torch.Tensor) -> torch.Tensor:
@@ -68,7 +72,7 @@ class LinGroup:
         # u gets RX extra columns, the first of them a constant one (the u GEMM's "bias" on a zero row of A), so the wgrad
         # GEMM's output is [dB | db | 0]: no separate pass over dy (it was 145 column-sum launches, 7.4 ms of the SigLIP
         # stage-2 step).  An MMA with N = 32 costs what N = 16 costs.
-        self.RX = 16 if (self.R and any(self.train_bias)) else 0
+        self.RX = 16 if (self.R and any(self.train_bias) and LORA_ONES_COLUMN) else 0
         self.A_ext = torch.zeros(self.R + self.RX, self.K, dtype=BF16, device=dev) if self.R else None
         self.A = self.A_ext[:self.R] if self.R else None
         self.u_bias = None
@@ -160,7 +164,7 @@ class LinGroup:
         if not self.R:
             return K.gemm(x2d, self.w, bias=self.bias, **epi), None
         xd = None
-        if drop is not None and self.R in (16, 32, 48) and self.K % 8 == 0:
+        if drop is not None and LORA_FUSED and self.R in (16, 32, 48) and self.K % 8 == 0:
             # the mask sits between x and A: dropout and the skinny product in ONE pass over x (csrc/lora_fused.cu)
             xd, ux = K.lora_dropout_fwd(x2d.contiguous(), self.A_ext, self.R, self.s, *drop)
             return K.gemm(x2d, self.w, bias=self.bias, a2=ux[:, :self.R], b2=self.Bm, **epi), (ux, xd, drop)
@@ -180,7 +184,7 @@ class LinGroup:
                     dx = K.gemm(dy2d, self.w, b_mn=True, a2=du, b2=self.A, **dx_epi)
                 else:  # the mask sits between x and A: dx = dy W + mask * (du A) / (1 - p), then the epilogue math
                     dx = K.gemm(dy2d, self.w, b_mn=True)
-                    if self.R in (16, 32, 48) and self.K % 8 == 0:
+                    if LORA_FUSED and self.R in (16, 32, 48) and self.K % 8 == 0:
                         K.lora_dropout_bwd(du, self.A, dx, *drop)      # du A never exists in memory
                     else:
                         K.dropout_bwd_add(K.gemm(du, self.A, b_mn=True), dx, *drop)
