@@ -45,6 +45,9 @@ struct AttnFwdParams {
   float* lse2;       // [B, H, Lq]  log2-domain logsumexp of the scaled scores
 };
 
+#ifndef GH_FWD64_KSTAGES
+#define GH_FWD64_KSTAGES 1
+#endif
 template <int D>
 struct AttnFwdCfg {
   static constexpr int Q_BYTES = ATT_BQ * D * 2;
@@ -52,8 +55,8 @@ struct AttnFwdCfg {
   static constexpr int V_BYTES = ATT_BKV * D * 2;
   static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = Q_BYTES;                 // 2 stages
-  static constexpr int OFF_V = OFF_K + 2 * K_BYTES;     // 1 stage
+  static constexpr int OFF_K = Q_BYTES;                 // K_STAGES stages (defined below)
+  static constexpr int OFF_V = OFF_K + (D == 64 ? GH_FWD64_KSTAGES : 2) * K_BYTES;     // 1 stage
   static constexpr int OFF_P = OFF_V + V_BYTES;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
@@ -71,7 +74,10 @@ struct AttnFwdCfg {
   static constexpr int S_BUFS = LEAN64 ? 1 : 2;
   static constexpr int TMEM_COLS = LEAN64 ? 128 : 256;
   static constexpr int TM_S = 0, TM_O = LEAN64 ? 64 : 128;
-  static constexpr int CTAS_PER_SM = LEAN64 ? 3 : 2;
+  // D = 64 with ONE K stage (K_{j+1} is requested when S_j has retired, i.e. during softmax_j): 48 KB of shared memory and
+  // 128 TMEM columns per CTA -> FOUR CTAs per SM (A/B: -DGH_FWD64_KSTAGES=2 is the three-CTA form)
+  static constexpr int K_STAGES = D == 64 ? GH_FWD64_KSTAGES : 2;
+  static constexpr int CTAS_PER_SM = LEAN64 ? (K_STAGES == 1 ? 4 : 3) : 2;
 };
 
 
@@ -176,10 +182,10 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const uint64_t vdesc = umma_desc_base(8192u, 1024u);    // V as MN-major B operand
       auto load_k = [&](int j) {
         if (elect_one()) {
-          uint8_t* dst = sK + (j & 1) * Cfg::K_BYTES;
-          mbar_arrive_expect_tx(&bar_k[j & 1], Cfg::K_BYTES);
+          uint8_t* dst = sK + (j % Cfg::K_STAGES) * Cfg::K_BYTES;
+          mbar_arrive_expect_tx(&bar_k[j % Cfg::K_STAGES], Cfg::K_BYTES);
   #pragma unroll
-          for (int c = 0; c < DC; ++c) tma_load_4d(dst + c * 8192, &tm_k, &bar_k[j & 1], c * 64, j * ATT_BKV, h, b);
+          for (int c = 0; c < DC; ++c) tma_load_4d(dst + c * 8192, &tm_k, &bar_k[j % Cfg::K_STAGES], c * 64, j * ATT_BKV, h, b);
         }
       };
       auto load_v = [&](int j) {
@@ -191,7 +197,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       };
       auto issue_s = [&](int j) {
         if (elect_one()) {
-          const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + (j & 1) * Cfg::K_BYTES);
+          const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + (j % Cfg::K_STAGES) * Cfg::K_BYTES);
           mma_over_head_dim<D, 16384, 8192>(ksteps, tmem + Cfg::TM_S + (Cfg::S_BUFS == 2 ? (j & 1) * ATT_BKV : 0), kdesc, aQ, aK,
                                             idesc_s);
           umma_commit(&bar_s[j & 1]);
@@ -204,22 +210,26 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
       load_k(0);
       load_v(0);
-      if (nkv > 1) load_k(1);
+      if (Cfg::K_STAGES == 2 && nkv > 1) load_k(1);
       mbar_wait(bar_q, 0);
       mbar_wait(&bar_k[0], 0);
       tc_fence_after();
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
+        if (Cfg::K_STAGES == 1 && j + 1 < nkv) {
+          mbar_wait(&bar_s[j & 1], (j >> 1) & 1);   // S_j retired: the one K buffer is free (softmax_j runs meanwhile)
+          load_k(j + 1);
+        }
         if (Cfg::S_BUFS == 2 && j + 1 < nkv) {
           // S buffer (j+1)&1 was last read by softmax_{j-1}, which arrived on bar_p before we got here
-          mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(&bar_k[(j + 1) % Cfg::K_STAGES], ((j + 1) / Cfg::K_STAGES) & 1);
           tc_fence_after();
           issue_s(j + 1);
         }
         mbar_wait(bar_p, j & 1);  // P_j is in smem (and O has been rescaled if needed); softmax_j has read S_j
         if (Cfg::S_BUFS == 1 && j + 1 < nkv) {
           // single S buffer: S_{j+1} may overwrite S_j now; issued BEFORE PV_j so that softmax_{j+1} starts earlier
-          mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(&bar_k[(j + 1) % Cfg::K_STAGES], ((j + 1) / Cfg::K_STAGES) & 1);
           tc_fence_after();
           issue_s(j + 1);
         }
@@ -230,7 +240,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           mma_group<4, 0, 32, 0, 2048>(tmem + Cfg::TM_O, kdesc, aP, vdesc, aV, idesc_o, j != 0 ? 1u : 0u);
           umma_commit(bar_o);
         }
-        if (j + 2 < nkv) load_k(j + 2);  // K buffer j&1 is free: S_j completed before softmax_j started
+        if (Cfg::K_STAGES == 2 && j + 2 < nkv) load_k(j + 2);  // K buffer j&1 is free: S_j completed before softmax_j started
         if (j + 1 < nkv) {
           mbar_wait(bar_o, j & 1);       // PV_j done -> V (single buffer) and P are free
           load_v(j + 1);
