@@ -423,6 +423,7 @@ constexpr int ATT_BWD_CPT = 64 / ATT_BWD_SPLIT;        // columns per thread
 constexpr int ATT_BWD_CW = 4 * ATT_BWD_SPLIT;          // compute warps (also the index of the control warp)
 constexpr int ATT_BWD_THREADS = 32 * (ATT_BWD_CW + 1);
 
+#ifdef GH_ATTN_BWD_V1   // the first form of the backward (128 x 64 tiles, every operand in shared memory): A/B builds only
 template <int D>
 struct AttnBwdKVCfg {
   static constexpr int KV_BYTES = 128 * D * 2;  // K_j or V_j (resident)
@@ -876,9 +877,13 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+#endif  // GH_ATTN_BWD_V1
+
 }  // namespace gh
 #include "attn_bwd2.cuh"
+#ifdef GH_ATTN_FWD_V2
 #include "attn_fwd2.cuh"
+#endif
 namespace gh {
 
 // 4-D map over [b, h, l, d] with arbitrary (16-byte multiple) strides; box = 64 x box_rows x 1 x 1
@@ -901,6 +906,7 @@ int attn_init() {
                                      AttnFwdCfg<64>::SMEM_BYTES));
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnFwdCfg<128>::SMEM_BYTES));
+#ifdef GH_ATTN_BWD_V1
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnBwdKVCfg<64>::SMEM_BYTES));
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -909,10 +915,13 @@ int attn_init() {
                                      AttnBwdQCfg<64>::SMEM_BYTES));
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnBwdQCfg<128>::SMEM_BYTES));
+#endif
+#ifdef GH_ATTN_FWD_V2
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_fwd2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnFwd2Cfg<64>::SMEM_BYTES));
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_fwd2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnFwd2Cfg<128>::SMEM_BYTES));
+#endif
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnBwdKV2Cfg<64>::SMEM_BYTES));
   GH_CHECK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1061,7 +1070,7 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
     GH_CHECK_CUDA(cudaGetLastError());
     return GH_OK;
   }
-#endif
+#else   // GH_ATTN_BWD_V1
   {
     CUtensorMap mk_, mv, mq, mdo;
     if (int e = make_qkv_map(&mk_, k, B, H, Lk, D, 128)) return e;
@@ -1089,4 +1098,5 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
     GH_CHECK_CUDA(cudaGetLastError());
   }
   return GH_OK;
+#endif
 }

@@ -294,7 +294,9 @@ int gh_flash_attn_fwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh
                       int32_t Lq, int32_t Lk, int32_t D, int32_t d_valid, float scale, const gh_attn_out* o, float* lse2,
                       void* stream);
 /* Backward of the above (autograd of math.py:9 / modeling_clip.py:319-331): three launches --
- * prep (delta = rowsum(dO*O), dO gathered head-major), dK/dV pass, dQ pass (S and dP recomputed; no atomics).
+ * prep (delta = rowsum(dO*O), dO gathered head-major), dK/dV pass, dQ pass (S and dP recomputed; no atomics, so the
+ * result is bit-reproducible).  128 x 128 score tiles; P^T / dS^T / dS reach the accumulating MMAs through TMEM; dq/dk/dv
+ * leave through bulk tensor stores (csrc/attn_bwd2.cuh).
  * o / d_o are token-major with the same two-segment split as the forward output; dq/dk/dv are written at
  * [b,h,l,:] = ptr + b*batch_stride + h*head_stride + l*row_stride.
  * Workspaces: ws_do_headmajor bf16 [B,H,Lq,D], ws_delta fp32 [B,H,Lq]. */
@@ -302,8 +304,9 @@ int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* k, const gh
                       const gh_attn_out* d_o, const float* lse2, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
                       int32_t D, int32_t d_valid, float scale, const gh_attn_tensor* dq, const gh_attn_tensor* dk,
                       const gh_attn_tensor* dv, void* ws_do_headmajor, float* ws_delta, void* stream);
-/* Bring-up aid (like gh_debug_gemm_prof): a device buffer of 16 int64 that CTA (0,0,0) of the dK/dV kernel fills with
- * cycle counters of its pipeline phases; NULL (the default) switches it off.  Process-global, not for production. */
+/* Bring-up aid (like gh_debug_gemm_prof): a device buffer of 16 int64 that CTA (0,0,0) of the FIRST-FORM dK/dV kernel
+ * (A/B builds with -DGH_ATTN_BWD_V1; the product kernels of attn_bwd2.cuh carry no counters) fills with cycle counters of its
+ * pipeline phases; NULL (the default) switches it off.  Process-global, not for production. */
 int gh_debug_attn_prof(void* device_buf);
 /* bytes of the two workspaces of gh_flash_attn_bwd: [0] = ws_do_headmajor, [1] = ws_delta */
 int64_t gh_flash_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t Lq, int32_t D, int32_t which);
