@@ -384,33 +384,38 @@ struct AttnBwdParams {
   int64_t dq_bs, dq_hs, dq_rs, dk_bs, dk_hs, dk_rs, dv_bs, dv_hs, dv_rs;
 };
 
+// One lane = 8 consecutive head lanes (16 bytes) of one (token, head) row: D / 8 lanes per row, 256 / D rows per warp.  (The first
+// version gave a whole warp to a row -- 8-byte accesses for D = 128, 4-byte for D = 64 -- and was issue-bound at 2.6-3.7 TB/s.)
 template <int D>
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(SegOut o, SegOut dout, int B, int H, int L,
                                                             float* __restrict__ delta, bf16* __restrict__ do_hm) {
-  constexpr int E = D / 32;  // elements per lane (4 or 2)
+  constexpr int LPR = D / 8;          // lanes per row (16 or 8)
+  constexpr int RPW = 32 / LPR;       // rows per warp
   const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
   const int64_t wid = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (wid >= static_cast<int64_t>(B) * L * H) return;
-  const int h = static_cast<int>(wid % H);
-  const int64_t tok = wid / H;
-  const int l = static_cast<int>(tok % L), b = static_cast<int>(tok / L);
-  const bf16* po = o.row(b, l) + h * D + lane * E;
-  const bf16* pd = dout.row(b, l) + h * D + lane * E;
-  bf16* dst = do_hm + ((static_cast<int64_t>(b) * H + h) * L + l) * D + lane * E;
+  const int64_t rid = wid * RPW + lane / LPR;                     // (b, l, h) row, h fastest
+  const bool ok = rid < static_cast<int64_t>(B) * L * H;
   float acc = 0.f;
-  if (E == 4) {
-    const uint2 a = *reinterpret_cast<const uint2*>(po), g = *reinterpret_cast<const uint2*>(pd);
-    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
-    acc = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y;
-    *reinterpret_cast<uint2*>(dst) = g;
-  } else {
-    const uint32_t a = *reinterpret_cast<const uint32_t*>(po), g = *reinterpret_cast<const uint32_t*>(pd);
-    const float2 a0 = unpack_bf16x2(a), g0 = unpack_bf16x2(g);
-    acc = a0.x * g0.x + a0.y * g0.y;
-    *reinterpret_cast<uint32_t*>(dst) = g;
+  int h = 0, l = 0, b = 0;
+  if (ok) {
+    h = static_cast<int>(rid % H);
+    const int64_t tok = rid / H;
+    l = static_cast<int>(tok % L);
+    b = static_cast<int>(tok / L);
+    const uint4 a = *reinterpret_cast<const uint4*>(o.row(b, l) + h * D + sub * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(dout.row(b, l) + h * D + sub * 8);
+    *reinterpret_cast<uint4*>(do_hm + ((static_cast<int64_t>(b) * H + h) * L + l) * D + sub * 8) = g;
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 x = unpack_bf16x2(aw[q]), y = unpack_bf16x2(gw[q]);
+      acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) delta[(static_cast<int64_t>(b) * H + h) * L + l] = acc;
+#pragma unroll
+  for (int off = LPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (ok && sub == 0) delta[(static_cast<int64_t>(b) * H + h) * L + l] = acc;
 }
 
 // Backward kernels: 16 compute warps (thread = a QUARTER of a score row: 16 columns) + 1 control warp.  With one CTA per
@@ -1020,17 +1025,21 @@ extern "C" int gh_flash_attn_bwd(const gh_attn_tensor* q, const gh_attn_tensor* 
   GH_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, GH_ERR_BAD_SHAPE, "gh_flash_attn_bwd: bad shape");
   if (B == 0 || Lq == 0) return GH_OK;
   GH_REQUIRE(aligned16(ws_do_headmajor), GH_ERR_ALIGN, "gh_flash_attn_bwd: workspace must be 16B aligned");
+  for (const gh_attn_out* t : {o, d_o})   // (the prep pass reads o / d_o with 16-byte accesses)
+    GH_REQUIRE(t->n_split >= 0 && t->n_split <= Lq && t->seg1_row_stride % 8 == 0 && t->seg1_batch_stride % 8 == 0 && aligned16(t->seg1) &&
+                   (t->n_split == 0 || (t->seg0 && t->seg0_row_stride % 8 == 0 && t->seg0_batch_stride % 8 == 0 && aligned16(t->seg0))),
+               GH_ERR_ALIGN, "gh_flash_attn_bwd: o / d_o segments must be 16B aligned with strides that are multiples of 8 elements");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SegOut so, sdo;
   seg_from(o, &so);
   seg_from(d_o, &sdo);
   const int64_t n = static_cast<int64_t>(B) * Lq * H;
   if (D == 64)
-    attn_bwd_prep_kernel<64><<<static_cast<int>((n + 7) / 8), 256, 0, s>>>(so, sdo, B, H, Lq, ws_delta,
-                                                                          static_cast<bf16*>(ws_do_headmajor));
+    attn_bwd_prep_kernel<64><<<static_cast<int>((n + 31) / 32), 256, 0, s>>>(so, sdo, B, H, Lq, ws_delta,
+                                                                            static_cast<bf16*>(ws_do_headmajor));
   else
-    attn_bwd_prep_kernel<128><<<static_cast<int>((n + 7) / 8), 256, 0, s>>>(so, sdo, B, H, Lq, ws_delta,
-                                                                           static_cast<bf16*>(ws_do_headmajor));
+    attn_bwd_prep_kernel<128><<<static_cast<int>((n + 15) / 16), 256, 0, s>>>(so, sdo, B, H, Lq, ws_delta,
+                                                                             static_cast<bf16*>(ws_do_headmajor));
   GH_CHECK_CUDA(cudaGetLastError());
 
   gh_attn_tensor dot;
