@@ -106,7 +106,7 @@ SIGNATURES: dict[str, list] = {
     "gh_dropout_fwd": [_vp, _vp, _i64, _f32, C.c_uint64, C.c_uint64, _vp, _vp],
     "gh_dropout_bwd_add": [_vp, _vp, _i64, _f32, C.c_uint64, C.c_uint64, _vp, _vp],
     "gh_lora_dropout_fwd": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _f32, _f32, C.c_uint64, C.c_uint64, _vp, _vp],
-    "gh_lora_dropout_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _f32, C.c_uint64, C.c_uint64, _vp, _vp],
+    "gh_lora_dropout_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _f32, C.c_uint64, C.c_uint64, _vp, _vp, _i32, _vp],
     "gh_flash_attn_fwd": [_at, _at, _at, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _ao, _vp, _vp],
     "gh_debug_attn_prof": [_vp],
     "gh_flash_attn_bwd_workspace_bytes": [_i32, _i32, _i32, _i32, _i32],

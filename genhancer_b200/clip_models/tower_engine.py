@@ -184,14 +184,21 @@ class LinGroup:
                     dx = K.gemm(dy2d, self.w, b_mn=True, a2=du, b2=self.A, **dx_epi)
                 else:  # the mask sits between x and A: dx = dy W + mask * (du A) / (1 - p), then the epilogue math
                     dx = K.gemm(dy2d, self.w, b_mn=True)
-                    if LORA_FUSED and self.R in (16, 32, 48) and self.K % 8 == 0:
-                        K.lora_dropout_bwd(du, self.A, dx, *drop)      # du A never exists in memory
+                    fused = LORA_FUSED and self.R in (16, 32, 48) and self.K % 8 == 0
+                    ag = bool(dx_epi.get("act_grad"))
+                    if dx_epi and not ag:
+                        raise NotImplementedError(f"LoRA dropout with dgrad epilogue {sorted(dx_epi)}")
+                    if fused:      # du A never exists in memory; act'(pre) applied in the same read-modify-write
+                        pre = dx_epi["aux_in"] if ag else None
+                        if pre is not None and not (pre.is_contiguous() and pre.shape == dx.shape):
+                            pre = None
+                        K.lora_dropout_bwd(du, self.A, dx, *drop, act_pre=pre, act=dx_epi["act"] if pre is not None else ACT_NONE)
+                        if ag and pre is None:
+                            dx = K.act_bwd(dx, dx_epi["aux_in"], dx_epi["act"])
                     else:
                         K.dropout_bwd_add(K.gemm(du, self.A, b_mn=True), dx, *drop)
-                    if dx_epi.get("act_grad"):
-                        dx = K.act_bwd(dx, dx_epi["aux_in"], dx_epi["act"])
-                    elif dx_epi:
-                        raise NotImplementedError(f"LoRA dropout with dgrad epilogue {sorted(dx_epi)}")
+                        if ag:
+                            dx = K.act_bwd(dx, dx_epi["aux_in"], dx_epi["act"])
             # skinny outputs reduced over every token of the batch: split-K, partial products added into the staging
             # (which is all-zero between backward calls, see TowerEngine._scatter_grads)
             K.gemm(du, x2d if xd is None else xd, a_mn=True, b_mn=True, out=self.gA, k_splits=-1)

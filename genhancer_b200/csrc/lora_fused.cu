@@ -52,6 +52,8 @@ struct LoraDropParams {
   uint2 key;
   unsigned long long offset;
   const unsigned long long* offset_base;
+  const __nv_bfloat16* pre;   // backward only, may be NULL: dx = (dx + drop'(du A)) * act'(pre)  -- the dgrad through an MLP's
+  int act;                    // activation (fc2's input gradient), which the masked term keeps out of the GEMM's epilogue
 };
 
 // ----------------------------------------------------------------------------------------------------------
@@ -193,6 +195,11 @@ __global__ void __launch_bounds__(256) lora_dropout_bwd_kernel(const bf16* __res
     const int c8 = c0 + cb + t * 8;
     if (c0 + cb >= p.K) break;
     const bool okc = c8 < p.K;
+    uint4 pa = make_uint4(0u, 0u, 0u, 0u), pb = pa;
+    if (p.pre != nullptr) {   // requested before the MMAs and the Philox rounds
+      if (oka && okc) pa = *reinterpret_cast<const uint4*>(p.pre + ra * K + c8);
+      if (okb && okc) pb = *reinterpret_cast<const uint4*>(p.pre + rb * K + c8);
+    }
     float acc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -210,15 +217,30 @@ __global__ void __launch_bounds__(256) lora_dropout_bwd_kernel(const bf16* __res
       const uint4 rnd = dropout_bits((r * K + c8) >> 3, off, p.key);
       const uint4 d = half ? db[st] : da[st];
       const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w}, dw[4] = {d.x, d.y, d.z, d.w};
-      uint32_t ow[4];
+      float v[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 c = unpack_bf16x2(dw[j]);
         const float v0 = acc[j][2 * half], v1 = acc[j][2 * half + 1];
-        ow[j] = pack_bf16x2(c.x + ((rw[j] & 0xffffu) >= p.thresh16 ? v0 * p.inv_keep : 0.f),
-                            c.y + ((rw[j] >> 16) >= p.thresh16 ? v1 * p.inv_keep : 0.f));
+        v[2 * j] = c.x + ((rw[j] & 0xffffu) >= p.thresh16 ? v0 * p.inv_keep : 0.f);
+        v[2 * j + 1] = c.y + ((rw[j] >> 16) >= p.thresh16 ? v1 * p.inv_keep : 0.f);
       }
-      *reinterpret_cast<uint4*>(dx + r * K + c8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      if (p.pre != nullptr) {
+        // (as the separate pass did: the sum is rounded to bf16 before it meets act')
+        const uint4 pr = half ? pb : pa;
+        const uint32_t pw[4] = {pr.x, pr.y, pr.z, pr.w};
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 xx = unpack_bf16x2(pw[j]);
+          x[2 * j] = xx.x; x[2 * j + 1] = xx.y;
+          v[2 * j] = __bfloat162float(__float2bfloat16(v[2 * j]));
+          v[2 * j + 1] = __bfloat162float(__float2bfloat16(v[2 * j + 1]));
+        }
+        act_bwd_mul8(p.act, x, v);
+      }
+      *reinterpret_cast<uint4*>(dx + r * K + c8) =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
   }
 }
@@ -268,11 +290,14 @@ extern "C" int gh_lora_dropout_fwd(const void* x_bf16, void* xd_bf16, const void
 
 extern "C" int gh_lora_dropout_bwd(const void* du_bf16, const void* a_bf16, void* dx_bf16, int32_t M, int32_t K, int32_t R,
                                    int64_t ldu, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_base,
-                                   void* stream) {
+                                   const void* act_pre_bf16, int32_t act, void* stream) {
   GH_REQUIRE(du_bf16 && a_bf16 && dx_bf16, GH_ERR_NULL, "gh_lora_dropout_bwd: NULL pointer");
   GH_REQUIRE(aligned16(du_bf16) && aligned16(a_bf16) && aligned16(dx_bf16), GH_ERR_ALIGN, "gh_lora_dropout_bwd: 16-byte alignment");
   LoraDropParams q{};
   if (int e = fill_params(q, M, K, R, 0, ldu, 1.f, p, seed, offset, offset_base, "gh_lora_dropout_bwd")) return e;
+  GH_REQUIRE(!act_pre_bf16 || aligned16(act_pre_bf16), GH_ERR_ALIGN, "gh_lora_dropout_bwd: act_pre must be 16-byte aligned");
+  q.pre = static_cast<const __nv_bfloat16*>(act_pre_bf16);
+  q.act = act;
   if (M == 0) return GH_OK;
   const dim3 grid((M + 127) / 128, (K + 127) / 128);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

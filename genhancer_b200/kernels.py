@@ -659,13 +659,16 @@ def lora_dropout_fwd(x: torch.Tensor, a_ext: torch.Tensor, r: int, alpha: float,
 
 
 def lora_dropout_bwd(du: torch.Tensor, a: torch.Tensor, dx: torch.Tensor, p: float, seed: int, offset: int,
-                     offset_base: torch.Tensor | None = None) -> None:
-    """dx += mask(seed, offset) * (du @ a) / (1 - p), in place; du [M,R] (unit inner stride), a [R,K] contiguous."""
+                     offset_base: torch.Tensor | None = None, act_pre: torch.Tensor | None = None, act: int = ACT_NONE) -> None:
+    """dx += mask(seed, offset) * (du @ a) / (1 - p), in place; du [M,R] (unit inner stride), a [R,K] contiguous.
+    ``act_pre`` ([M,K] bf16, contiguous): the sum is then multiplied by act'(act_pre) (dgrad through an MLP activation)."""
     _ensure(du)
     assert du.dtype == BF16 and a.dtype == BF16 and dx.dtype == BF16 and a.is_contiguous() and dx.is_contiguous()
     assert du.dim() == 2 and du.stride(1) == 1 and dx.dim() == 2 and dx.shape == (du.shape[0], a.shape[1]) and du.shape[1] == a.shape[0]
+    assert act_pre is None or (act_pre.dtype == BF16 and act_pre.is_contiguous() and act_pre.shape == dx.shape)
     check(_lib.lib().gh_lora_dropout_bwd(du.data_ptr(), a.data_ptr(), dx.data_ptr(), dx.shape[0], dx.shape[1], a.shape[0],
-                                         du.stride(0), float(p), int(seed), int(offset), _p(offset_base), _stream()))
+                                         du.stride(0), float(p), int(seed), int(offset), _p(offset_base), _p(act_pre),
+                                         int(act), _stream()))
     _count()
 
 

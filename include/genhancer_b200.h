@@ -252,14 +252,17 @@ int gh_batched_copy(const gh_copy_desc* descs_device, int32_t n_desc, int32_t bl
  * backward of that pair, peft/tuners/lora/layer.py Linear.forward):
  *   gh_lora_dropout_fwd : xd = drop(x) [M,K] AND u[:, 0:R] = alpha * xd A^T (A [R,K] bf16 row-major) in one pass over x;
  *                         RX = 16 also writes u[:, R:R+16] = [1, 0, ...] (the bias gradient then rides in the dB GEMM).
- *   gh_lora_dropout_bwd : dx [M,K] += drop'(du [M,R] A): one read-modify-write of dx, the product never exists in memory.
+ *   gh_lora_dropout_bwd : dx [M,K] += drop'(du [M,R] A): one read-modify-write of dx, the product never exists in memory;
+ *                         act_pre != NULL: the result is then multiplied by act'(act_pre) (contiguous [M,K] bf16) -- the
+ *                         dgrad through an MLP's activation, which the masked term keeps out of the GEMM's epilogue.
  * Same mask as gh_dropout_fwd for the same (p, seed, offset, offset_base) on the contiguous [M,K] tensor.  K % 8 == 0,
  * R in {16, 32, 48}, ldu (row pitch of u / du) % 8 == 0. */
 int gh_lora_dropout_fwd(const void* x_bf16, void* xd_bf16, const void* a_bf16, void* u_bf16, int32_t M, int32_t K, int32_t R,
                         int32_t RX, int64_t ldu, float alpha, float p, uint64_t seed, uint64_t offset,
                         const uint64_t* offset_base, void* stream);
 int gh_lora_dropout_bwd(const void* du_bf16, const void* a_bf16, void* dx_bf16, int32_t M, int32_t K, int32_t R, int64_t ldu,
-                        float p, uint64_t seed, uint64_t offset, const uint64_t* offset_base, void* stream);
+                        float p, uint64_t seed, uint64_t offset, const uint64_t* offset_base, const void* act_pre_bf16,
+                        int32_t act, void* stream);
 int gh_dropout_fwd(const void* x_bf16, void* y_bf16, int64_t numel, float p, uint64_t seed, uint64_t offset,
                    const uint64_t* offset_base, void* stream);
 int gh_dropout_bwd_add(const void* t_bf16, void* dx_bf16, int64_t numel, float p, uint64_t seed, uint64_t offset,

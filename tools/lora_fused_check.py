@@ -49,14 +49,22 @@ def case(M, Kd, R, RX=16, p=0.1):
     dx = dx0.clone()
     K.lora_dropout_bwd(du, a_ext[:R], dx, *drop)
     e_dx = rel(dx, dx_ref)     # (the unfused pair rounds du A to bf16 before the add: agreement to bf16 precision)
+    # the same with the MLP's act' applied in the pass (fc2's input gradient)
+    pre = torch.randn(M, Kd, device=dev, generator=g).to(BF)
+    dxa_ref = dx0.clone()
+    K.dropout_bwd_add(K.gemm(du, a_ext[:R], b_mn=True), dxa_ref, *drop)
+    dxa_ref = K.act_bwd(dxa_ref, pre, K.ACT_GELU_TANH)
+    dxa = dx0.clone()
+    K.lora_dropout_bwd(du, a_ext[:R], dxa, *drop, act_pre=pre, act=K.ACT_GELU_TANH)
+    e_dxa = rel(dxa, dxa_ref)
     t_f_ref = timeit(lambda: K.gemm(K.dropout_fwd(x, *drop), a_ext, alpha=2.0, bias=ub if RX else None))
     t_f = timeit(lambda: K.lora_dropout_fwd(x, a_ext, R, 2.0, *drop))
     t_b_ref = timeit(lambda: K.dropout_bwd_add(K.gemm(du, a_ext[:R], b_mn=True), dx_ref, *drop))
     t_b = timeit(lambda: K.lora_dropout_bwd(du, a_ext[:R], dx, *drop))
-    ok = e_xd == 0 and e_u < 5e-3 and ones_ok and e_dx < 4e-3
+    ok = e_xd == 0 and e_u < 5e-3 and ones_ok and e_dx < 4e-3 and e_dxa < 6e-3
     gb = M * Kd * 2 / 1e9
     print(f"{'PASS' if ok else 'FAIL'} M={M} K={Kd} R={R}+{RX}: xd mismatches {e_xd}, u relerr {e_u:.2e}, ones column {ones_ok}, "
-          f"dx relerr {e_dx:.2e} | fwd {t_f:.0f} us ({2 * gb / t_f * 1e3:.2f} TB/s) vs unfused {t_f_ref:.0f}; "
+          f"dx relerr {e_dx:.2e} (with act' {e_dxa:.2e}) | fwd {t_f:.0f} us ({2 * gb / t_f * 1e3:.2f} TB/s) vs unfused {t_f_ref:.0f}; "
           f"bwd {t_b:.0f} us ({2 * gb / t_b * 1e3:.2f} TB/s) vs unfused {t_b_ref:.0f}")
     return ok
 
