@@ -27,10 +27,18 @@ __global__ void __launch_bounds__(256) fm_interp_kernel(const float4* __restrict
 
 // loss += sum((pred - (x0 - x1))^2) / numel ; dpred = bf16(scale * 2 (pred - (x0-x1)) / numel)
 // algorithmic bytes / element: 2 + 4 + 4 + 2 = 12
-__global__ void __launch_bounds__(256) fm_mse_kernel(const uint2* __restrict__ pred, const float4* __restrict__ x0,
-                                                     const float4* __restrict__ x1, float* __restrict__ loss,
-                                                     uint2* __restrict__ dpred, float gscale, float inv_numel,
-                                                     int64_t n4) {
+// The grid is ONE thread-block cluster (8 CTAs of 1024 threads): every CTA reduces its share in a fixed order, the CTAs'
+// partial sums meet in CTA 0's shared memory (DSMEM) and ONE thread adds their fixed-order sum to the accumulator -- the
+// loss is bit-reproducible.  (The first version let every block atomicAdd its partial: the loss of two identical steps
+// could differ in the last bit with the order the blocks happened to finish in, which a bit-equality test caught.)  The
+// tensor is small (batch x 441 x 64 latents: ~13 MB of traffic), so eight SMs cost ~10 us per step.
+constexpr int FM_MSE_CTAS = 8;
+__global__ void __launch_bounds__(1024) fm_mse_kernel(const uint2* __restrict__ pred, const float4* __restrict__ x0,
+                                                      const float4* __restrict__ x1, float* __restrict__ loss,
+                                                      uint2* __restrict__ dpred, float gscale, float inv_numel,
+                                                      int64_t n4) {
+  __shared__ float part[32];
+  __shared__ float cpart[FM_MSE_CTAS];
   float acc = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -50,13 +58,20 @@ __global__ void __launch_bounds__(256) fm_mse_kernel(const uint2* __restrict__ p
     }
   }
   acc = warp_sum(acc);
-  __shared__ float part[8];
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
-    float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
+    float v = part[threadIdx.x];
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(loss, v * inv_numel);
+    if (threadIdx.x == 0)   // my partial -> slot [rank] of CTA 0
+      st_shared_cluster_u32(mapa_u32(smem_u32(&cpart[cluster_ctarank()]), 0u), __float_as_uint(v));
+  }
+  cluster_sync_all();       // (release / acquire at cluster scope: the remote stores are visible to CTA 0)
+  if (cluster_ctarank() == 0 && threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < FM_MSE_CTAS; ++r) t += cpart[r];
+    atomicAdd(loss, t * inv_numel);   // ONE add per launch
   }
 }
 
@@ -187,11 +202,21 @@ extern "C" int gh_fm_mse_loss_fwdbwd(const void* pred_bf16, const float* x0, con
   GH_REQUIRE(aligned16(x0) && aligned16(x1) && aligned16(pred_bf16) && (!dpred_bf16 || aligned16(dpred_bf16)),
              GH_ERR_ALIGN, "gh_fm_mse_loss_fwdbwd: 16B alignment");
   const int64_t n4 = numel / 4;
-  fm_mse_kernel<<<ew_grid(n4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const uint2*>(pred_bf16), reinterpret_cast<const float4*>(x0),
-      reinterpret_cast<const float4*>(x1), loss_accum, reinterpret_cast<uint2*>(dpred_bf16), grad_scale,
-      1.0f / static_cast<float>(numel), n4);
-  GH_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(FM_MSE_CTAS);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = FM_MSE_CTAS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  GH_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fm_mse_kernel, reinterpret_cast<const uint2*>(pred_bf16),
+                                   reinterpret_cast<const float4*>(x0), reinterpret_cast<const float4*>(x1), loss_accum,
+                                   reinterpret_cast<uint2*>(dpred_bf16), grad_scale, 1.0f / static_cast<float>(numel), n4));
   return GH_OK;
 }
 

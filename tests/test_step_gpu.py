@@ -101,8 +101,11 @@ def test_step_takes_the_decoded_uint8_batch_and_gives_the_same_loss():
     with torch.no_grad():
         l_u8, p_u8 = step(u8, return_parts=True, **draws)
         l_f32, p_f32 = step(K.u8hwc_to_f32chw(u8), return_parts=True, **draws)
-    assert torch.equal(p_u8["x_1"], p_f32["x_1"]) and torch.equal(p_u8["vec"], p_f32["vec"])
-    assert torch.equal(p_u8["pred"], p_f32["pred"]) and l_u8.item() == l_f32.item()
+    diag = {k: (int(torch.isnan(p_u8[k].float()).sum()), int(torch.isnan(p_f32[k].float()).sum()),
+                float((p_u8[k].float() - p_f32[k].float()).abs().max())) for k in ("x_1", "vec", "txt", "x_t", "pred")}
+    print("uint8 vs fp32 path (nan u8, nan f32, max |diff|):", diag, l_u8.item(), l_f32.item())
+    assert torch.equal(p_u8["x_1"], p_f32["x_1"]) and torch.equal(p_u8["vec"], p_f32["vec"]), diag
+    assert torch.equal(p_u8["pred"], p_f32["pred"]) and l_u8.item() == l_f32.item(), diag
 
 
 def test_cfg1_full_size_step_matches_reference():
