@@ -82,19 +82,28 @@ __global__ void __launch_bounds__(256) lora_dropout_fwd_kernel(const bf16* __res
   float acc[NT][4];
 #pragma unroll
   for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-  uint4 va[U], vb[U], na[U], nb[U];
-  auto load = [&](int it, uint4 (&a)[U], uint4 (&b)[U]) {
+  // The LoRA rows ride in the same software pipeline as x when they fit in registers (rank 16: NT = 2): read at their first
+  // use they exposed one L2 round trip per chunk and output tile in front of every MMA pair.
+  constexpr bool PREFETCH_W = NT <= 2;
+  constexpr int NW = PREFETCH_W ? NT : 1;
+  uint4 va[U], vb[U], na[U], nb[U], wa[U][NW], wn[U][NW];
+  auto load = [&](int it, uint4 (&a)[U], uint4 (&b)[U], uint4 (&w)[U][NW]) {
 #pragma unroll
     for (int uu = 0; uu < U; ++uu) {
       const int c8 = (it * U + uu) * 32 + t * 8;
       const bool okc = it < it1 && c8 < p.K;
       a[uu] = (oka && okc) ? *reinterpret_cast<const uint4*>(x + ra * K + c8) : make_uint4(0u, 0u, 0u, 0u);
       b[uu] = (okb && okc) ? *reinterpret_cast<const uint4*>(x + rb * K + c8) : make_uint4(0u, 0u, 0u, 0u);
+      if (PREFETCH_W) {
+#pragma unroll
+        for (int n = 0; n < NW; ++n)
+          w[uu][n] = okc ? __ldg(reinterpret_cast<const uint4*>(A + static_cast<int64_t>(n * 8 + g) * K + c8)) : make_uint4(0u, 0u, 0u, 0u);
+      }
     }
   };
-  load(it0, va, vb);
+  load(it0, va, vb, wa);
   for (int it = it0; it < it1; ++it) {
-    load(it + 1, na, nb);
+    load(it + 1, na, nb, wn);
 #pragma unroll
     for (int uu = 0; uu < U; ++uu) {
       const int c8 = (it * U + uu) * 32 + t * 8;
@@ -110,13 +119,19 @@ __global__ void __launch_bounds__(256) lora_dropout_fwd_kernel(const bf16* __res
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
         // LoRA row n * 8 + g, the same 8 K columns: elements 0-3 feed the first MMA, 4-7 the second
-        const uint4 w = okc ? __ldg(reinterpret_cast<const uint4*>(A + static_cast<int64_t>(n * 8 + g) * K + c8)) : make_uint4(0u, 0u, 0u, 0u);
+        uint4 w;
+        if (PREFETCH_W) w = wa[uu][n < NW ? n : 0];
+        else w = okc ? __ldg(reinterpret_cast<const uint4*>(A + static_cast<int64_t>(n * 8 + g) * K + c8)) : make_uint4(0u, 0u, 0u, 0u);
         mma16816(acc[n], va[uu].x, vb[uu].x, va[uu].y, vb[uu].y, w.x, w.y);
         mma16816(acc[n], va[uu].z, vb[uu].z, va[uu].w, vb[uu].w, w.z, w.w);
       }
     }
 #pragma unroll
-    for (int uu = 0; uu < U; ++uu) { va[uu] = na[uu]; vb[uu] = nb[uu]; }
+    for (int uu = 0; uu < U; ++uu) {
+      va[uu] = na[uu]; vb[uu] = nb[uu];
+#pragma unroll
+      for (int n = 0; n < NW; ++n) wa[uu][n] = wn[uu][n];
+    }
   }
   if (quarter > 0) {
 #pragma unroll
