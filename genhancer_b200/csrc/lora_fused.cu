@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) lora_dropout_fwd_kernel(const bf16* __res
 // Output columns: lane t of a quad owns the 8 consecutive columns t * 8 .. t * 8 + 7 of a 32-column step (one Philox
 // block, one 16-byte read-modify-write): column 2 t' + i of MMA n-tile j is DECLARED to be column t' * 8 + j * 2 + i.
 // ----------------------------------------------------------------------------------------------------------
-template <int KS>
+template <int KS, bool ACT>   // ACT: also multiply by act'(pre) (its own instantiation: the activation code costs ~40 registers)
 __global__ void __launch_bounds__(256) lora_dropout_bwd_kernel(const bf16* __restrict__ du, const bf16* __restrict__ A,
                                                                bf16* __restrict__ dx, const LoraDropParams p) {
   constexpr int R = KS * 16;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) lora_dropout_bwd_kernel(const bf16* __res
     if (c0 + cb >= p.K) break;
     const bool okc = c8 < p.K;
     uint4 pa = make_uint4(0u, 0u, 0u, 0u), pb = pa;
-    if (p.pre != nullptr) {   // requested before the MMAs and the Philox rounds
+    if (ACT) {   // requested before the MMAs and the Philox rounds
       if (oka && okc) pa = *reinterpret_cast<const uint4*>(p.pre + ra * K + c8);
       if (okb && okc) pb = *reinterpret_cast<const uint4*>(p.pre + rb * K + c8);
     }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) lora_dropout_bwd_kernel(const bf16* __res
         v[2 * j] = c.x + ((rw[j] & 0xffffu) >= p.thresh16 ? v0 * p.inv_keep : 0.f);
         v[2 * j + 1] = c.y + ((rw[j] >> 16) >= p.thresh16 ? v1 * p.inv_keep : 0.f);
       }
-      if (p.pre != nullptr) {
+      if (ACT) {
         // (as the separate pass did: the sum is rounded to bf16 before it meets act')
         const uint4 pr = half ? pb : pa;
         const uint32_t pw[4] = {pr.x, pr.y, pr.z, pr.w};
@@ -318,10 +318,18 @@ extern "C" int gh_lora_dropout_bwd(const void* du_bf16, const void* a_bf16, void
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bf16 *du = static_cast<const bf16*>(du_bf16), *a = static_cast<const bf16*>(a_bf16);
   bf16* dx = static_cast<bf16*>(dx_bf16);
-  switch (R) {
-    case 16: lora_dropout_bwd_kernel<1><<<grid, 256, 0, s>>>(du, a, dx, q); break;
-    case 32: lora_dropout_bwd_kernel<2><<<grid, 256, 0, s>>>(du, a, dx, q); break;
-    default: lora_dropout_bwd_kernel<3><<<grid, 256, 0, s>>>(du, a, dx, q); break;
+  if (q.pre != nullptr) {
+    switch (R) {
+      case 16: lora_dropout_bwd_kernel<1, true><<<grid, 256, 0, s>>>(du, a, dx, q); break;
+      case 32: lora_dropout_bwd_kernel<2, true><<<grid, 256, 0, s>>>(du, a, dx, q); break;
+      default: lora_dropout_bwd_kernel<3, true><<<grid, 256, 0, s>>>(du, a, dx, q); break;
+    }
+  } else {
+    switch (R) {
+      case 16: lora_dropout_bwd_kernel<1, false><<<grid, 256, 0, s>>>(du, a, dx, q); break;
+      case 32: lora_dropout_bwd_kernel<2, false><<<grid, 256, 0, s>>>(du, a, dx, q); break;
+      default: lora_dropout_bwd_kernel<3, false><<<grid, 256, 0, s>>>(du, a, dx, q); break;
+    }
   }
   GH_CHECK_CUDA(cudaGetLastError());
   return GH_OK;
